@@ -1,0 +1,135 @@
+/* C-ABI of the B200 PINN residual-loss + gradient engine (libpinn_engine.so).
+ *
+ * Drop-in boundary for the hot path of Cc1-Yy/PINN-based-online-PDE-calculator.
+ * Every entry point cites the reference interface (pinn_app/software.py, "sw:")
+ * it replaces.  Plain pointers and sizes only; no torch / Python types.
+ *
+ * Conventions: functions return 0 on success, non-zero on failure with a
+ * thread-local message in pinn_last_error().  All kernels are enqueued on the
+ * stream set by pinn_engine_set_stream (default: an engine-owned stream); the
+ * only host synchronisation is where a host scalar / host buffer is returned.
+ * The engine never falls back to the CPU: without a CUDA device create() fails.
+ */
+#ifndef PINN_ENGINE_H
+#define PINN_ENGINE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pinn_engine pinn_engine_t;
+
+/* Problem + network description.  Replaces the closures built by
+ * sol_pred_create (sw:207-218), mNN_pred_create (sw:221-234), gov_eqn
+ * (sw:283-297) and loss_create (sw:310-383). */
+typedef struct pinn_spec {
+  int32_t d_in;        /* number of inputs: 1..3 (reference: 2)                        */
+  int32_t feat_mode;   /* 0: affine 2(z-lb)/(ub-lb)-1 per input; 1: reference polar map
+                          [2(r-lb0)/(ub0-lb0)-1, cos t, sin t]  (sw:172-175)            */
+  int32_t n_hidden;    /* hidden layers  (reference kwarg network_size["width"] !)     */
+  int32_t width;       /* units/layer    (reference kwarg network_size["depth"] !)     */
+  int32_t act_first;   /* 0 tanh, 1 sin  (sw:170,178)                                  */
+  int32_t act_hidden;  /* 0 tanh (sw:180-181), 1 sin (extension)                       */
+  float scl, epsil;    /* first-layer scale (sw:178), output scale (sw:215)            */
+  float lb[3], ub[3];  /* domain bounds (sw:705-707)                                   */
+  int32_t n1, n2, mix; /* jet channels of the collocation term: u, first derivatives
+                          wrt inputs 0..n1-1, pure second derivatives wrt inputs
+                          0..n2-1, and (mix) the 0-1 mixed derivative                  */
+  int32_t n_ops;       /* residual bytecode (see csrc/pinn_common.h, PinnOp)           */
+  const int32_t* ops;
+  int32_t n_consts;
+  const float* consts;
+  int32_t n_aux_col;   /* per-point aux columns of the collocation set (source terms)  */
+  int32_t n_bc;        /* boundary/initial-condition groups = data loss terms (sw:334) */
+} pinn_spec_t;
+
+typedef struct pinn_lbfgs_result {
+  int32_t iterations;      /* L-BFGS iterations performed                       */
+  int32_t evaluations;     /* objective evaluations (sw:511 num_objective_evaluations) */
+  int32_t converged;       /* ||g||_inf <= tol                                  */
+  int32_t failed;          /* line search failed                                */
+  double final_loss;
+} pinn_lbfgs_result_t;
+
+/* per-evaluation callback of L-BFGS: loss_info row (sw:485-488) */
+typedef void (*pinn_eval_cb)(const double* loss_info, int32_t n_info, void* user);
+
+const char* pinn_last_error(void);
+int pinn_device_count(void);
+
+/* sol_pred_create + loss_create (sw:207, 310).  Fails when no CUDA device. */
+int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engine_t** out);
+void pinn_engine_destroy(pinn_engine_t* h);
+int pinn_engine_set_stream(pinn_engine_t* h, void* cuda_stream);
+
+/* P = number of parameters in jax.flatten_util.ravel_pytree order (sw:466,502) */
+int64_t pinn_engine_num_params(pinn_engine_t* h);
+/* length of loss_info = 3 + n_bc + 1 (sw:377-378) */
+int32_t pinn_engine_num_loss_info(pinn_engine_t* h);
+/* points per CTA tile / grid size of the collocation kernel (for roofline maths) */
+int32_t pinn_engine_tile_points(pinn_engine_t* h);
+int32_t pinn_engine_launches_per_eval(pinn_engine_t* h);
+
+/* params pytree <-> flat fp32 vector (sw:142-154 layout, sw:466 order) */
+int pinn_engine_set_params(pinn_engine_t* h, const float* flat, int on_device);
+int pinn_engine_get_params(pinn_engine_t* h, float* flat_out, int on_device);
+
+/* the `data` dict of sw:572: x_col [n_col,d_in]; per BC group x_bd[i] [n_bd[i],d_in],
+ * u_bd[i] [n_bd[i]] (per-point targets, sw:557); optional aux_col [n_col,n_aux_col]
+ * and base_col [n_col,K] / base_bd[i] [n_bd[i]] (frozen stage-1 jets, sw:228-232).
+ * Host pointers are copied; device pointers (on_device=1) to x_col/aux_col/base_col
+ * are BORROWED until the next call; BC arrays are always copied (they are small).
+ * Each rank passes ITS shard. */
+int pinn_engine_set_points(pinn_engine_t* h, const float* x_col, int64_t n_col, const float* aux_col,
+                           const float* base_col, int32_t n_bc, const float* const* x_bd,
+                           const float* const* u_bd, const float* const* base_bd, const int64_t* n_bd,
+                           int on_device);
+/* multi-GPU: the GLOBAL point counts the means are taken over (default: local counts) */
+int pinn_engine_set_global_counts(pinn_engine_t* h, int64_t n_col_global, const int64_t* n_bd_global);
+/* loss_fun.lw[0] and loss_fun.ref (sw:381-382, 739) */
+int pinn_engine_set_loss(pinn_engine_t* h, double lw_eqn, double lref);
+
+/* grad(lossf, has_aux=True)(params, data) (sw:390, 479): writes the flat gradient of
+ * loss/lref (device pointer, may be NULL) and the UN-normalised loss_info (host
+ * pointer, may be NULL; forces a stream sync when given).  params_dev NULL => the
+ * engine's current parameters.  Includes the allreduce when a communicator is set. */
+int pinn_engine_loss_grad(pinn_engine_t* h, const float* params_dev, float* grad_out_dev,
+                          double* loss_info_host);
+
+/* adam_minimizer (sw:387-393), optax.adam defaults, on the engine's parameters.
+ * adam_init == opt.init (sw:400).  adam_steps runs n_steps fused steps as one CUDA
+ * graph replayed n_steps times; loss_info rows (per step, sw:425) are returned in
+ * loss_rows_host [n_steps][n_info] if non-NULL. lr may change between calls while
+ * m, v, count are kept (sw:439-440). */
+int pinn_engine_adam_init(pinn_engine_t* h);
+int pinn_engine_adam_steps(pinn_engine_t* h, int32_t n_steps, double lr, double* loss_rows_host);
+
+/* f_u (sw:213) and gov_eqn (sw:283) without parameter gradient (sw:608-616, 766-770).
+ * Outputs may be NULL. jets_out: [n,K]. */
+int pinn_engine_eval(pinn_engine_t* h, const float* z, int64_t n, const float* aux, const float* base,
+                     float* u_out, float* f_out, float* jets_out, int on_device);
+
+/* lbfgs_optimizer (sw:499-514): tfp.optimizer.lbfgs_minimize restated (m=10,
+ * Hager-Zhang line search).  value_unnormalised=1 reproduces the reference's
+ * (un-normalised value, normalised gradient) pairing (sw:479-490). */
+int pinn_engine_lbfgs(pinn_engine_t* h, int32_t max_iter, double tol, int32_t value_unnormalised,
+                      pinn_eval_cb cb, void* user, pinn_lbfgs_result_t* out);
+
+/* NCCL data parallelism: one fused allreduce [grad | loss partial sums] per evaluation.
+ * pinn_nccl_unique_id fills 128 bytes; every rank then calls pinn_engine_init_nccl. */
+int pinn_nccl_unique_id(uint8_t id_out[128]);
+int pinn_engine_init_nccl(pinn_engine_t* h, const uint8_t id[128], int32_t rank, int32_t world);
+
+/* fp32 FMA-pipe microbenchmark (roofline denominator of the SIMT path):
+ * returns achieved TFLOP/s; variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2 */
+int pinn_fma_peak(int device, int variant, double* tflops_out);
+
+/* timing helper: device time (ms) of the last adam_steps / loss_grad call measured
+ * with CUDA events on the engine stream */
+double pinn_engine_last_ms(pinn_engine_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,289 @@
+// Small device kernels around the fused jet-MLP kernel: parameter packing,
+// deterministic gradient/loss reduction, loss_info, Adam, L-BFGS vector maths,
+// FMA-pipe microbenchmark.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pinn_common.h"
+
+#define PINN_MAX_NL (PINN_MAX_LAYERS + 2)
+
+// flat (ravel_pytree, software.py:466) <-> packed layout map
+struct FlatMap {
+  int n_layers;             // L+1 linear layers
+  int wp;
+  int in_dim[PINN_MAX_NL], out_dim[PINN_MAX_NL];
+  int f_w[PINN_MAX_NL];     // flat offset of W_l (bias follows)
+  int p_w[PINN_MAX_NL], p_b[PINN_MAX_NL], p_wt[PINN_MAX_NL], ld[PINN_MAX_NL];
+  int n_params;
+};
+
+// flat index -> packed index (and transposed index, or -1)
+__device__ __forceinline__ int flat_to_pack(const FlatMap& M, int i, int& pt) {
+  pt = -1;
+  for (int l = 0; l < M.n_layers; ++l) {
+    const int nW = M.in_dim[l] * M.out_dim[l];
+    const int o = i - M.f_w[l];
+    if (o < nW) {
+      const int r = o / M.out_dim[l], c = o % M.out_dim[l];
+      if (M.p_wt[l] >= 0) pt = M.p_wt[l] + c * M.wp + r;
+      return M.p_w[l] + r * M.ld[l] + c;
+    }
+    if (o < nW + M.out_dim[l]) return M.p_b[l] + (o - nW);
+  }
+  return 0;
+}
+
+__global__ void k_pack(const FlatMap M, const float* __restrict__ flat, float* __restrict__ wpack) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M.n_params) return;
+  int pt;
+  const int p = flat_to_pack(M, i, pt);
+  const float v = flat[i];
+  wpack[p] = v;
+  if (pt >= 0) wpack[pt] = v;
+}
+
+// fused[i] = sum_b gacc[b][pack(i)]  (fixed order => deterministic)
+__global__ void k_grad_reduce(const FlatMap M, const float* __restrict__ gacc, int nb, int pg,
+                              float* __restrict__ fused) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M.n_params) return;
+  int pt;
+  const int p = flat_to_pack(M, i, pt);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int b = 0;
+  for (; b + 4 <= nb; b += 4) {
+    s0 += gacc[(size_t)(b + 0) * pg + p];
+    s1 += gacc[(size_t)(b + 1) * pg + p];
+    s2 += gacc[(size_t)(b + 2) * pg + p];
+    s3 += gacc[(size_t)(b + 3) * pg + p];
+  }
+  for (; b < nb; ++b) s0 += gacc[(size_t)b * pg + p];
+  fused[i] = (s0 + s1) + (s2 + s3);
+}
+
+// loss partial sums: tail[2s], tail[2s+1] = hi/lo split of sum_b loss_part[b][s]
+__global__ void k_loss_reduce(const double* __restrict__ loss_part, int nb, int n_slots,
+                              float* __restrict__ tail) {
+  const int s = threadIdx.x;
+  if (s >= n_slots) return;
+  double t = 0.0;
+  for (int b = 0; b < nb; ++b) t += loss_part[(size_t)b * n_slots + s];
+  const float hi = (float)t;
+  tail[2 * s] = hi;
+  tail[2 * s + 1] = (float)(t - (double)hi);
+}
+
+struct LossMeta {
+  int n_slots;               // n_bc data terms then one equation term
+  double count[PINN_MAX_SEG];   // global point counts
+  double weight[PINN_MAX_SEG];  // 1 for data terms, lw[0] for the equation term
+};
+
+// loss_info = [loss, loss_d, loss_e, data_err..., eqn_err]  (software.py:370-378)
+// Also advances the Adam step count and its bias corrections when tick != 0.
+__global__ void k_loss_info(const LossMeta* __restrict__ meta, const float* __restrict__ tail,
+                            double* __restrict__ ring, int* __restrict__ ring_pos, int ring_cap,
+                            int tick, int* __restrict__ adam_count, float* __restrict__ adam_c) {
+  if (threadIdx.x != 0) return;
+  const int n = meta->n_slots;
+  const int pos = *ring_pos;
+  double* row = ring + (size_t)(pos % ring_cap) * (3 + n);
+  double ld = 0.0, le = 0.0;
+  for (int s = 0; s < n; ++s) {
+    const double S = (double)tail[2 * s] + (double)tail[2 * s + 1];
+    const double m = S / meta->count[s];
+    row[3 + s] = m;
+    if (s < n - 1) ld += m; else le += m;
+  }
+  row[1] = ld;
+  row[2] = le;
+  row[0] = ld + meta->weight[n - 1] * le;
+  *ring_pos = pos + 1;
+  if (tick) {
+    const int t = *adam_count + 1;
+    *adam_count = t;
+    adam_c[0] = (float)(1.0 - pow(0.9, (double)t));
+    adam_c[1] = (float)(1.0 - pow(0.999, (double)t));
+  }
+}
+
+// optax.adam (b1=.9, b2=.999, eps=1e-8, eps_root=0), software.py:391-392
+__global__ void k_adam(int n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                       float* __restrict__ v, const float* __restrict__ lr, const float* __restrict__ c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = 0.9f * m[i] + 0.1f * gi;
+  const float vi = 0.999f * v[i] + 0.001f * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float mh = mi / c[0];
+  const float vh = vi / c[1];
+  p[i] -= lr[0] * mh / (sqrtf(vh) + 1e-8f);
+}
+
+__global__ void k_set_f32(float* dst, float v) { *dst = v; }
+
+// ---------------------------------------------------------------- L-BFGS helpers
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// all threads of a 1024-thread block get the sum; deterministic
+__device__ __forceinline__ double block_sum_d(double v, double* sh) {
+  v = warp_sum_d(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+  return t;
+}
+
+__global__ void k_axpy_out(int n, const float* __restrict__ x, const float* __restrict__ d, double alpha,
+                           float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)((double)x[i] + alpha * (double)d[i]);
+}
+
+// out[0] = g.d, out[1] = ||g||_inf
+__global__ void k_dot_inf(int n, const float* __restrict__ g, const float* __restrict__ d,
+                          double* __restrict__ out) {
+  __shared__ double sh[32];
+  double s = 0.0, mx = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    s += (double)g[i] * (double)d[i];
+    mx = fmax(mx, fabs((double)g[i]));
+  }
+  s = block_sum_d(s, sh);
+  // max via sum trick is wrong; do an explicit max reduction
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sh[w]);
+    out[0] = s;
+    out[1] = m;
+  }
+}
+
+// two-loop recursion (Nocedal & Wright alg. 7.4): d = -H g, history ring of `cnt` pairs,
+// newest at slot (head-1) mod m.  Single block.
+__global__ void k_lbfgs_direction(int n, int m, int cnt, int head, const float* __restrict__ g,
+                                  const float* __restrict__ Sh, const float* __restrict__ Yh,
+                                  const double* __restrict__ rho, float* __restrict__ d,
+                                  double* __restrict__ alpha /* [m] scratch */) {
+  __shared__ double sh[32];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = g[i];
+  __syncthreads();
+  for (int j = 0; j < cnt; ++j) {
+    const int slot = ((head - 1 - j) % m + m) % m;
+    const float* s = Sh + (size_t)slot * n;
+    const float* y = Yh + (size_t)slot * n;
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) t += (double)s[i] * (double)d[i];
+    t = block_sum_d(t, sh);
+    const double a = rho[slot] * t;
+    if (threadIdx.x == 0) alpha[slot] = a;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = (float)((double)d[i] - a * (double)y[i]);
+    __syncthreads();
+  }
+  if (cnt > 0) {
+    const int slot = ((head - 1) % m + m) % m;
+    const float* s = Sh + (size_t)slot * n;
+    const float* y = Yh + (size_t)slot * n;
+    double sy = 0.0, yy = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      sy += (double)s[i] * (double)y[i];
+      yy += (double)y[i] * (double)y[i];
+    }
+    sy = block_sum_d(sy, sh);
+    yy = block_sum_d(yy, sh);
+    const double gamma = sy / yy;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = (float)(gamma * (double)d[i]);
+    __syncthreads();
+  }
+  for (int j = cnt - 1; j >= 0; --j) {
+    const int slot = ((head - 1 - j) % m + m) % m;
+    const float* s = Sh + (size_t)slot * n;
+    const float* y = Yh + (size_t)slot * n;
+    double t = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) t += (double)y[i] * (double)d[i];
+    t = block_sum_d(t, sh);
+    const double b = rho[slot] * t;
+    const double a = alpha[slot];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = (float)((double)d[i] + (a - b) * (double)s[i]);
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = -d[i];
+}
+
+// push (s,y) = (xt-x, gt-g) into slot; x<-xt, g<-gt; out[0]=s.y, out[1]=||gt||_inf, rho[slot]=1/s.y
+__global__ void k_lbfgs_push(int n, int slot, float* __restrict__ x, float* __restrict__ g,
+                             const float* __restrict__ xt, const float* __restrict__ gt,
+                             float* __restrict__ Sh, float* __restrict__ Yh, double* __restrict__ rho,
+                             double* __restrict__ out) {
+  __shared__ double sh[32];
+  float* s = Sh + (size_t)slot * n;
+  float* y = Yh + (size_t)slot * n;
+  double sy = 0.0, mx = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float si = xt[i] - x[i], yi = gt[i] - g[i];
+    s[i] = si; y[i] = yi;
+    x[i] = xt[i]; g[i] = gt[i];
+    sy += (double)si * (double)yi;
+    mx = fmax(mx, fabs((double)gt[i]));
+  }
+  sy = block_sum_d(sy, sh);
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sh[w]);
+    out[0] = sy;
+    out[1] = m;
+    rho[slot] = 1.0 / sy;
+  }
+}
+
+// ---------------------------------------------------------------- FMA peak
+template <int VARIANT>
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float seed) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = seed + (float)(threadIdx.x + i);
+  const float b = 1.0000001f, c = 1e-9f;
+  for (int it = 0; it < iters; ++it) {
+    if (VARIANT == 0) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], b, c);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          unsigned long long av, bv, cv;
+          asm("mov.b64 %0, {%1, %2};" : "=l"(av) : "f"(a[i]), "f"(a[i + 1]));
+          asm("mov.b64 %0, {%1, %2};" : "=l"(bv) : "f"(b), "f"(b));
+          asm("mov.b64 %0, {%1, %2};" : "=l"(cv) : "f"(c), "f"(c));
+          asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(av) : "l"(av), "l"(bv), "l"(cv));
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(a[i]), "=f"(a[i + 1]) : "l"(av));
+        }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 12345.678f) out[0] = s;  // keep the loop alive
+}

@@ -1,0 +1,895 @@
+// C-ABI implementation of include/pinn_engine.h: per-call engine handle, device
+// buffers, kernel dispatch, CUDA-graph Adam loop, on-device L-BFGS, NCCL hook.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/pinn_engine.h"
+#include "aux_kernels.cuh"
+#include "jet_launch.h"
+#include "pinn_common.h"
+
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) return fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" const char* pinn_last_error(void) { return g_err.c_str(); }
+extern "C" int pinn_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+// ---------------------------------------------------------------- NCCL via dlopen
+struct Id128 { char b[128]; };  // ncclUniqueId (passed by value)
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.lib) return 0;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return fail("cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) return fail("libnccl: missing symbols");
+  g_nccl.lib = lib;
+  return 0;
+}
+
+// ---------------------------------------------------------------- engine
+struct PointSet {
+  float* coords = nullptr;  // device
+  float* aux = nullptr;
+  float* base = nullptr;
+  bool own_coords = false, own_aux = false, own_base = false;
+  size_t cap_coords = 0, cap_aux = 0, cap_base = 0;  // owned capacities (floats)
+};
+
+struct pinn_engine {
+  int device = 0, num_sms = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  pinn_spec_t spec{};
+  std::vector<int32_t> ops;
+  std::vector<float> consts;
+  PinnNet net{};
+  FlatMap fmap{};
+  int n_info = 0, n_slots = 0;
+  const JetKernelInfo* kcol = nullptr;
+  const JetKernelInfo* kbc = nullptr;
+  PinnProgram prog_col{}, prog_bc{};
+
+  // device state
+  float *d_params = nullptr, *d_fused = nullptr, *d_m = nullptr, *d_v = nullptr, *d_wpack = nullptr;
+  float *d_stash = nullptr, *d_gacc = nullptr, *d_seg_scale = nullptr, *d_lr = nullptr, *d_adam_c = nullptr;
+  double *d_loss_part = nullptr, *d_ring = nullptr;
+  int *d_ring_pos = nullptr, *d_adam_count = nullptr;
+  LossMeta* d_meta = nullptr;
+  int ring_cap = 4096;
+  size_t stash_floats = 0;
+  int grid_max = 0;
+
+  // points
+  PointSet col, bc;
+  int64_t n_col = 0;
+  std::vector<int64_t> n_bd;
+  int64_t n_bd_total = 0;
+  int64_t n_col_global = 0;
+  std::vector<int64_t> n_bd_global;
+  double lw = 1.0, lref = 1.0;
+  bool points_set = false;
+
+  // launches
+  PinnLaunch Lcol{}, Lbc{};
+  int grid_col = 0, grid_bc = 0;
+
+  // graph
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_valid = false;
+  double cur_lr = -1.0;
+
+  // nccl
+  void* comm = nullptr;
+  int world = 1, rank = 0;
+
+  // timing
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+
+  // lbfgs buffers
+  float *d_x = nullptr, *d_g = nullptr, *d_d = nullptr, *d_xt = nullptr, *d_S = nullptr, *d_Y = nullptr;
+  double *d_rho = nullptr, *d_alpha = nullptr, *d_scal = nullptr;
+};
+
+static int pad_width(int w) {
+  if (w <= 32) return 32;
+  if (w <= 64) return 64;
+  if (w <= 128) return 128;
+  if (w <= 256) return 256;
+  return -1;
+}
+
+static int build_layout(pinn_engine* h) {
+  const pinn_spec_t& s = h->spec;
+  PinnNet& n = h->net;
+  const int WP = pad_width(s.width);
+  if (WP < 0) return fail("width %d > 256 not supported", s.width);
+  if (s.n_hidden < 1 || s.n_hidden > PINN_MAX_LAYERS) return fail("n_hidden must be in 1..%d", PINN_MAX_LAYERS);
+  if (s.d_in < 1 || s.d_in > 3) return fail("d_in must be 1..3");
+  if (s.feat_mode == PINN_FEAT_POLAR && s.d_in != 2) return fail("polar feature map needs d_in == 2");
+  n.d_in = s.d_in;
+  n.feat_mode = s.feat_mode;
+  n.n_feat = (s.feat_mode == PINN_FEAT_POLAR) ? 3 : s.d_in;
+  n.n_hidden = s.n_hidden;
+  n.width = s.width;
+  n.wp = WP;
+  n.act_first = s.act_first;
+  n.act_hidden = s.act_hidden;
+  n.scl = s.scl;
+  n.epsil = s.epsil;
+  for (int i = 0; i < 3; ++i) {
+    const double lb = s.lb[i], ub = s.ub[i];
+    if (i < s.d_in && ub != lb) {
+      n.fa[i] = (float)(2.0 / (ub - lb));
+      n.fb[i] = (float)(-2.0 * lb / (ub - lb) - 1.0);
+    } else {
+      n.fa[i] = 0.f;
+      n.fb[i] = 0.f;
+    }
+  }
+  int o = 0;
+  n.off_w0 = o; o += 4 * WP;
+  n.off_b0 = o; o += WP;
+  for (int l = 1; l < s.n_hidden; ++l) {
+    n.off_w[l] = o; o += WP * WP;
+    n.off_b[l] = o; o += WP;
+  }
+  n.off_wl = o; o += WP;
+  n.off_bl = o; o += 4;
+  n.pg = o;
+  for (int l = 1; l < s.n_hidden; ++l) {
+    n.off_wt[l] = o; o += WP * WP;
+  }
+  n.pw = o;
+
+  FlatMap& M = h->fmap;
+  M.n_layers = s.n_hidden + 1;
+  M.wp = WP;
+  int f = 0;
+  for (int l = 0; l <= s.n_hidden; ++l) {
+    M.in_dim[l] = (l == 0) ? n.n_feat : s.width;
+    M.out_dim[l] = (l == s.n_hidden) ? 1 : s.width;
+    M.f_w[l] = f;
+    f += M.in_dim[l] * M.out_dim[l] + M.out_dim[l];
+    if (l == 0) { M.p_w[l] = n.off_w0; M.p_b[l] = n.off_b0; M.ld[l] = WP; M.p_wt[l] = -1; }
+    else if (l == s.n_hidden) { M.p_w[l] = n.off_wl; M.p_b[l] = n.off_bl; M.ld[l] = 1; M.p_wt[l] = -1; }
+    else { M.p_w[l] = n.off_w[l]; M.p_b[l] = n.off_b[l]; M.ld[l] = WP; M.p_wt[l] = n.off_wt[l]; }
+  }
+  M.n_params = f;
+  return 0;
+}
+
+extern "C" int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engine_t** out) {
+  if (!spec || !out) return fail("null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: the B200 engine has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
+  CK(cudaSetDevice(device));
+  if (spec->n_ops <= 0 || spec->n_ops > PINN_MAX_OPS) return fail("residual program length %d not in 1..%d", spec->n_ops, PINN_MAX_OPS);
+  if (spec->n_consts < 0 || spec->n_consts > PINN_MAX_CONSTS) return fail("too many constants");
+  if (spec->n_bc < 0 || spec->n_bc > PINN_MAX_SEG - 1) return fail("n_bc must be 0..%d", PINN_MAX_SEG - 1);
+  pinn_engine* h = new pinn_engine();
+  h->device = device;
+  h->spec = *spec;
+  h->ops.assign(spec->ops, spec->ops + spec->n_ops);
+  h->consts.assign(spec->consts, spec->consts + spec->n_consts);
+  h->spec.ops = h->ops.data();
+  h->spec.consts = h->consts.data();
+  if (build_layout(h)) { delete h; return 1; }
+  h->kcol = pinn_find_kernel(h->net.wp, spec->n1, spec->n2, spec->mix);
+  h->kbc = pinn_find_kernel(h->net.wp, 0, 0, 0);
+  if (!h->kcol || !h->kbc) {
+    const int wp = h->net.wp;
+    delete h;
+    return fail("no kernel instantiation for WP=%d jets (n1=%d,n2=%d,mix=%d)", wp, spec->n1, spec->n2, spec->mix);
+  }
+  cudaError_t e = h->kcol->prepare();
+  if (e == cudaSuccess) e = h->kbc->prepare();
+  if (e != cudaSuccess) { delete h; return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  h->num_sms = prop.multiProcessorCount;
+  h->grid_max = h->num_sms;
+  h->n_slots = spec->n_bc + 1;
+  h->n_info = 3 + h->n_slots;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  CK(cudaEventCreate(&h->ev0));
+  CK(cudaEventCreate(&h->ev1));
+
+  // programs
+  h->prog_col.n_ops = spec->n_ops;
+  memcpy(h->prog_col.ops, spec->ops, sizeof(int32_t) * spec->n_ops);
+  memcpy(h->prog_col.consts, spec->consts, sizeof(float) * spec->n_consts);
+  h->prog_bc.n_ops = 3;  // u - aux0   (software.py:344)
+  h->prog_bc.ops[0] = OP_JET | (0 << 8);
+  h->prog_bc.ops[1] = OP_AUX | (0 << 8);
+  h->prog_bc.ops[2] = OP_SUB;
+
+  const int P = h->fmap.n_params;
+  const size_t nf = (size_t)P + 2 * h->n_slots;
+  CK(cudaMalloc(&h->d_params, sizeof(float) * P));
+  CK(cudaMalloc(&h->d_fused, sizeof(float) * nf));
+  CK(cudaMalloc(&h->d_m, sizeof(float) * P));
+  CK(cudaMalloc(&h->d_v, sizeof(float) * P));
+  CK(cudaMalloc(&h->d_wpack, sizeof(float) * h->net.pw));
+  CK(cudaMemset(h->d_wpack, 0, sizeof(float) * h->net.pw));
+  CK(cudaMemset(h->d_params, 0, sizeof(float) * P));
+  CK(cudaMemset(h->d_m, 0, sizeof(float) * P));
+  CK(cudaMemset(h->d_v, 0, sizeof(float) * P));
+  h->stash_floats = (size_t)h->grid_max * spec->n_hidden *
+                    std::max(h->kcol->stash_floats_per_layer, h->kbc->stash_floats_per_layer);
+  CK(cudaMalloc(&h->d_stash, sizeof(float) * h->stash_floats));
+  CK(cudaMalloc(&h->d_gacc, sizeof(float) * (size_t)h->grid_max * h->net.pg));
+  CK(cudaMalloc(&h->d_loss_part, sizeof(double) * (size_t)h->grid_max * h->n_slots));
+  CK(cudaMalloc(&h->d_seg_scale, sizeof(float) * PINN_MAX_SEG));
+  CK(cudaMalloc(&h->d_lr, sizeof(float)));
+  CK(cudaMalloc(&h->d_adam_c, sizeof(float) * 2));
+  CK(cudaMalloc(&h->d_ring, sizeof(double) * (size_t)h->ring_cap * h->n_info));
+  CK(cudaMalloc(&h->d_ring_pos, sizeof(int)));
+  CK(cudaMalloc(&h->d_adam_count, sizeof(int)));
+  CK(cudaMalloc(&h->d_meta, sizeof(LossMeta)));
+  CK(cudaMemset(h->d_ring_pos, 0, sizeof(int)));
+  CK(cudaMemset(h->d_adam_count, 0, sizeof(int)));
+  *out = h;
+  return 0;
+}
+
+static void free_set(PointSet& s) {
+  if (s.own_coords && s.coords) cudaFree(s.coords);
+  if (s.own_aux && s.aux) cudaFree(s.aux);
+  if (s.own_base && s.base) cudaFree(s.base);
+  s = PointSet();
+}
+
+extern "C" void pinn_engine_destroy(pinn_engine_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  void* bufs[] = {h->d_params, h->d_fused, h->d_m, h->d_v, h->d_wpack, h->d_stash, h->d_gacc, h->d_seg_scale,
+                  h->d_lr, h->d_adam_c, h->d_loss_part, h->d_ring, h->d_ring_pos, h->d_adam_count, h->d_meta,
+                  h->d_x, h->d_g, h->d_d, h->d_xt, h->d_S, h->d_Y, h->d_rho, h->d_alpha, h->d_scal};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  free_set(h->col);
+  free_set(h->bc);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int pinn_engine_set_stream(pinn_engine_t* h, void* s) {
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  h->stream = (cudaStream_t)s;
+  h->own_stream = false;
+  h->graph_valid = false;
+  return 0;
+}
+
+extern "C" int64_t pinn_engine_num_params(pinn_engine_t* h) { return h->fmap.n_params; }
+extern "C" int32_t pinn_engine_num_loss_info(pinn_engine_t* h) { return h->n_info; }
+extern "C" int32_t pinn_engine_tile_points(pinn_engine_t* h) { return h->kcol->tile_points; }
+extern "C" int32_t pinn_engine_launches_per_eval(pinn_engine_t* h) { return 6; }
+
+extern "C" int pinn_engine_set_params(pinn_engine_t* h, const float* flat, int on_device) {
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->d_params, flat, sizeof(float) * h->fmap.n_params,
+                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  if (!on_device) CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+extern "C" int pinn_engine_get_params(pinn_engine_t* h, float* out, int on_device) {
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(out, h->d_params, sizeof(float) * h->fmap.n_params,
+                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  if (!on_device) CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static int ensure(float** p, size_t* cap, bool* own, size_t need) {
+  if (*own && *p && *cap >= need) return 0;
+  if (*own && *p) cudaFree(*p);
+  *p = nullptr;
+  const size_t c = std::max<size_t>(need, 16);
+  CK(cudaMalloc(p, sizeof(float) * c));
+  *cap = c;
+  *own = true;
+  return 0;
+}
+
+static int upload_meta(pinn_engine* h) {
+  LossMeta M{};
+  M.n_slots = h->n_slots;
+  float sc[PINN_MAX_SEG] = {0};
+  for (int i = 0; i < h->spec.n_bc; ++i) {
+    const double N = (double)(h->n_bd_global.empty() ? h->n_bd[i] : h->n_bd_global[i]);
+    M.count[i] = N > 0 ? N : 1.0;
+    M.weight[i] = 1.0;
+    sc[i] = (float)(2.0 / (M.count[i] * h->lref));
+  }
+  const int e = h->n_slots - 1;
+  const double Nc = (double)(h->n_col_global > 0 ? h->n_col_global : h->n_col);
+  M.count[e] = Nc > 0 ? Nc : 1.0;
+  M.weight[e] = h->lw;
+  sc[e] = (float)(2.0 * h->lw / (M.count[e] * h->lref));
+  CK(cudaMemcpyAsync(h->d_meta, &M, sizeof M, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_seg_scale, sc, sizeof sc, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));  // host temporaries
+  return 0;
+}
+
+static void fill_launch(pinn_engine* h, PinnLaunch& L, const JetKernelInfo* k, const PinnProgram& prog) {
+  memset(&L, 0, sizeof L);
+  L.net = h->net;
+  L.wpack = h->d_wpack;
+  L.seg_scale = h->d_seg_scale;
+  L.stash = h->d_stash;
+  L.gacc = h->d_gacc;
+  L.loss_part = h->d_loss_part;
+  L.n_slots = h->n_slots;
+  L.prog = prog;
+  (void)k;
+}
+
+extern "C" int pinn_engine_set_points(pinn_engine_t* h, const float* x_col, int64_t n_col, const float* aux_col,
+                                      const float* base_col, int32_t n_bc, const float* const* x_bd,
+                                      const float* const* u_bd, const float* const* base_bd,
+                                      const int64_t* n_bd, int on_device) {
+  CK(cudaSetDevice(h->device));
+  if (n_bc != h->spec.n_bc) return fail("n_bc %d != spec.n_bc %d", n_bc, h->spec.n_bc);
+  if (n_col <= 0) return fail("n_col must be > 0");
+  if (h->spec.n_aux_col > 0 && !aux_col) return fail("aux_col required (n_aux_col=%d)", h->spec.n_aux_col);
+  const int d = h->spec.d_in, K = h->kcol->k;
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  // collocation set
+  if (on_device) {
+    if (h->col.own_coords && h->col.coords) cudaFree(h->col.coords);
+    h->col.coords = const_cast<float*>(x_col); h->col.own_coords = false; h->col.cap_coords = 0;
+    if (h->col.own_aux && h->col.aux) cudaFree(h->col.aux);
+    h->col.aux = const_cast<float*>(aux_col); h->col.own_aux = false; h->col.cap_aux = 0;
+    if (h->col.own_base && h->col.base) cudaFree(h->col.base);
+    h->col.base = const_cast<float*>(base_col); h->col.own_base = false; h->col.cap_base = 0;
+  } else {
+    if (ensure(&h->col.coords, &h->col.cap_coords, &h->col.own_coords, (size_t)n_col * d)) return 1;
+    CK(cudaMemcpyAsync(h->col.coords, x_col, sizeof(float) * n_col * d, kind, h->stream));
+    if (aux_col) {
+      if (ensure(&h->col.aux, &h->col.cap_aux, &h->col.own_aux, (size_t)n_col * h->spec.n_aux_col)) return 1;
+      CK(cudaMemcpyAsync(h->col.aux, aux_col, sizeof(float) * n_col * h->spec.n_aux_col, kind, h->stream));
+    } else if (h->col.own_aux) { /* keep buffer, unused */ } else h->col.aux = nullptr;
+    if (base_col) {
+      if (ensure(&h->col.base, &h->col.cap_base, &h->col.own_base, (size_t)n_col * K)) return 1;
+      CK(cudaMemcpyAsync(h->col.base, base_col, sizeof(float) * n_col * K, kind, h->stream));
+    } else { if (h->col.own_base && h->col.base) cudaFree(h->col.base); h->col.base = nullptr; h->col.own_base = false; h->col.cap_base = 0; }
+  }
+  const bool shape_changed = (n_col != h->n_col);
+  h->n_col = n_col;
+  // boundary groups: concatenated copies
+  int64_t tot = 0;
+  std::vector<int64_t> nb(n_bc);
+  for (int i = 0; i < n_bc; ++i) { nb[i] = n_bd[i]; tot += n_bd[i]; }
+  bool bc_changed = (nb != h->n_bd);
+  bool has_base_bd = false;
+  for (int i = 0; i < n_bc; ++i) if (base_bd && base_bd[i]) has_base_bd = true;
+  if (tot > 0) {
+    if (ensure(&h->bc.coords, &h->bc.cap_coords, &h->bc.own_coords, (size_t)tot * d)) return 1;
+    if (ensure(&h->bc.aux, &h->bc.cap_aux, &h->bc.own_aux, (size_t)tot)) return 1;
+    if (has_base_bd) { if (ensure(&h->bc.base, &h->bc.cap_base, &h->bc.own_base, (size_t)tot)) return 1; }
+    else if (h->bc.base) { cudaFree(h->bc.base); h->bc.base = nullptr; h->bc.own_base = false; h->bc.cap_base = 0; bc_changed = true; }
+    int64_t o = 0;
+    for (int i = 0; i < n_bc; ++i) {
+      if (nb[i] == 0) continue;
+      CK(cudaMemcpyAsync(h->bc.coords + o * d, x_bd[i], sizeof(float) * nb[i] * d, kind, h->stream));
+      CK(cudaMemcpyAsync(h->bc.aux + o, u_bd[i], sizeof(float) * nb[i], kind, h->stream));
+      if (has_base_bd) CK(cudaMemcpyAsync(h->bc.base + o, base_bd[i], sizeof(float) * nb[i], kind, h->stream));
+      o += nb[i];
+    }
+  }
+  h->n_bd = nb;
+  h->n_bd_total = tot;
+
+  // launch descriptors
+  fill_launch(h, h->Lcol, h->kcol, h->prog_col);
+  {
+    PinnLaunch& L = h->Lcol;
+    L.coords = h->col.coords; L.aux = h->col.aux; L.base = h->col.base; L.n_aux = h->spec.n_aux_col;
+    L.n_seg = 1;
+    const int tp = h->kcol->tile_points;
+    L.n_tiles = (int)((n_col + tp - 1) / tp);
+    L.seg_tile_end[0] = L.n_tiles; L.seg_pt_begin[0] = 0; L.seg_pt_end[0] = n_col; L.seg_slot[0] = h->n_slots - 1;
+    h->grid_col = std::min(L.n_tiles, h->grid_max);
+  }
+  fill_launch(h, h->Lbc, h->kbc, h->prog_bc);
+  {
+    PinnLaunch& L = h->Lbc;
+    L.coords = h->bc.coords; L.aux = h->bc.aux; L.base = h->bc.base; L.n_aux = 1;
+    const int tp = h->kbc->tile_points;
+    int tiles = 0, ns = 0;
+    int64_t o = 0;
+    for (int i = 0; i < n_bc; ++i) {
+      if (nb[i] > 0) {
+        tiles += (int)((nb[i] + tp - 1) / tp);
+        L.seg_tile_end[ns] = tiles; L.seg_pt_begin[ns] = o; L.seg_pt_end[ns] = o + nb[i]; L.seg_slot[ns] = i;
+        ++ns;
+      }
+      o += nb[i];
+    }
+    L.n_seg = ns; L.n_tiles = tiles;
+    h->grid_bc = std::min(tiles, h->grid_max);
+  }
+  if (!on_device) CK(cudaStreamSynchronize(h->stream));  // host buffers may be reused by the caller
+  h->points_set = true;
+  if (shape_changed || bc_changed || on_device) h->graph_valid = false;
+  h->n_col_global = 0;
+  h->n_bd_global.clear();
+  return upload_meta(h);
+}
+
+extern "C" int pinn_engine_set_global_counts(pinn_engine_t* h, int64_t n_col_global, const int64_t* n_bd_global) {
+  CK(cudaSetDevice(h->device));
+  h->n_col_global = n_col_global;
+  h->n_bd_global.assign(n_bd_global, n_bd_global + h->spec.n_bc);
+  return upload_meta(h);
+}
+
+extern "C" int pinn_engine_set_loss(pinn_engine_t* h, double lw_eqn, double lref) {
+  CK(cudaSetDevice(h->device));
+  h->lw = lw_eqn;
+  h->lref = lref;
+  if (!h->points_set) return 0;
+  return upload_meta(h);
+}
+
+// enqueue one evaluation: pack -> zero -> bc -> col -> reduce -> (allreduce) -> loss_info
+static int enqueue_eval(pinn_engine* h, const float* params_dev, int tick) {
+  if (!h->points_set) return fail("set_points has not been called");
+  cudaStream_t st = h->stream;
+  const int P = h->fmap.n_params;
+  const int nb = std::max(h->grid_col, h->grid_bc);
+  k_pack<<<(P + 255) / 256, 256, 0, st>>>(h->fmap, params_dev ? params_dev : h->d_params, h->d_wpack);
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(h->d_gacc, 0, sizeof(float) * (size_t)nb * h->net.pg, st));
+  CK(cudaMemsetAsync(h->d_loss_part, 0, sizeof(double) * (size_t)nb * h->n_slots, st));
+  if (h->Lbc.n_tiles > 0) CK(h->kbc->launch(h->Lbc, true, h->grid_bc, st));
+  CK(h->kcol->launch(h->Lcol, true, h->grid_col, st));
+  k_grad_reduce<<<(P + 127) / 128, 128, 0, st>>>(h->fmap, h->d_gacc, nb, h->net.pg, h->d_fused);
+  CK(cudaGetLastError());
+  k_loss_reduce<<<1, 32, 0, st>>>(h->d_loss_part, nb, h->n_slots, h->d_fused + P);
+  CK(cudaGetLastError());
+  if (h->comm) {
+    const int rc = g_nccl.AllReduce(h->d_fused, h->d_fused, (size_t)P + 2 * h->n_slots, /*ncclFloat32*/ 7,
+                                    /*ncclSum*/ 0, h->comm, st);
+    if (rc != 0) return fail("ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+  }
+  k_loss_info<<<1, 32, 0, st>>>(h->d_meta, h->d_fused + P, h->d_ring, h->d_ring_pos, h->ring_cap, tick,
+                                h->d_adam_count, h->d_adam_c);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pinn_engine_loss_grad(pinn_engine_t* h, const float* params_dev, float* grad_out_dev,
+                                     double* loss_info_host) {
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemsetAsync(h->d_ring_pos, 0, sizeof(int), h->stream));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  if (enqueue_eval(h, params_dev, 0)) return 1;
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->timed = true;
+  if (grad_out_dev)
+    CK(cudaMemcpyAsync(grad_out_dev, h->d_fused, sizeof(float) * h->fmap.n_params, cudaMemcpyDeviceToDevice, h->stream));
+  if (loss_info_host) {
+    CK(cudaMemcpyAsync(loss_info_host, h->d_ring, sizeof(double) * h->n_info, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+extern "C" int pinn_engine_adam_init(pinn_engine_t* h) {
+  CK(cudaSetDevice(h->device));
+  const int P = h->fmap.n_params;
+  CK(cudaMemsetAsync(h->d_m, 0, sizeof(float) * P, h->stream));
+  CK(cudaMemsetAsync(h->d_v, 0, sizeof(float) * P, h->stream));
+  CK(cudaMemsetAsync(h->d_adam_count, 0, sizeof(int), h->stream));
+  return 0;
+}
+
+static int enqueue_adam_step(pinn_engine* h) {
+  if (enqueue_eval(h, nullptr, 1)) return 1;
+  const int P = h->fmap.n_params;
+  k_adam<<<(P + 255) / 256, 256, 0, h->stream>>>(P, h->d_params, h->d_fused, h->d_m, h->d_v, h->d_lr, h->d_adam_c);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pinn_engine_adam_steps(pinn_engine_t* h, int32_t n_steps, double lr, double* rows) {
+  CK(cudaSetDevice(h->device));
+  if (n_steps <= 0) return 0;
+  if (lr != h->cur_lr) {
+    k_set_f32<<<1, 1, 0, h->stream>>>(h->d_lr, (float)lr);
+    CK(cudaGetLastError());
+    h->cur_lr = lr;
+  }
+  if (!h->graph_valid) {
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_adam_step(h);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+    if (e != cudaSuccess) return fail("graph capture: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&h->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail("graph instantiate: %s", cudaGetErrorString(e));
+    h->graph_valid = true;
+  }
+  CK(cudaEventRecord(h->ev0, h->stream));
+  int done = 0;
+  while (done < n_steps) {
+    const int chunk = std::min(n_steps - done, h->ring_cap);
+    CK(cudaMemsetAsync(h->d_ring_pos, 0, sizeof(int), h->stream));
+    for (int i = 0; i < chunk; ++i) CK(cudaGraphLaunch(h->graph_exec, h->stream));
+    if (rows) {
+      CK(cudaMemcpyAsync(rows + (size_t)done * h->n_info, h->d_ring, sizeof(double) * (size_t)chunk * h->n_info,
+                         cudaMemcpyDeviceToHost, h->stream));
+      if (done + chunk < n_steps) CK(cudaStreamSynchronize(h->stream));
+    }
+    done += chunk;
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->timed = true;
+  if (rows) CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" double pinn_engine_last_ms(pinn_engine_t* h) {
+  if (!h->timed) return -1.0;
+  cudaSetDevice(h->device);
+  if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+extern "C" int pinn_engine_eval(pinn_engine_t* h, const float* z, int64_t n, const float* aux, const float* base,
+                                float* u_out, float* f_out, float* jets_out, int on_device) {
+  CK(cudaSetDevice(h->device));
+  if (n <= 0) return 0;
+  const int d = h->spec.d_in, K = h->kcol->k, na = h->spec.n_aux_col;
+  if (na > 0 && !aux) return fail("aux required");
+  cudaStream_t st = h->stream;
+  std::vector<void*> tmp;
+  auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr; tmp.push_back(p); return p; };
+  auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); };
+  const float *dz = z, *daux = aux, *dbase = base;
+  float *du = u_out, *df = f_out, *dj = jets_out;
+  if (!on_device) {
+    float* t = (float*)dalloc(sizeof(float) * n * d);
+    if (!t) { cleanup(); return fail("cudaMalloc failed"); }
+    cudaMemcpyAsync(t, z, sizeof(float) * n * d, cudaMemcpyHostToDevice, st); dz = t;
+    if (aux) { t = (float*)dalloc(sizeof(float) * n * na); if (!t) { cleanup(); return fail("cudaMalloc failed"); }
+      cudaMemcpyAsync(t, aux, sizeof(float) * n * na, cudaMemcpyHostToDevice, st); daux = t; }
+    if (base) { t = (float*)dalloc(sizeof(float) * n * K); if (!t) { cleanup(); return fail("cudaMalloc failed"); }
+      cudaMemcpyAsync(t, base, sizeof(float) * n * K, cudaMemcpyHostToDevice, st); dbase = t; }
+    if (u_out) { du = (float*)dalloc(sizeof(float) * n); if (!du) { cleanup(); return fail("cudaMalloc failed"); } }
+    if (f_out) { df = (float*)dalloc(sizeof(float) * n); if (!df) { cleanup(); return fail("cudaMalloc failed"); } }
+    if (jets_out) { dj = (float*)dalloc(sizeof(float) * n * K); if (!dj) { cleanup(); return fail("cudaMalloc failed"); } }
+  }
+  const int P = h->fmap.n_params;
+  k_pack<<<(P + 255) / 256, 256, 0, st>>>(h->fmap, h->d_params, h->d_wpack);
+  PinnLaunch L;
+  fill_launch(h, L, h->kcol, h->prog_col);
+  L.coords = dz; L.aux = daux; L.base = dbase; L.n_aux = na;
+  L.out_u = du; L.out_f = df; L.out_jets = dj;
+  L.n_seg = 1;
+  const int tp = h->kcol->tile_points;
+  L.n_tiles = (int)((n + tp - 1) / tp);
+  L.seg_tile_end[0] = L.n_tiles; L.seg_pt_begin[0] = 0; L.seg_pt_end[0] = n; L.seg_slot[0] = 0;
+  cudaError_t e = h->kcol->launch(L, false, std::min(L.n_tiles, h->grid_max), st);
+  if (e != cudaSuccess) { cleanup(); return fail("eval launch: %s", cudaGetErrorString(e)); }
+  if (!on_device) {
+    if (u_out) cudaMemcpyAsync(u_out, du, sizeof(float) * n, cudaMemcpyDeviceToHost, st);
+    if (f_out) cudaMemcpyAsync(f_out, df, sizeof(float) * n, cudaMemcpyDeviceToHost, st);
+    if (jets_out) cudaMemcpyAsync(jets_out, dj, sizeof(float) * n * K, cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess) return fail("eval: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- L-BFGS (software.py:499-514)
+namespace {
+struct Phi { double a, f, d; };  // step, value, directional derivative
+
+struct LineSearch {
+  // Hager & Zhang (2006) "Algorithm 851: CG_DESCENT" line search, the algorithm
+  // tfp.optimizer.linesearch.hager_zhang implements (delta=.1, sigma=.9, eps=1e-6,
+  // gamma=.66, rho=5, bisection theta=.5, max 50 evaluations).
+  pinn_engine* h;
+  int value_unnorm;
+  pinn_eval_cb cb;
+  void* user;
+  int evals = 0, max_evals = 50;
+  double f_lim = 0, phi0 = 0, dphi0 = 0;
+  bool error = false;
+  std::vector<double> info;
+
+  int eval(double a, Phi& out);
+  bool wolfe(const Phi& p) const {
+    const double delta = 0.1, sigma = 0.9;
+    if (!(isfinite(p.f) && isfinite(p.d))) return false;
+    const bool exact = (p.f <= phi0 + delta * p.a * dphi0) && (p.d >= sigma * dphi0);
+    const bool approx = (p.f <= f_lim) && ((2 * delta - 1) * dphi0 >= p.d) && (p.d >= sigma * dphi0);
+    return exact || approx;
+  }
+};
+
+int LineSearch::eval(double a, Phi& out) {
+  pinn_engine* e = h;
+  const int P = e->fmap.n_params;
+  cudaStream_t st = e->stream;
+  k_axpy_out<<<(P + 255) / 256, 256, 0, st>>>(P, e->d_x, e->d_d, a, e->d_xt);
+  CK(cudaMemsetAsync(e->d_ring_pos, 0, sizeof(int), st));
+  if (enqueue_eval(e, e->d_xt, 0)) return 1;
+  k_dot_inf<<<1, 1024, 0, st>>>(P, e->d_fused, e->d_d, e->d_scal);
+  CK(cudaGetLastError());
+  double sc[2];
+  info.resize(e->n_info);
+  CK(cudaMemcpyAsync(info.data(), e->d_ring, sizeof(double) * e->n_info, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(sc, e->d_scal, sizeof sc, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  ++evals;
+  if (cb) cb(info.data(), e->n_info, user);
+  out.a = a;
+  out.f = value_unnorm ? info[0] : info[0] / e->lref;
+  out.d = sc[0];
+  if (!isfinite(out.f)) { out.f = INFINITY; out.d = -1.0; }
+  return 0;
+}
+}  // namespace
+
+static int lbfgs_alloc(pinn_engine* h) {
+  if (h->d_x) return 0;
+  const int P = h->fmap.n_params, m = 10;
+  CK(cudaMalloc(&h->d_x, sizeof(float) * P));
+  CK(cudaMalloc(&h->d_g, sizeof(float) * P));
+  CK(cudaMalloc(&h->d_d, sizeof(float) * P));
+  CK(cudaMalloc(&h->d_xt, sizeof(float) * P));
+  CK(cudaMalloc(&h->d_S, sizeof(float) * (size_t)P * m));
+  CK(cudaMalloc(&h->d_Y, sizeof(float) * (size_t)P * m));
+  CK(cudaMalloc(&h->d_rho, sizeof(double) * m));
+  CK(cudaMalloc(&h->d_alpha, sizeof(double) * m));
+  CK(cudaMalloc(&h->d_scal, sizeof(double) * 4));
+  return 0;
+}
+
+extern "C" int pinn_engine_lbfgs(pinn_engine_t* h, int32_t max_iter, double tol, int32_t value_unnorm,
+                                 pinn_eval_cb cb, void* user, pinn_lbfgs_result_t* out) {
+  CK(cudaSetDevice(h->device));
+  if (lbfgs_alloc(h)) return 1;
+  const int P = h->fmap.n_params, m = 10;
+  cudaStream_t st = h->stream;
+  pinn_lbfgs_result_t R{};
+  LineSearch ls{h, value_unnorm, cb, user};
+  CK(cudaMemcpyAsync(h->d_x, h->d_params, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemsetAsync(h->d_d, 0, sizeof(float) * P, st));
+  // initial evaluation at x0 (tfp evaluates value_and_gradients at the initial position)
+  Phi p0;
+  if (ls.eval(0.0, p0)) return 1;
+  CK(cudaMemcpyAsync(h->d_g, h->d_fused, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
+  k_dot_inf<<<1, 1024, 0, st>>>(P, h->d_g, h->d_g, h->d_scal);
+  double sc[2];
+  CK(cudaMemcpyAsync(sc, h->d_scal, sizeof sc, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  double fcur = p0.f, ginf = sc[1];
+  int total_evals = ls.evals;
+  int cnt = 0, head = 0;
+  R.converged = ginf <= tol;
+  while (!R.converged && !R.failed && R.iterations < max_iter) {
+    k_lbfgs_direction<<<1, 1024, 0, st>>>(P, m, cnt, head, h->d_g, h->d_S, h->d_Y, h->d_rho, h->d_d, h->d_alpha);
+    k_dot_inf<<<1, 1024, 0, st>>>(P, h->d_g, h->d_d, h->d_scal);
+    CK(cudaMemcpyAsync(sc, h->d_scal, sizeof sc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const double dphi0 = sc[0];
+    if (!(dphi0 < 0.0) || !isfinite(dphi0)) { R.failed = 1; break; }
+    // ---- Hager-Zhang line search
+    ls.evals = 0;
+    ls.phi0 = fcur;
+    ls.dphi0 = dphi0;
+    ls.f_lim = fcur + 1e-6 * fabs(fcur);
+    Phi lo{0.0, fcur, dphi0}, hi{}, c{};
+    bool found = false, ok = true;
+    auto ev = [&](double a, Phi& p) -> bool {  // returns true when p satisfies the Wolfe test
+      if (ls.eval(a, p)) { ok = false; return false; }
+      return ls.wolfe(p);
+    };
+    // U3 bisection on [A, B] with phi'(A) < 0, phi(A) <= f_lim, phi'(B) < 0, phi(B) > f_lim
+    auto bisect = [&](Phi& A, Phi& B) -> bool {
+      while (ok && ls.evals < ls.max_evals) {
+        Phi d;
+        if (ev(0.5 * (A.a + B.a), d)) { c = d; return true; }
+        if (!ok) return false;
+        if (d.d >= 0) { B = d; return false; }
+        if (d.f <= ls.f_lim) A = d; else B = d;
+        if (B.a - A.a <= 1e-16 * fmax(1.0, fabs(B.a))) break;
+      }
+      return false;
+    };
+    // update(a,b,c): returns true if a Wolfe point was found during a nested bisection
+    auto update = [&](Phi& A, Phi& B, const Phi& p) -> bool {
+      if (!(p.a > A.a && p.a < B.a)) return false;
+      if (p.d >= 0) { B = p; return false; }
+      if (p.f <= ls.f_lim) { A = p; return false; }
+      Phi Bb = p;
+      const bool f = bisect(A, Bb);
+      B = Bb;
+      return f;
+    };
+    // bracket, starting from step 1 (tfp initial_step_size = 1)
+    {
+      Phi prev = lo;
+      double a = 1.0;
+      bool bracketed = false;
+      while (ok && ls.evals < ls.max_evals) {
+        if (ev(a, c)) { found = true; break; }
+        if (!ok) break;
+        if (c.d >= 0) { lo = prev; hi = c; bracketed = true; break; }
+        if (c.f > ls.f_lim) {
+          lo = Phi{0.0, fcur, dphi0}; hi = c;
+          if (bisect(lo, hi)) found = true;
+          bracketed = true;
+          break;
+        }
+        prev = c;
+        a *= 5.0;
+      }
+      if (!found && !bracketed) ok = false;
+    }
+    auto secant = [](const Phi& A, const Phi& B) { return (A.a * B.d - B.a * A.d) / (B.d - A.d); };
+    while (ok && !found && ls.evals < ls.max_evals) {
+      const Phi a0 = lo, b0 = hi;
+      // secant2
+      Phi p;
+      double cs = secant(lo, hi);
+      if (!isfinite(cs) || !(cs > lo.a && cs < hi.a)) cs = 0.5 * (lo.a + hi.a);
+      if (ev(cs, p)) { c = p; found = true; break; }
+      if (!ok) break;
+      if (update(lo, hi, p)) { found = true; break; }
+      double c2 = NAN;
+      if (p.a == hi.a) c2 = secant(b0, hi);
+      else if (p.a == lo.a) c2 = secant(a0, lo);
+      if (isfinite(c2) && c2 > lo.a && c2 < hi.a && ls.evals < ls.max_evals) {
+        Phi p2;
+        if (ev(c2, p2)) { c = p2; found = true; break; }
+        if (!ok) break;
+        if (update(lo, hi, p2)) { found = true; break; }
+      }
+      if (hi.a - lo.a > 0.66 * (b0.a - a0.a) && ls.evals < ls.max_evals) {
+        Phi pm;
+        if (ev(0.5 * (lo.a + hi.a), pm)) { c = pm; found = true; break; }
+        if (!ok) break;
+        if (update(lo, hi, pm)) { found = true; break; }
+      }
+      if (hi.a - lo.a <= 1e-16 * fmax(1.0, hi.a)) break;
+    }
+    total_evals += ls.evals;
+    if (!ok && !g_err.empty() && ls.evals == 0) return 1;
+    if (!found) { R.failed = 1; break; }
+    // accept: the last evaluation was at c (xt, fused hold x_new, g_new)
+    k_lbfgs_push<<<1, 1024, 0, st>>>(P, head, h->d_x, h->d_g, h->d_xt, h->d_fused, h->d_S, h->d_Y, h->d_rho, h->d_scal);
+    CK(cudaMemcpyAsync(sc, h->d_scal, sizeof sc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (sc[0] > 0.0 && isfinite(sc[0])) { head = (head + 1) % m; cnt = std::min(cnt + 1, m); }
+    ginf = sc[1];
+    const double fprev = fcur;
+    fcur = c.f;
+    ++R.iterations;
+    if (ginf <= tol) R.converged = 1;
+    if (fcur == fprev && c.a == 0.0) R.converged = 1;  // x_tolerance = f_relative_tolerance = 0
+  }
+  CK(cudaMemcpyAsync(h->d_params, h->d_x, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  R.evaluations = total_evals;
+  R.final_loss = value_unnorm ? fcur : fcur * h->lref;
+  if (out) *out = R;
+  return 0;
+}
+
+// ---------------------------------------------------------------- NCCL
+extern "C" int pinn_nccl_unique_id(uint8_t id_out[128]) {
+  if (nccl_load()) return 1;
+  Id128 id;
+  memset(&id, 0, sizeof id);
+  const int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) return fail("ncclGetUniqueId failed (%d)", rc);
+  memcpy(id_out, id.b, 128);
+  return 0;
+}
+extern "C" int pinn_engine_init_nccl(pinn_engine_t* h, const uint8_t id[128], int32_t rank, int32_t world) {
+  CK(cudaSetDevice(h->device));
+  if (nccl_load()) return 1;
+  Id128 uid;
+  memcpy(uid.b, id, 128);
+  void* comm = nullptr;
+  const int rc = g_nccl.CommInitRank(&comm, world, uid, rank);
+  if (rc != 0) return fail("ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+  h->comm = comm;
+  h->rank = rank;
+  h->world = world;
+  h->graph_valid = false;
+  return 0;
+}
+
+// ---------------------------------------------------------------- FMA microbenchmark
+extern "C" int pinn_fma_peak(int device, int variant, double* tflops_out) {
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  float* d = nullptr;
+  CK(cudaMalloc(&d, 4));
+  const int grid = prop.multiProcessorCount * 8, iters = 4096;
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(a));
+    if (variant == 0) k_fma_peak<0><<<grid, 256>>>(d, iters, 0.5f);
+    else k_fma_peak<1><<<grid, 256>>>(d, iters, 0.5f);
+    CK(cudaEventRecord(b));
+    CK(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    const double flops = 2.0 * 16 * 8 * (double)iters * 256.0 * grid;
+    best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  *tflops_out = best;
+  return 0;
+}

@@ -1,0 +1,33 @@
+// One translation unit per kernel configuration:
+//   nvcc ... -DJ_WP=64 -DJ_N1=2 -DJ_N2=2 -DJ_MIX=0 -c jet_inst.cu -o jet_64_220.o
+#include "jet_kernel.cuh"
+#include "jet_launch.h"
+
+#ifndef J_WP
+#error "compile with -DJ_WP= -DJ_N1= -DJ_N2= -DJ_MIX="
+#endif
+
+using Cfg = JetCfg<J_WP, J_N1, J_N2, J_MIX>;
+
+static cudaError_t launch_impl(const PinnLaunch& L, bool train, int grid, cudaStream_t stream) {
+  if (train)
+    jet_mlp_kernel<Cfg, true><<<grid, PINN_NT, Cfg::smem_bytes(true), stream>>>(L);
+  else
+    jet_mlp_kernel<Cfg, false><<<grid, PINN_NT, Cfg::smem_bytes(false), stream>>>(L);
+  return cudaGetLastError();
+}
+
+static cudaError_t prepare_impl() {
+  cudaError_t e = cudaFuncSetAttribute(jet_mlp_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg::smem_bytes(true));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(jet_mlp_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)Cfg::smem_bytes(false));
+}
+
+#define CAT_(a, b, c, d) pinn_jet_info_##a##_##b##c##d
+#define CAT(a, b, c, d) CAT_(a, b, c, d)
+
+extern const JetKernelInfo CAT(J_WP, J_N1, J_N2, J_MIX) = {
+    J_WP, J_N1, J_N2, J_MIX, Cfg::K, Cfg::TP, Cfg::smem_bytes(true), Cfg::smem_bytes(false),
+    (size_t)Cfg::TP * Cfg::K * Cfg::WP, launch_impl, prepare_impl};

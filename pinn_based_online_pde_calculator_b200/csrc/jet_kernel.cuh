@@ -1,0 +1,721 @@
+// Fused jet-MLP kernel (fp32 SIMT path): forward Taylor-mode propagation of
+// (u, du, d2u) through the MLP, residual program, loss partial sums, and the
+// hand-written backward to the parameter gradient -- one persistent CTA per SM,
+// activations in shared memory, per-layer stash in a CTA-private (L2-resident)
+// scratch, weights streamed by cp.async.bulk (TMA bulk copy) + mbarrier.
+//
+// Replaces the nested reverse-mode autograd of pinn_app/software.py:246-297
+// (vgmat/vectgrad/gov_eqn) and grad(loss_fun) at software.py:318-379, 390.
+// Math: SURVEY.md section 8(a) addendum; layout + roofline: DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pinn_common.h"
+
+template <int WP_, int N1_, int N2_, int MIX_>
+struct JetCfg {
+  static constexpr int WP = WP_, N1 = N1_, N2 = N2_, MIX = MIX_;
+  static constexpr int K = 1 + N1 + N2 + MIX;   // jet channels
+  static constexpr int NT = PINN_NT, TU = PINN_TU;
+  static constexpr int UT = WP / TU;            // threads across units
+  static constexpr int ROWS = NT / UT;          // thread rows across points
+  static constexpr int PT = (K == 1) ? 8 : (K <= 4 ? 3 : 2);  // points per thread
+  static constexpr int TP = ROWS * PT;          // points per tile
+  static constexpr int SP = K * WP + 4;         // smem stride per point (== 4 mod 32)
+  static constexpr int KC = (2048 / WP) < WP ? (2048 / WP) : WP;  // weight rows per chunk
+  static constexpr int NCH = WP / KC;
+  static constexpr int WT8 = WP / 8;
+  static constexpr int TILES = WT8 * WT8;       // 8x8 wgrad tiles
+  static constexpr int NG = TILES <= NT ? NT / TILES : 1;
+  static constexpr int NPASS = TILES <= NT ? 1 : TILES / NT;
+  static constexpr int HS_FLOATS = TP * SP;
+  static constexpr uint32_t CHUNK_BYTES = KC * WP * 4;
+  static_assert(WP % 32 == 0, "padded width must be a multiple of 32");
+  static_assert(NG == 1 || NG * WP * WP <= HS_FLOATS, "wgrad scratch must fit in Hs");
+  static_assert(5 * NT * 8 + NT <= HS_FLOATS, "final scratch must fit in Hs");
+  static constexpr size_t smem_bytes(bool train) {
+    return (size_t)(HS_FLOATS * (train ? 2 : 1) + 2 * KC * WP) * 4 + 64;
+  }
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* b, int cnt) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(cnt));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(b))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+
+// ---------------------------------------------------------------- activations
+// forward: y = act(a0), d1 = act'(a0), d2 = act''(a0); s0 = value stashed for backward
+__device__ __forceinline__ void act_fwd(int act, float a0, float& y, float& d1, float& d2, float& s0) {
+  if (act == PINN_TANH) {
+    y = tanhf(a0);
+    d1 = fmaf(-y, y, 1.0f);
+    d2 = -2.0f * y * d1;
+    s0 = y;
+  } else {
+    float s, c;
+    sincosf(a0, &s, &c);
+    y = s; d1 = c; d2 = -s; s0 = a0;
+  }
+}
+// from the stashed value: y, d1, d2, d3
+__device__ __forceinline__ void act_bwd(int act, float s0, float& y, float& d1, float& d2, float& d3) {
+  if (act == PINN_TANH) {
+    y = s0;
+    d1 = fmaf(-y, y, 1.0f);
+    d2 = -2.0f * y * d1;
+    d3 = d1 * fmaf(6.0f * y, y, -2.0f);
+  } else {
+    float s, c;
+    sincosf(s0, &s, &c);
+    y = s; d1 = c; d2 = -s; d3 = -c;
+  }
+}
+
+// ---------------------------------------------------------------- residual VM
+// Forward-mode dual numbers over the K network-output channels.
+template <int K>
+__device__ __noinline__ void vm_run(const PinnProgram& P, const float* z, const float* aux,
+                                    const float* u, float& f, float* df) {
+  float sv[PINN_VM_STACK];
+  float sd[PINN_VM_STACK][K];
+  int sp = 0;
+  for (int i = 0; i < P.n_ops; ++i) {
+    const int w = P.ops[i];
+    const int op = w & 0xff, arg = w >> 8;
+    switch (op) {
+      case OP_CONST: sv[sp] = P.consts[arg];
+        for (int c = 0; c < K; ++c) sd[sp][c] = 0.f; ++sp; break;
+      case OP_COORD: sv[sp] = z[arg];
+        for (int c = 0; c < K; ++c) sd[sp][c] = 0.f; ++sp; break;
+      case OP_AUX: sv[sp] = aux[arg];
+        for (int c = 0; c < K; ++c) sd[sp][c] = 0.f; ++sp; break;
+      case OP_JET: sv[sp] = u[arg];
+        for (int c = 0; c < K; ++c) sd[sp][c] = (c == arg) ? 1.f : 0.f; ++sp; break;
+      case OP_ADD: --sp; sv[sp - 1] += sv[sp];
+        for (int c = 0; c < K; ++c) sd[sp - 1][c] += sd[sp][c]; break;
+      case OP_SUB: --sp; sv[sp - 1] -= sv[sp];
+        for (int c = 0; c < K; ++c) sd[sp - 1][c] -= sd[sp][c]; break;
+      case OP_MUL: { --sp; const float a = sv[sp - 1], b = sv[sp];
+        for (int c = 0; c < K; ++c) sd[sp - 1][c] = sd[sp - 1][c] * b + a * sd[sp][c];
+        sv[sp - 1] = a * b; break; }
+      case OP_DIV: { --sp; const float a = sv[sp - 1], b = sv[sp]; const float ib = 1.0f / b;
+        const float q = a * ib;
+        for (int c = 0; c < K; ++c) sd[sp - 1][c] = (sd[sp - 1][c] - q * sd[sp][c]) * ib;
+        sv[sp - 1] = q; break; }
+      case OP_NEG: sv[sp - 1] = -sv[sp - 1];
+        for (int c = 0; c < K; ++c) sd[sp - 1][c] = -sd[sp - 1][c]; break;
+      case OP_POWI: { const float a = sv[sp - 1]; float pm1 = 1.f;  // a^(n-1)
+        for (int q = 1; q < arg; ++q) pm1 *= a;
+        const float dv = (arg == 0) ? 0.f : (float)arg * pm1;
+        sv[sp - 1] = (arg == 0) ? 1.f : pm1 * a;
+        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= dv; break; }
+      case OP_POWF: { const float a = sv[sp - 1], e = P.consts[arg];
+        const float v = powf(a, e); const float dv = e * powf(a, e - 1.0f);
+        sv[sp - 1] = v;
+        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= dv; break; }
+      case OP_SIN: { float s, co; sincosf(sv[sp - 1], &s, &co); sv[sp - 1] = s;
+        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= co; break; }
+      case OP_COS: { float s, co; sincosf(sv[sp - 1], &s, &co); sv[sp - 1] = co;
+        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= -s; break; }
+      case OP_EXP: { const float v = expf(sv[sp - 1]); sv[sp - 1] = v;
+        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= v; break; }
+      case OP_LOG: { const float a = sv[sp - 1]; sv[sp - 1] = logf(a); const float dv = 1.0f / a;
+        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= dv; break; }
+      case OP_TANH: { const float v = tanhf(sv[sp - 1]); sv[sp - 1] = v; const float dv = 1.f - v * v;
+        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= dv; break; }
+      case OP_SQRT: { const float v = sqrtf(sv[sp - 1]); sv[sp - 1] = v; const float dv = 0.5f / v;
+        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= dv; break; }
+      default: break;
+    }
+  }
+  f = sv[0];
+  for (int c = 0; c < K; ++c) df[c] = sd[0][c];
+}
+
+// ---------------------------------------------------------------- building blocks
+// acc[c][p][j] += sum_{k in chunk} S[pt(p)][c][kbase+k] * wc[k][unit(j)]
+// S points at the thread-row's first point; wc at the chunk base (smem).
+template <class C>
+__device__ __forceinline__ void gemm_chunk(float (&acc)[C::K][C::PT][8], const float* __restrict__ S,
+                                           const float* __restrict__ wc, int ua, int kbase) {
+#pragma unroll 1
+  for (int kk = 0; kk < C::KC; kk += 4) {
+    float4 a[C::K][C::PT];
+#pragma unroll
+    for (int c = 0; c < C::K; ++c)
+#pragma unroll
+      for (int p = 0; p < C::PT; ++p)
+        a[c][p] = *reinterpret_cast<const float4*>(S + p * (C::ROWS * C::SP) + c * C::WP + kbase + kk);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b0 = *reinterpret_cast<const float4*>(wc + (kk + q) * C::WP + ua);
+      const float4 b1 = *reinterpret_cast<const float4*>(wc + (kk + q) * C::WP + C::WP / 2 + ua);
+#pragma unroll
+      for (int c = 0; c < C::K; ++c)
+#pragma unroll
+        for (int p = 0; p < C::PT; ++p) {
+          const float av = (q == 0) ? a[c][p].x : (q == 1) ? a[c][p].y : (q == 2) ? a[c][p].z : a[c][p].w;
+          acc[c][p][0] = fmaf(av, b0.x, acc[c][p][0]);
+          acc[c][p][1] = fmaf(av, b0.y, acc[c][p][1]);
+          acc[c][p][2] = fmaf(av, b0.z, acc[c][p][2]);
+          acc[c][p][3] = fmaf(av, b0.w, acc[c][p][3]);
+          acc[c][p][4] = fmaf(av, b1.x, acc[c][p][4]);
+          acc[c][p][5] = fmaf(av, b1.y, acc[c][p][5]);
+          acc[c][p][6] = fmaf(av, b1.z, acc[c][p][6]);
+          acc[c][p][7] = fmaf(av, b1.w, acc[c][p][7]);
+        }
+    }
+  }
+}
+
+// store the thread's [K][PT][8] register tile to smem S (point-major, channel, unit)
+template <class C>
+__device__ __forceinline__ void store_tile(float* __restrict__ S, const float (&acc)[C::K][C::PT][8],
+                                           int row, int ua) {
+#pragma unroll
+  for (int p = 0; p < C::PT; ++p)
+#pragma unroll
+    for (int c = 0; c < C::K; ++c) {
+      float* d = S + (row + p * C::ROWS) * C::SP + c * C::WP;
+      *reinterpret_cast<float4*>(d + ua) = make_float4(acc[c][p][0], acc[c][p][1], acc[c][p][2], acc[c][p][3]);
+      *reinterpret_cast<float4*>(d + C::WP / 2 + ua) =
+          make_float4(acc[c][p][4], acc[c][p][5], acc[c][p][6], acc[c][p][7]);
+    }
+}
+
+// feature jets of the network input (software.py:172-175 for 'polar')
+template <class C>
+__device__ __forceinline__ void feature_jets(const PinnNet& net, const float (&z)[3], float (&hj)[C::K][3]) {
+#pragma unroll
+  for (int c = 0; c < C::K; ++c) hj[c][0] = hj[c][1] = hj[c][2] = 0.f;
+  if (net.feat_mode == PINN_FEAT_POLAR) {
+    float s, co;
+    sincosf(z[1], &s, &co);
+    hj[0][0] = fmaf(net.fa[0], z[0], net.fb[0]); hj[0][1] = co; hj[0][2] = s;
+    if (C::N1 >= 1) hj[1][0] = net.fa[0];
+    if (C::N1 >= 2) { hj[2][1] = -s; hj[2][2] = co; }
+    if (C::N2 >= 2) { hj[1 + C::N1 + 1][1] = -co; hj[1 + C::N1 + 1][2] = -s; }
+  } else {
+#pragma unroll
+    for (int f = 0; f < 3; ++f) hj[0][f] = (f < net.d_in) ? fmaf(net.fa[f], z[f], net.fb[f]) : 0.f;
+#pragma unroll
+    for (int i = 0; i < C::N1; ++i) hj[1 + i][i] = net.fa[i];
+  }
+}
+
+// pre-activation jets A_c (bias NOT yet added) -> output jets Y_c, in place; optional stash
+template <class C, bool TRAIN>
+__device__ __forceinline__ void act_forward(float (&acc)[C::K][C::PT][8], const float* __restrict__ bias,
+                                            int act, float* __restrict__ stash_l, int row, int ua) {
+  const float4 ba = __ldg(reinterpret_cast<const float4*>(bias + ua));
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + C::WP / 2 + ua));
+  const float b[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+  for (int p = 0; p < C::PT; ++p) {
+    float y[8], d1[8], d2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s0;
+      act_fwd(act, acc[0][p][j] + b[j], y[j], d1[j], d2[j], s0);
+      acc[0][p][j] = s0;
+    }
+    if (TRAIN) {
+#pragma unroll
+      for (int c = 0; c < C::K; ++c) {
+        float* d = stash_l + ((size_t)(row + p * C::ROWS) * C::K + c) * C::WP;
+        *reinterpret_cast<float4*>(d + ua) = make_float4(acc[c][p][0], acc[c][p][1], acc[c][p][2], acc[c][p][3]);
+        *reinterpret_cast<float4*>(d + C::WP / 2 + ua) =
+            make_float4(acc[c][p][4], acc[c][p][5], acc[c][p][6], acc[c][p][7]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int i = 0; i < C::N2; ++i) {
+        const float Ai = acc[1 + i][p][j];
+        acc[1 + C::N1 + i][p][j] = fmaf(d2[j] * Ai, Ai, d1[j] * acc[1 + C::N1 + i][p][j]);
+      }
+      if (C::MIX)
+        acc[C::K - 1][p][j] = fmaf(d2[j] * acc[1][p][j], acc[2][p][j], d1[j] * acc[C::K - 1][p][j]);
+#pragma unroll
+      for (int i = 0; i < C::N1; ++i) acc[1 + i][p][j] *= d1[j];
+      acc[0][p][j] = y[j];
+    }
+  }
+}
+
+// adjoint of act_forward: acc holds Ybar_c on entry, Abar_c on exit (reads the stash)
+template <class C>
+__device__ __forceinline__ void act_backward(float (&acc)[C::K][C::PT][8], int act,
+                                             const float* __restrict__ stash_l, int row, int ua) {
+#pragma unroll
+  for (int p = 0; p < C::PT; ++p) {
+    float st[C::K][8];
+#pragma unroll
+    for (int c = 0; c < C::K; ++c) {
+      const float* s = stash_l + ((size_t)(row + p * C::ROWS) * C::K + c) * C::WP;
+      const float4 v0 = *reinterpret_cast<const float4*>(s + ua);
+      const float4 v1 = *reinterpret_cast<const float4*>(s + C::WP / 2 + ua);
+      st[c][0] = v0.x; st[c][1] = v0.y; st[c][2] = v0.z; st[c][3] = v0.w;
+      st[c][4] = v1.x; st[c][5] = v1.y; st[c][6] = v1.z; st[c][7] = v1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y, d1, d2, d3;
+      act_bwd(act, st[0][j], y, d1, d2, d3);
+      float ab0 = d1 * acc[0][p][j];
+      float ab1[C::N1 > 0 ? C::N1 : 1];
+#pragma unroll
+      for (int i = 0; i < C::N1; ++i) {
+        const float yb = acc[1 + i][p][j];
+        ab1[i] = d1 * yb;
+        ab0 = fmaf(d2 * st[1 + i][j], yb, ab0);
+      }
+#pragma unroll
+      for (int i = 0; i < C::N2; ++i) {
+        const float yb = acc[1 + C::N1 + i][p][j];
+        const float Ai = st[1 + i][j], Aii = st[1 + C::N1 + i][j];
+        acc[1 + C::N1 + i][p][j] = d1 * yb;
+        ab1[i] = fmaf(2.0f * d2 * Ai, yb, ab1[i]);
+        ab0 = fmaf(fmaf(d3 * Ai, Ai, d2 * Aii), yb, ab0);
+      }
+      if (C::MIX) {
+        const float yb = acc[C::K - 1][p][j];
+        const float A0 = st[1][j], A1 = st[2][j], A01 = st[C::K - 1][j];
+        acc[C::K - 1][p][j] = d1 * yb;
+        ab1[0] = fmaf(d2 * A1, yb, ab1[0]);
+        ab1[C::N1 > 1 ? 1 : 0] = fmaf(d2 * A0, yb, ab1[C::N1 > 1 ? 1 : 0]);
+        ab0 = fmaf(fmaf(d3 * A0, A1, d2 * A01), yb, ab0);
+      }
+#pragma unroll
+      for (int i = 0; i < C::N1; ++i) acc[1 + i][p][j] = ab1[i];
+      acc[0][p][j] = ab0;
+    }
+  }
+}
+
+// recompute a layer's OUTPUT jets Y_c from its stash and write them to smem S
+template <class C>
+__device__ __forceinline__ void recompute_outputs(float* __restrict__ S, int act,
+                                                  const float* __restrict__ stash_l, int row, int ua) {
+#pragma unroll
+  for (int p = 0; p < C::PT; ++p) {
+    float st[C::K][8];
+#pragma unroll
+    for (int c = 0; c < C::K; ++c) {
+      const float* s = stash_l + ((size_t)(row + p * C::ROWS) * C::K + c) * C::WP;
+      const float4 v0 = *reinterpret_cast<const float4*>(s + ua);
+      const float4 v1 = *reinterpret_cast<const float4*>(s + C::WP / 2 + ua);
+      st[c][0] = v0.x; st[c][1] = v0.y; st[c][2] = v0.z; st[c][3] = v0.w;
+      st[c][4] = v1.x; st[c][5] = v1.y; st[c][6] = v1.z; st[c][7] = v1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y, d1, d2, d3;
+      act_bwd(act, st[0][j], y, d1, d2, d3);
+#pragma unroll
+      for (int i = 0; i < C::N2; ++i) {
+        const float Ai = st[1 + i][j];
+        st[1 + C::N1 + i][j] = fmaf(d2 * Ai, Ai, d1 * st[1 + C::N1 + i][j]);
+      }
+      if (C::MIX) st[C::K - 1][j] = fmaf(d2 * st[1][j], st[2][j], d1 * st[C::K - 1][j]);
+#pragma unroll
+      for (int i = 0; i < C::N1; ++i) st[1 + i][j] *= d1;
+      st[0][j] = y;
+    }
+#pragma unroll
+    for (int c = 0; c < C::K; ++c) {
+      float* d = S + (row + p * C::ROWS) * C::SP + c * C::WP;
+      *reinterpret_cast<float4*>(d + ua) = make_float4(st[c][0], st[c][1], st[c][2], st[c][3]);
+      *reinterpret_cast<float4*>(d + C::WP / 2 + ua) = make_float4(st[c][4], st[c][5], st[c][6], st[c][7]);
+    }
+  }
+}
+
+// unit/row index of wgrad-tile element e (0..7): split halves like the GEMM tile
+template <class C>
+__device__ __forceinline__ int tile_idx(int t, int e) {
+  return (e < 4) ? (4 * t + e) : (C::WP / 2 + 4 * t + (e - 4));
+}
+
+// hidden-layer weight gradient for one layer: gW[k][u] += sum_{pt,c} H[pt][c][k] * G[pt][c][u]
+// Hs doubles as cross-group scratch when NG > 1 (callers guarantee the barriers).
+template <class C>
+__device__ __forceinline__ void wgrad_layer(float* __restrict__ Hs, const float* __restrict__ Gs,
+                                            float* __restrict__ gW, float* __restrict__ gB, int tid) {
+  // bias gradient: sum over points of the value-channel adjoint
+  float bsum = 0.f;
+  if (tid < C::WP) {
+#pragma unroll 4
+    for (int pt = 0; pt < C::TP; ++pt) bsum += Gs[pt * C::SP + tid];
+  }
+#pragma unroll 1
+  for (int pass = 0; pass < C::NPASS; ++pass) {
+    const int tt = (C::NG > 1) ? (tid % C::TILES) : (tid + pass * C::NT);
+    const int grp = (C::NG > 1) ? (tid / C::TILES) : 0;
+    const int ki = tt / C::WT8, ui = tt % C::WT8;
+    constexpr int PPG = C::TP / C::NG;  // points per group
+    float w[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[i][j] = 0.f;
+    const float* hp = Hs + (grp * PPG) * C::SP + 4 * ki;
+    const float* gp = Gs + (grp * PPG) * C::SP + 4 * ui;
+#pragma unroll 1
+    for (int pt = 0; pt < PPG; ++pt) {
+#pragma unroll
+      for (int c = 0; c < C::K; ++c) {
+        const float4 h0 = *reinterpret_cast<const float4*>(hp + pt * C::SP + c * C::WP);
+        const float4 h1 = *reinterpret_cast<const float4*>(hp + pt * C::SP + c * C::WP + C::WP / 2);
+        const float4 g0 = *reinterpret_cast<const float4*>(gp + pt * C::SP + c * C::WP);
+        const float4 g1 = *reinterpret_cast<const float4*>(gp + pt * C::SP + c * C::WP + C::WP / 2);
+        const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[i][j] = fmaf(h[i], g[j], w[i][j]);
+      }
+    }
+    if (C::NG == 1) {
+      // read-modify-write the CTA-private accumulator directly
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float* d = gW + tile_idx<C>(ki, i) * C::WP;
+        float4* d0 = reinterpret_cast<float4*>(d + 4 * ui);
+        float4* d1 = reinterpret_cast<float4*>(d + C::WP / 2 + 4 * ui);
+        float4 v0 = *d0, v1 = *d1;
+        v0.x += w[i][0]; v0.y += w[i][1]; v0.z += w[i][2]; v0.w += w[i][3];
+        v1.x += w[i][4]; v1.y += w[i][5]; v1.z += w[i][6]; v1.w += w[i][7];
+        *d0 = v0; *d1 = v1;
+      }
+    } else {
+      __syncthreads();  // everyone finished reading Hs
+      float* sc = Hs + grp * (C::WP * C::WP);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float* d = sc + tile_idx<C>(ki, i) * C::WP;
+        *reinterpret_cast<float4*>(d + 4 * ui) = make_float4(w[i][0], w[i][1], w[i][2], w[i][3]);
+        *reinterpret_cast<float4*>(d + C::WP / 2 + 4 * ui) = make_float4(w[i][4], w[i][5], w[i][6], w[i][7]);
+      }
+      __syncthreads();
+      constexpr int NV = C::WP * C::WP / 4;  // float4 outputs
+      for (int v = tid; v < NV; v += C::NT) {
+        float4 s = reinterpret_cast<const float4*>(Hs)[v];
+#pragma unroll
+        for (int g = 1; g < C::NG; ++g) {
+          const float4 t = reinterpret_cast<const float4*>(Hs + g * (C::WP * C::WP))[v];
+          s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        float4* d = reinterpret_cast<float4*>(gW) + v;
+        float4 o = *d;
+        o.x += s.x; o.y += s.y; o.z += s.z; o.w += s.w;
+        *d = o;
+      }
+    }
+  }
+  if (tid < C::WP) gB[tid] += bsum;
+}
+
+// ---------------------------------------------------------------- the kernel
+template <class C, bool TRAIN>
+__global__ void __launch_bounds__(PINN_NT, 1) jet_mlp_kernel(const __grid_constant__ PinnLaunch L) {
+  constexpr int K = C::K, PT = C::PT, WP = C::WP, SP = C::SP, ROWS = C::ROWS, NCH = C::NCH, KC = C::KC;
+  extern __shared__ __align__(128) float smem[];
+  float* Hs = smem;
+  float* Gs = Hs + C::HS_FLOATS;
+  float* Wc = TRAIN ? (Gs + C::HS_FLOATS) : Gs;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(Wc + 2 * KC * WP);
+
+  const PinnNet& net = L.net;
+  const int tid = threadIdx.x;
+  const int ut = tid % C::UT, row = tid / C::UT;
+  const int ua = 4 * ut;
+  const int Lh = net.n_hidden;
+  const int nF = (Lh - 1) * NCH;
+  const int S = TRAIN ? 2 * nF : nF;
+  const int my_tiles = (L.n_tiles > (int)blockIdx.x) ? (L.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const long long total = (long long)my_tiles * S;
+  long long gpos = 0;
+
+  auto issue = [&](long long g) {
+    const int p = (int)(g % S);
+    const float* src;
+    if (p < nF) {
+      const int l = 1 + p / NCH, ch = p % NCH;
+      src = L.wpack + net.off_w[l] + ch * (KC * WP);
+    } else {
+      const int q = p - nF;
+      const int l = (Lh - 1) - q / NCH, ch = q % NCH;
+      src = L.wpack + net.off_wt[l] + ch * (KC * WP);
+    }
+    const int st = (int)(g & 1);
+    mbar_expect_tx(&mbar[st], C::CHUNK_BYTES);
+    bulk_g2s(Wc + st * (KC * WP), src, C::CHUNK_BYTES, &mbar[st]);
+  };
+
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0 && total > 0) issue(0);
+
+  float* stash = TRAIN ? (L.stash + (size_t)blockIdx.x * Lh * (C::TP * K * WP)) : nullptr;
+  float* gacc = TRAIN ? (L.gacc + (size_t)blockIdx.x * net.pg) : nullptr;
+  constexpr size_t STL = (size_t)C::TP * K * WP;  // stash floats per layer
+
+  // persistent small-gradient accumulators (first layer, output layer)
+  float w0acc[3][8], b0acc[8], wlacc[8], blacc = 0.f;
+  double lsum[PINN_MAX_SEG];
+  if (TRAIN) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { w0acc[0][j] = w0acc[1][j] = w0acc[2][j] = 0.f; b0acc[j] = 0.f; wlacc[j] = 0.f; }
+#pragma unroll
+    for (int s = 0; s < PINN_MAX_SEG; ++s) lsum[s] = 0.0;
+  }
+
+  // one consumed weight chunk: prefetch the next, wait for this one
+  auto chunk_begin = [&]() -> const float* {
+    if (tid == 0 && gpos + 1 < total) issue(gpos + 1);
+    const int st = (int)(gpos & 1);
+    mbar_wait(&mbar[st], (uint32_t)((gpos >> 1) & 1));
+    return Wc + st * (KC * WP);
+  };
+
+#pragma unroll 1
+  for (int it = 0; it < my_tiles; ++it) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    int seg = 0;
+    while (seg + 1 < L.n_seg && tile >= L.seg_tile_end[seg]) ++seg;
+    const int tile0 = seg ? L.seg_tile_end[seg - 1] : 0;
+    const long long pbegin = L.seg_pt_begin[seg] + (long long)(tile - tile0) * C::TP;
+    const long long rem = L.seg_pt_end[seg] - pbegin;
+    const int cnt = rem < C::TP ? (int)rem : C::TP;
+    const int slot = L.seg_slot[seg];
+
+    float z[PT][3];
+    long long gp[PT];
+    bool valid[PT];
+#pragma unroll
+    for (int p = 0; p < PT; ++p) {
+      const int lp = row + p * ROWS;
+      valid[p] = lp < cnt;
+      gp[p] = pbegin + (valid[p] ? lp : 0);
+      z[p][0] = z[p][1] = z[p][2] = 0.f;
+      for (int d = 0; d < net.d_in; ++d) z[p][d] = __ldg(L.coords + gp[p] * net.d_in + d);
+    }
+
+    float acc[K][PT][8];
+    // ---------------- first layer: A_c = scl * hjet_c . W0
+    {
+      float w0[3][8];
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(L.wpack + net.off_w0 + f * WP + ua));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(L.wpack + net.off_w0 + f * WP + WP / 2 + ua));
+        w0[f][0] = a.x; w0[f][1] = a.y; w0[f][2] = a.z; w0[f][3] = a.w;
+        w0[f][4] = b.x; w0[f][5] = b.y; w0[f][6] = b.z; w0[f][7] = b.w;
+      }
+#pragma unroll
+      for (int p = 0; p < PT; ++p) {
+        float hj[K][3];
+        feature_jets<C>(net, z[p], hj);
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            acc[c][p][j] = net.scl * fmaf(hj[c][0], w0[0][j], fmaf(hj[c][1], w0[1][j], hj[c][2] * w0[2][j]));
+      }
+    }
+    act_forward<C, TRAIN>(acc, L.wpack + net.off_b0, net.act_first, stash, row, ua);
+
+    // ---------------- hidden layers
+#pragma unroll 1
+    for (int l = 1; l < Lh; ++l) {
+      __syncthreads();  // previous readers of Hs are done
+      store_tile<C>(Hs, acc, row, ua);
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < K; ++c)
+#pragma unroll
+        for (int p = 0; p < PT; ++p)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[c][p][j] = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < NCH; ++ch) {
+        const float* wc = chunk_begin();
+        gemm_chunk<C>(acc, Hs + row * SP, wc, ua, ch * KC);
+        __syncthreads();
+        ++gpos;
+      }
+      act_forward<C, TRAIN>(acc, L.wpack + net.off_b[l], net.act_hidden, stash + l * STL, row, ua);
+    }
+
+    // ---------------- output layer (software.py:183, 215) + residual program
+    float wl[8];
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(L.wpack + net.off_wl + ua));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(L.wpack + net.off_wl + WP / 2 + ua));
+      wl[0] = a.x; wl[1] = a.y; wl[2] = a.z; wl[3] = a.w; wl[4] = b.x; wl[5] = b.y; wl[6] = b.z; wl[7] = b.w;
+    }
+    const float bl = __ldg(L.wpack + net.off_bl);
+    float ubar[K][PT];
+#pragma unroll
+    for (int p = 0; p < PT; ++p) {
+      float u[K];
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s = fmaf(acc[c][p][j], wl[j], s);
+#pragma unroll
+        for (int o = C::UT / 2; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        u[c] = net.epsil * (s + (c == 0 ? bl : 0.f));
+        if (L.base) u[c] += __ldg(L.base + gp[p] * K + c);
+      }
+      float f, df[K];
+      vm_run<K>(L.prog, z[p], L.aux ? (L.aux + gp[p] * L.n_aux) : nullptr, u, f, df);
+      if (TRAIN) {
+        const float sc = valid[p] ? __ldg(L.seg_scale + slot) : 0.f;
+#pragma unroll
+        for (int c = 0; c < K; ++c) ubar[c][p] = sc * f * df[c];
+        if (ut == 0 && valid[p]) lsum[slot] += (double)f * (double)f;
+      } else {
+        if (ut == 0 && valid[p]) {
+          if (L.out_u) L.out_u[gp[p]] = u[0];
+          if (L.out_f) L.out_f[gp[p]] = f;
+          if (L.out_jets)
+            for (int c = 0; c < K; ++c) L.out_jets[gp[p] * K + c] = u[c];
+        }
+      }
+    }
+
+    if (TRAIN) {
+      // output-layer gradients and the adjoint of the last hidden layer's outputs
+#pragma unroll
+      for (int p = 0; p < PT; ++p) {
+        if (ut == 0) blacc += net.epsil * ubar[0][p];
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const float e = net.epsil * ubar[c][p];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            wlacc[j] = fmaf(e, acc[c][p][j], wlacc[j]);
+            acc[c][p][j] = e * wl[j];
+          }
+        }
+      }
+      // ---------------- backward through the hidden layers
+#pragma unroll 1
+      for (int l = Lh - 1; l >= 1; --l) {
+        act_backward<C>(acc, net.act_hidden, stash + l * STL, row, ua);
+        __syncthreads();  // previous readers of Hs/Gs are done
+        store_tile<C>(Gs, acc, row, ua);
+        recompute_outputs<C>(Hs, (l - 1 == 0) ? net.act_first : net.act_hidden, stash + (l - 1) * STL, row, ua);
+        __syncthreads();
+        wgrad_layer<C>(Hs, Gs, gacc + net.off_w[l], gacc + net.off_b[l], tid);
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+          for (int p = 0; p < PT; ++p)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[c][p][j] = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+          const float* wc = chunk_begin();
+          gemm_chunk<C>(acc, Gs + row * SP, wc, ua, ch * KC);
+          __syncthreads();
+          ++gpos;
+        }
+      }
+      // ---------------- first layer gradients
+      act_backward<C>(acc, net.act_first, stash, row, ua);
+#pragma unroll
+      for (int p = 0; p < PT; ++p) {
+        float hj[K][3];
+        feature_jets<C>(net, z[p], hj);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          b0acc[j] += acc[0][p][j];
+#pragma unroll
+          for (int c = 0; c < K; ++c) {
+            const float a = net.scl * acc[c][p][j];
+            w0acc[0][j] = fmaf(hj[c][0], a, w0acc[0][j]);
+            w0acc[1][j] = fmaf(hj[c][1], a, w0acc[1][j]);
+            w0acc[2][j] = fmaf(hj[c][2], a, w0acc[2][j]);
+          }
+        }
+      }
+    }
+  }
+
+  if (TRAIN) {
+    // ---------------- fold the per-thread small accumulators (fixed order => deterministic)
+    __syncthreads();
+    float* sc = Hs;  // [5][ROWS][WP]
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const float* src = (q < 3) ? w0acc[q] : (q == 3 ? b0acc : wlacc);
+      float* d = sc + (q * ROWS + row) * WP;
+      *reinterpret_cast<float4*>(d + ua) = make_float4(src[0], src[1], src[2], src[3]);
+      *reinterpret_cast<float4*>(d + WP / 2 + ua) = make_float4(src[4], src[5], src[6], src[7]);
+    }
+    float* sc2 = sc + 5 * ROWS * WP;  // [ROWS]
+    if (ut == 0) sc2[row] = blacc;
+    __syncthreads();
+    for (int idx = tid; idx < 5 * WP; idx += C::NT) {
+      const int q = idx / WP, u = idx % WP;
+      float s = 0.f;
+      for (int r = 0; r < ROWS; ++r) s += sc[(q * ROWS + r) * WP + u];
+      const int dst = (q < 3) ? (net.off_w0 + q * WP + u) : (q == 3 ? net.off_b0 + u : net.off_wl + u);
+      gacc[dst] += s;
+    }
+    if (tid == 0) {
+      float s = 0.f;
+      for (int r = 0; r < ROWS; ++r) s += sc2[r];
+      gacc[net.off_bl] += s;
+    }
+    // loss partial sums per slot
+    double* dsc = reinterpret_cast<double*>(Gs);
+    for (int s = 0; s < L.n_slots; ++s) {
+      __syncthreads();
+      if (ut == 0) dsc[row] = lsum[s];
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int r = 0; r < ROWS; ++r) t += dsc[r];
+        L.loss_part[(size_t)blockIdx.x * L.n_slots + s] += t;
+      }
+    }
+  }
+}

@@ -1,0 +1,349 @@
+"""ctypes binding of libpinn_engine.so (include/pinn_engine.h) and the host-side
+mirror of the reference's operator API for the hot path:
+
+    loss_fun(params, data) -> (loss_n, loss_info)         software.py:318
+    grad(lossf, has_aux=True)(params, data)                software.py:390, 479
+    adam_minimizer(lossf, params, data, opt, opt_state)    software.py:388
+    f(params_1d) -> (loss_value, grads_1d)                 software.py:475
+    f_u(params, z) -> u ; gov_eqn(f_u, z) -> f             software.py:213, 283
+
+There is NO CPU fallback: importing works anywhere (so CPU-only tests can check
+the exported symbols), but creating an engine without the library or without a
+CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .equation import CompiledEquation
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpinn_engine.so")
+_lib = None
+
+EXPORTS = [
+    "pinn_last_error", "pinn_device_count", "pinn_engine_create", "pinn_engine_destroy",
+    "pinn_engine_set_stream", "pinn_engine_num_params", "pinn_engine_num_loss_info",
+    "pinn_engine_tile_points", "pinn_engine_launches_per_eval", "pinn_engine_set_params",
+    "pinn_engine_get_params", "pinn_engine_set_points", "pinn_engine_set_global_counts",
+    "pinn_engine_set_loss", "pinn_engine_loss_grad", "pinn_engine_adam_init", "pinn_engine_adam_steps",
+    "pinn_engine_eval", "pinn_engine_lbfgs", "pinn_nccl_unique_id", "pinn_engine_init_nccl",
+    "pinn_fma_peak", "pinn_engine_last_ms",
+]
+
+
+class PinnSpecC(C.Structure):
+    _fields_ = [
+        ("d_in", C.c_int32), ("feat_mode", C.c_int32), ("n_hidden", C.c_int32), ("width", C.c_int32),
+        ("act_first", C.c_int32), ("act_hidden", C.c_int32), ("scl", C.c_float), ("epsil", C.c_float),
+        ("lb", C.c_float * 3), ("ub", C.c_float * 3), ("n1", C.c_int32), ("n2", C.c_int32), ("mix", C.c_int32),
+        ("n_ops", C.c_int32), ("ops", C.POINTER(C.c_int32)), ("n_consts", C.c_int32),
+        ("consts", C.POINTER(C.c_float)), ("n_aux_col", C.c_int32), ("n_bc", C.c_int32),
+    ]
+
+
+class LbfgsResultC(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("evaluations", C.c_int32), ("converged", C.c_int32),
+                ("failed", C.c_int32), ("final_loss", C.c_double)]
+
+
+EVAL_CB = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int32, C.c_void_p)
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen the C-ABI library and declare signatures. Raises if it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or _LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the B200 engine)")
+    lib = C.CDLL(p)
+    lib.pinn_last_error.restype = C.c_char_p
+    lib.pinn_device_count.restype = C.c_int
+    lib.pinn_engine_create.argtypes = [C.POINTER(PinnSpecC), C.c_int, C.POINTER(C.c_void_p)]
+    lib.pinn_engine_destroy.argtypes = [C.c_void_p]
+    lib.pinn_engine_destroy.restype = None
+    lib.pinn_engine_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pinn_engine_num_params.argtypes = [C.c_void_p]
+    lib.pinn_engine_num_params.restype = C.c_int64
+    lib.pinn_engine_num_loss_info.argtypes = [C.c_void_p]
+    lib.pinn_engine_tile_points.argtypes = [C.c_void_p]
+    lib.pinn_engine_launches_per_eval.argtypes = [C.c_void_p]
+    lib.pinn_engine_set_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.pinn_engine_get_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.pinn_engine_set_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_int64), C.c_int]
+    lib.pinn_engine_set_global_counts.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    lib.pinn_engine_set_loss.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    lib.pinn_engine_loss_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pinn_engine_adam_init.argtypes = [C.c_void_p]
+    lib.pinn_engine_adam_steps.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_void_p]
+    lib.pinn_engine_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int]
+    lib.pinn_engine_lbfgs.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_int32, EVAL_CB, C.c_void_p,
+                                      C.POINTER(LbfgsResultC)]
+    lib.pinn_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.pinn_engine_init_nccl.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+    lib.pinn_fma_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    lib.pinn_engine_last_ms.argtypes = [C.c_void_p]
+    lib.pinn_engine_last_ms.restype = C.c_double
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _check(lib, rc: int):
+    if rc != 0:
+        raise RuntimeError("pinn_engine: " + (lib.pinn_last_error() or b"unknown error").decode())
+
+
+@dataclass
+class NetworkSpec:
+    """sol_pred_create / neural_net arguments (software.py:158-218)."""
+    n_hidden: int
+    width: int
+    lb: Sequence[float]
+    ub: Sequence[float]
+    scl: float = 1.0
+    epsil: float = 1.0
+    act_first: int = 0          # 0 tanh, 1 sin (software.py:170)
+    act_hidden: int = 0         # extension: all-layer sin
+    feature_map: str = "polar"  # 'polar' (reference, software.py:172-175) | 'affine'
+    d_in: int = 2
+
+    @property
+    def n_feat(self) -> int:
+        return 3 if self.feature_map == "polar" else self.d_in
+
+    @property
+    def layer_widths(self) -> List[int]:
+        return [self.n_feat] + self.n_hidden * [self.width] + [1]
+
+    @property
+    def n_params(self) -> int:
+        lw = self.layer_widths
+        return sum(a * b + b for a, b in zip(lw[:-1], lw[1:]))
+
+
+def _ptr(a):
+    """Raw pointer of a numpy array (host) or a torch CUDA tensor (device)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(a.data_ptr())
+
+
+def _is_device(a) -> bool:
+    return a is not None and not isinstance(a, np.ndarray) and getattr(a, "is_cuda", False)
+
+
+def _as_f32(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return np.ascontiguousarray(a, dtype=np.float32)
+    import torch
+
+    if torch.is_tensor(a):
+        if a.is_cuda:
+            return a.contiguous().float() if a.dtype != torch.float32 or not a.is_contiguous() else a
+        return np.ascontiguousarray(a.detach().cpu().numpy(), dtype=np.float32)
+    return np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+
+
+class PinnEngine:
+    """One engine handle = one (network, residual, loss) closure of the reference."""
+
+    def __init__(self, net: NetworkSpec, eq: CompiledEquation, n_bc: int, device: int = 0, lib_path: Optional[str] = None):
+        self.lib = load_library(lib_path)
+        if self.lib.pinn_device_count() <= 0:
+            raise RuntimeError("pinn_engine: no CUDA device (the B200 engine has no CPU fallback)")
+        if eq.d_in != net.d_in:
+            raise ValueError("equation and network disagree on d_in")
+        self.net, self.eq, self.n_bc, self.device = net, eq, n_bc, device
+        spec = PinnSpecC()
+        spec.d_in = net.d_in
+        spec.feat_mode = 1 if net.feature_map == "polar" else 0
+        spec.n_hidden, spec.width = net.n_hidden, net.width
+        spec.act_first, spec.act_hidden = net.act_first, net.act_hidden
+        spec.scl, spec.epsil = float(net.scl), float(net.epsil)
+        for i in range(3):
+            spec.lb[i] = float(net.lb[i]) if i < len(net.lb) else 0.0
+            spec.ub[i] = float(net.ub[i]) if i < len(net.ub) else 1.0
+        spec.n1, spec.n2, spec.mix = eq.n1, eq.n2, eq.mix
+        self._ops = (C.c_int32 * len(eq.ops))(*eq.ops)
+        self._consts = (C.c_float * max(1, len(eq.consts)))(*(eq.consts or [0.0]))
+        spec.n_ops, spec.ops = len(eq.ops), self._ops
+        spec.n_consts, spec.consts = len(eq.consts), self._consts
+        spec.n_aux_col, spec.n_bc = eq.n_aux, n_bc
+        h = C.c_void_p()
+        _check(self.lib, self.lib.pinn_engine_create(C.byref(spec), device, C.byref(h)))
+        self.h = h
+        self.n_params = int(self.lib.pinn_engine_num_params(h))
+        self.n_info = int(self.lib.pinn_engine_num_loss_info(h))
+        self.K = eq.K
+        self._keep = []  # device tensors borrowed by the engine
+        self.lref = 1.0
+        self.lw = 1.0
+
+    # ---- lifetime
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pinn_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: int):
+        _check(self.lib, self.lib.pinn_engine_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    # ---- parameters (ravel_pytree order, software.py:466)
+    def set_params(self, flat):
+        a = _as_f32(flat)
+        n = a.size if isinstance(a, np.ndarray) else a.numel()
+        if n != self.n_params:
+            raise ValueError(f"expected {self.n_params} parameters, got {n}")
+        _check(self.lib, self.lib.pinn_engine_set_params(self.h, _ptr(a), int(_is_device(a))))
+
+    def get_params(self) -> np.ndarray:
+        out = np.empty(self.n_params, dtype=np.float32)
+        _check(self.lib, self.lib.pinn_engine_get_params(self.h, _ptr(out), 0))
+        return out
+
+    # ---- data dict (software.py:572)
+    def set_points(self, x_col, x_bd: Sequence = (), u_bd: Sequence = (), aux_col=None, base_col=None,
+                   base_bd: Optional[Sequence] = None):
+        x_col = _as_f32(x_col)
+        dev = _is_device(x_col)
+        aux_col, base_col = _as_f32(aux_col), _as_f32(base_col)
+        xb = [_as_f32(a) for a in x_bd]
+        ub = [_as_f32(a).reshape(-1) for a in u_bd]
+        bb = [(_as_f32(a).reshape(-1) if a is not None else None) for a in (base_bd or [None] * len(xb))]
+        if dev:
+            for a in [aux_col, base_col] + xb + ub + bb:
+                if a is not None and not _is_device(a):
+                    raise ValueError("mixing host and device buffers in set_points")
+        n_col = x_col.shape[0]
+        n = len(xb)
+        PX = (C.c_void_p * max(1, n))(*[_ptr(a) for a in xb])
+        PU = (C.c_void_p * max(1, n))(*[_ptr(a) for a in ub])
+        PB = (C.c_void_p * max(1, n))(*[_ptr(a) for a in bb])
+        NB = (C.c_int64 * max(1, n))(*[int(a.shape[0]) for a in xb])
+        self._keep = [x_col, aux_col, base_col]
+        _check(self.lib, self.lib.pinn_engine_set_points(self.h, _ptr(x_col), n_col, _ptr(aux_col), _ptr(base_col), n,
+                                                         PX, PU, PB, NB, int(dev)))
+        self.n_col = n_col
+        self.n_bd = [int(a.shape[0]) for a in xb]
+
+    def set_global_counts(self, n_col_global: int, n_bd_global: Sequence[int]):
+        NB = (C.c_int64 * max(1, len(n_bd_global)))(*[int(v) for v in n_bd_global])
+        _check(self.lib, self.lib.pinn_engine_set_global_counts(self.h, int(n_col_global), NB))
+
+    def set_loss(self, lw_eqn: float, lref: float):
+        """loss_fun.lw[0], loss_fun.ref (software.py:381-382)."""
+        self.lw, self.lref = float(lw_eqn), float(lref)
+        _check(self.lib, self.lib.pinn_engine_set_loss(self.h, self.lw, self.lref))
+
+    # ---- grad(lossf, has_aux=True) (software.py:390)
+    def loss_grad(self, params=None, want_grad: bool = True):
+        """Returns (grads_flat float32 [P] of loss/lref, loss_info float64 [3+n_bc+1] un-normalised)."""
+        import torch
+
+        info = np.empty(self.n_info, dtype=np.float64)
+        g = torch.empty(self.n_params, dtype=torch.float32, device=f"cuda:{self.device}") if want_grad else None
+        p = None
+        if params is not None:
+            p = params if _is_device(params) else torch.as_tensor(np.asarray(params, dtype=np.float32)).to(f"cuda:{self.device}")
+        _check(self.lib, self.lib.pinn_engine_loss_grad(self.h, _ptr(p), _ptr(g), _ptr(info)))
+        return g, info
+
+    def loss_fun(self, params=None):
+        """loss_fun(params, data) -> (loss_n, loss_info) (software.py:318-379)."""
+        _, info = self.loss_grad(params, want_grad=False)
+        return info[0] / self.lref, info
+
+    # ---- adam_minimizer (software.py:387-393)
+    def adam_init(self):
+        _check(self.lib, self.lib.pinn_engine_adam_init(self.h))
+
+    def adam_steps(self, n_steps: int, lr: float, want_rows: bool = True) -> Optional[np.ndarray]:
+        rows = np.empty((n_steps, self.n_info), dtype=np.float64) if want_rows else None
+        _check(self.lib, self.lib.pinn_engine_adam_steps(self.h, int(n_steps), float(lr), _ptr(rows)))
+        return rows
+
+    def last_ms(self) -> float:
+        return float(self.lib.pinn_engine_last_ms(self.h))
+
+    # ---- f_u / gov_eqn (software.py:213, 283)
+    def eval(self, z, aux=None, base=None, want_u=True, want_f=True, want_jets=False):
+        z = _as_f32(z)
+        n = z.shape[0]
+        dev = _is_device(z)
+        if dev:
+            import torch
+
+            mk = lambda *s: torch.empty(*s, dtype=torch.float32, device=z.device)
+        else:
+            mk = lambda *s: np.empty(s, dtype=np.float32)
+        u = mk(n) if want_u else None
+        f = mk(n) if want_f else None
+        j = mk(n, self.K) if want_jets else None
+        _check(self.lib, self.lib.pinn_engine_eval(self.h, _ptr(z), n, _ptr(_as_f32(aux)), _ptr(_as_f32(base)),
+                                                   _ptr(u), _ptr(f), _ptr(j), int(dev)))
+        return u, f, j
+
+    # ---- lbfgs_optimizer (software.py:499-514)
+    def lbfgs(self, max_iter: int, tol: float = 1e-10, value_unnormalised: bool = True, on_eval=None):
+        res = LbfgsResultC()
+        rows: List[np.ndarray] = []
+
+        def _cb(ptr, n, user):
+            row = np.array([ptr[i] for i in range(n)], dtype=np.float64)
+            rows.append(row)
+            if on_eval is not None:
+                on_eval(row)
+
+        cb = EVAL_CB(_cb)
+        _check(self.lib, self.lib.pinn_engine_lbfgs(self.h, int(max_iter), float(tol), int(value_unnormalised), cb,
+                                                    None, C.byref(res)))
+        return dict(iterations=res.iterations, evaluations=res.evaluations, converged=bool(res.converged),
+                    failed=bool(res.failed), final_loss=res.final_loss), rows
+
+    # ---- NCCL
+    def init_nccl(self, unique_id: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(self.lib, self.lib.pinn_engine_init_nccl(self.h, buf, rank, world))
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        lib = load_library()
+        buf = (C.c_uint8 * 128)()
+        _check(lib, lib.pinn_nccl_unique_id(buf))
+        return bytes(buf)
+
+
+def fma_peak_tflops(device: int = 0, variant: int = 0) -> float:
+    lib = load_library()
+    out = C.c_double()
+    _check(lib, lib.pinn_fma_peak(device, variant, C.byref(out)))
+    return out.value
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous equal shards: [begin, end) of rank."""
+    base, rem = divmod(n, world)
+    b = rank * base + min(rank, rem)
+    return b, b + base + (1 if rank < rem else 0)

@@ -1,0 +1,500 @@
+"""Symbolic PDE front end: validate, parse and compile the user's equation string.
+
+The reference accepts an ``equation`` string (pinn_app/software.py:627) and then
+ignores it; the only definition of the language is the validation regex at
+pinn_app/callbacks/input_validation.py:29-46 and the tooltip at
+pinn_app/layout.py:114-121.  This module
+
+* ``validate_reference(expr)`` -- hand-written recogniser with the same
+  accept/reject set as that regex (returns True when INVALID, like the callback);
+* ``parse(expr, extended=...)`` -- recursive-descent parser to an AST, either in
+  the strict reference language or with the documented extensions (functions,
+  ``pi``, bare ``t``/``z``, scientific notation, unary minus, nested parentheses,
+  ``^``);
+* ``compile_equation(expr, d_in, ...)`` -- AST -> stack bytecode for the device
+  residual VM (csrc/pinn_common.h ``PinnOp``) plus the jet-channel structure
+  (n1, n2, mix) the fused kernel must carry.
+"""
+from __future__ import annotations
+
+import math
+import string
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+# opcodes -- keep in sync with csrc/pinn_common.h
+OP_CONST, OP_COORD, OP_JET, OP_AUX = 0, 1, 2, 3
+OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG = 4, 5, 6, 7, 8
+OP_POWI, OP_POWF = 9, 10
+OP_SIN, OP_COS, OP_EXP, OP_LOG, OP_TANH, OP_SQRT = 11, 12, 13, 14, 15, 16
+MAX_OPS, MAX_CONSTS, VM_STACK = 192, 48, 12
+
+_FUNC_OPS = {"sin": OP_SIN, "cos": OP_COS, "exp": OP_EXP, "log": OP_LOG, "tanh": OP_TANH, "sqrt": OP_SQRT}
+_LETTERS = set(string.ascii_lowercase)
+
+# jet structures with a kernel instantiation (csrc/jet_configs.txt)
+SUPPORTED_JETS = {1: [(1, 1, 0)], 2: [(2, 1, 0), (2, 2, 0), (2, 2, 1)], 3: [(3, 2, 0)]}
+
+
+class EquationError(ValueError):
+    pass
+
+
+# ------------------------------------------------------------------ tokenizer
+@dataclass
+class Tok:
+    kind: str  # num, name, op, lpar, rpar, comma
+    text: str
+    value: float = 0.0
+
+
+def _tokenize(expr: str, extended: bool) -> List[Tok]:
+    s = "".join(expr.split())
+    toks: List[Tok] = []
+    i, n = 0, len(s)
+    while i < n:
+        ch = s[i]
+        if ch.isdigit() or ch == ".":
+            j = i
+            while j < n and s[j].isdigit():
+                j += 1
+            if j < n and s[j] == ".":
+                j += 1
+                while j < n and s[j].isdigit():
+                    j += 1
+            if s[i:j] == ".":
+                raise EquationError("lone '.'")
+            if extended and j < n and s[j] in "eE":
+                k = j + 1
+                if k < n and s[k] in "+-":
+                    k += 1
+                if k < n and s[k].isdigit():
+                    while k < n and s[k].isdigit():
+                        k += 1
+                    j = k
+            toks.append(Tok("num", s[i:j], float(s[i:j])))
+            i = j
+        elif ch in _LETTERS or ch == "_":
+            j = i
+            while j < n and (s[j] in _LETTERS or s[j] == "_" or (extended and s[j].isdigit() and j > i)):
+                j += 1
+            toks.append(Tok("name", s[i:j]))
+            i = j
+        elif ch == "*":
+            if i + 1 < n and s[i + 1] == "*":
+                toks.append(Tok("op", "**"))
+                i += 2
+            else:
+                toks.append(Tok("op", "*"))
+                i += 1
+        elif ch in "+-/":
+            toks.append(Tok("op", ch))
+            i += 1
+        elif ch == "^" and extended:
+            toks.append(Tok("op", "**"))
+            i += 1
+        elif ch == "(":
+            toks.append(Tok("lpar", ch))
+            i += 1
+        elif ch == ")":
+            toks.append(Tok("rpar", ch))
+            i += 1
+        elif ch == "," and extended:
+            toks.append(Tok("comma", ch))
+            i += 1
+        else:
+            raise EquationError(f"illegal character {ch!r}")
+    return toks
+
+
+# ------------------------------------------------------------------ reference validator
+def _is_ref_var(name: str) -> bool:
+    if name in ("x", "y", "u", "r"):
+        return True
+    if name.startswith("u_") and 1 <= len(name) - 2 <= 2 and all(c in _LETTERS for c in name[2:]):
+        return True
+    return False
+
+
+def _split_ref_names(text: str) -> Optional[List[str]]:
+    """The regex has no separators between tokens other than operators, so a
+    maximal run of letters/underscores must be exactly one variable."""
+    return [text] if _is_ref_var(text) else None
+
+
+def validate_reference(expr: Optional[str]) -> bool:
+    """Same contract as ``on_equation_change`` (input_validation.py:19-50):
+    returns True when the expression is INVALID, False when valid or empty."""
+    if not expr:
+        return False
+    try:
+        toks = _tokenize(expr, extended=False)
+    except EquationError:
+        return True
+    if not toks:
+        return False
+    # grammar: atom (op atom)* ; atom = num | var | '(' token (op token)* ')'
+    pos = 0
+
+    def is_token(t: Tok) -> bool:
+        return t.kind == "num" or (t.kind == "name" and _is_ref_var(t.text))
+
+    def atom() -> bool:
+        nonlocal pos
+        if pos >= len(toks):
+            return False
+        t = toks[pos]
+        if is_token(t):
+            pos += 1
+            return True
+        if t.kind == "lpar":
+            pos += 1
+            if pos >= len(toks) or not is_token(toks[pos]):
+                return False
+            pos += 1
+            while pos < len(toks) and toks[pos].kind == "op":
+                pos += 1
+                if pos >= len(toks) or not is_token(toks[pos]):
+                    return False
+                pos += 1
+            if pos >= len(toks) or toks[pos].kind != "rpar":
+                return False
+            pos += 1
+            return True
+        return False
+
+    if not atom():
+        return True
+    while pos < len(toks):
+        if toks[pos].kind != "op":
+            return True
+        pos += 1
+        if not atom():
+            return True
+    return False
+
+
+# ------------------------------------------------------------------ AST
+@dataclass
+class Node:
+    kind: str  # num, coord, u, du, aux, add, sub, mul, div, neg, pow, call
+    value: float = 0.0
+    name: str = ""
+    args: Tuple["Node", ...] = ()
+
+
+class _Parser:
+    """Precedence climbing: + - < * / < unary - < ** (right assoc), as Python."""
+
+    def __init__(self, toks: List[Tok], extended: bool):
+        self.t, self.i, self.ext = toks, 0, extended
+
+    def peek(self) -> Optional[Tok]:
+        return self.t[self.i] if self.i < len(self.t) else None
+
+    def take(self) -> Tok:
+        tok = self.t[self.i]
+        self.i += 1
+        return tok
+
+    def parse(self) -> Node:
+        node = self.expr()
+        if self.peek() is not None:
+            raise EquationError(f"unexpected {self.peek().text!r}")
+        return node
+
+    def expr(self) -> Node:
+        node = self.term()
+        while (p := self.peek()) is not None and p.kind == "op" and p.text in "+-":
+            op = self.take().text
+            rhs = self.term()
+            node = Node("add" if op == "+" else "sub", args=(node, rhs))
+        return node
+
+    def term(self) -> Node:
+        node = self.unary()
+        while (p := self.peek()) is not None and p.kind == "op" and p.text in ("*", "/"):
+            op = self.take().text
+            rhs = self.unary()
+            node = Node("mul" if op == "*" else "div", args=(node, rhs))
+        return node
+
+    def unary(self) -> Node:
+        p = self.peek()
+        if p is not None and p.kind == "op" and p.text == "-":
+            if not self.ext:
+                raise EquationError("unary minus is not in the reference grammar")
+            self.take()
+            return Node("neg", args=(self.unary(),))
+        if p is not None and p.kind == "op" and p.text == "+" and self.ext:
+            self.take()
+            return self.unary()
+        return self.power()
+
+    def power(self) -> Node:
+        base = self.atom()
+        p = self.peek()
+        if p is not None and p.kind == "op" and p.text == "**":
+            self.take()
+            expo = self.unary() if self.ext else self.power()
+            return Node("pow", args=(base, expo))
+        return base
+
+    def atom(self) -> Node:
+        p = self.peek()
+        if p is None:
+            raise EquationError("unexpected end of expression")
+        if p.kind == "num":
+            self.take()
+            return Node("num", value=p.value)
+        if p.kind == "lpar":
+            self.take()
+            node = self.expr()
+            q = self.peek()
+            if q is None or q.kind != "rpar":
+                raise EquationError("missing ')'")
+            self.take()
+            return node
+        if p.kind == "name":
+            self.take()
+            name = p.text
+            q = self.peek()
+            if self.ext and name in _FUNC_OPS:
+                if q is None or q.kind != "lpar":
+                    raise EquationError(f"{name} needs an argument")
+                self.take()
+                arg = self.expr()
+                q = self.peek()
+                if q is None or q.kind != "rpar":
+                    raise EquationError("missing ')'")
+                self.take()
+                return Node("call", name=name, args=(arg,))
+            if self.ext and name == "pi":
+                return Node("num", value=math.pi)
+            if name == "u":
+                return Node("u")
+            if name.startswith("u_") and 1 <= len(name) - 2 <= 2:
+                return Node("du", name=name[2:])
+            if self.ext and name.startswith("aux") and name[3:].isdigit():
+                return Node("aux", value=float(int(name[3:])))
+            if name in ("x", "y", "r") or (self.ext and name in ("t", "z")):
+                return Node("coord", name=name)
+            raise EquationError(f"unknown name {name!r}")
+        raise EquationError(f"unexpected {p.text!r}")
+
+
+def parse(expr: str, extended: bool = True) -> Node:
+    if not extended and validate_reference(expr):
+        raise EquationError("expression is not in the reference grammar")
+    toks = _tokenize(expr, extended)
+    if not toks:
+        raise EquationError("empty expression")
+    return _Parser(toks, extended).parse()
+
+
+# ------------------------------------------------------------------ compile
+def coord_index(name: str, d_in: int) -> int:
+    """Input column of a coordinate / derivative letter.  Column 0: x or r;
+    column 1: y, or t when there are two inputs; column 2: t or z."""
+    if name in ("x", "r"):
+        return 0
+    if name == "y":
+        if d_in < 2:
+            raise EquationError("'y' needs at least two inputs")
+        return 1
+    if name == "t":
+        if d_in == 1:
+            raise EquationError("'t' needs at least two inputs")
+        return 1 if d_in == 2 else 2
+    if name == "z":
+        if d_in < 3:
+            raise EquationError("'z' needs three inputs")
+        return 2
+    raise EquationError(f"no input column for {name!r}")
+
+
+@dataclass
+class CompiledEquation:
+    expr: str
+    d_in: int
+    n1: int
+    n2: int
+    mix: int
+    ops: List[int] = field(default_factory=list)
+    consts: List[float] = field(default_factory=list)
+    n_aux: int = 0
+    max_stack: int = 0
+
+    @property
+    def K(self) -> int:
+        return 1 + self.n1 + self.n2 + self.mix
+
+    def channel_names(self, names: Sequence[str] = ("x", "y", "t")) -> List[str]:
+        out = ["u"] + [f"u_{names[i]}" for i in range(self.n1)] + [f"u_{names[i]}{names[i]}" for i in range(self.n2)]
+        if self.mix:
+            out.append(f"u_{names[0]}{names[1]}")
+        return out
+
+
+def _collect(node: Node, d_in: int, firsts: set, seconds: set, aux: set):
+    if node.kind == "du":
+        idx = tuple(sorted(coord_index(c, d_in) for c in node.name))
+        if len(idx) == 1:
+            firsts.add(idx[0])
+        else:
+            seconds.add(idx)
+    elif node.kind == "aux":
+        aux.add(int(node.value))
+    for a in node.args:
+        _collect(a, d_in, firsts, seconds, aux)
+
+
+def choose_jets(d_in: int, firsts: set, seconds: set) -> Tuple[int, int, int]:
+    need_n1 = max([i + 1 for i in firsts] + [max(p) + 1 for p in seconds] + [0])
+    pure = [p[0] for p in seconds if p[0] == p[1]]
+    mixed = [p for p in seconds if p[0] != p[1]]
+    need_n2 = max([i + 1 for i in pure] + [0])
+    for m in mixed:
+        if m != (0, 1):
+            raise EquationError("only the mixed derivative of inputs 0 and 1 is supported")
+    need_mix = 1 if mixed else 0
+    for n1, n2, mix in SUPPORTED_JETS[d_in]:
+        if n1 >= need_n1 and n2 >= need_n2 and mix >= need_mix and (not need_mix or n2 >= 2):
+            return n1, n2, mix
+    raise EquationError(
+        f"derivative set first={sorted(firsts)} second={sorted(seconds)} has no kernel instantiation for d_in={d_in}")
+
+
+def compile_equation(expr: str, d_in: int = 2, extended: bool = True) -> CompiledEquation:
+    ast = parse(expr, extended)
+    firsts, seconds, aux = set(), set(), set()
+    _collect(ast, d_in, firsts, seconds, aux)
+    n1, n2, mix = choose_jets(d_in, firsts, seconds)
+    ce = CompiledEquation(expr, d_in, n1, n2, mix, n_aux=(max(aux) + 1 if aux else 0))
+    depth = 0
+
+    def const_index(v: float) -> int:
+        v = float(v)
+        for i, c in enumerate(ce.consts):
+            if c == v:
+                return i
+        ce.consts.append(v)
+        if len(ce.consts) > MAX_CONSTS:
+            raise EquationError("too many distinct constants")
+        return len(ce.consts) - 1
+
+    def emit(op: int, arg: int = 0, delta: int = 0):
+        nonlocal depth
+        ce.ops.append((op & 0xFF) | (int(arg) << 8))
+        depth += delta
+        ce.max_stack = max(ce.max_stack, depth)
+
+    def const_value(n: Node) -> Optional[float]:
+        """Fold constant sub-expressions (exponents like 2, (1/2), -1)."""
+        if n.kind == "num":
+            return n.value
+        if n.kind == "neg":
+            v = const_value(n.args[0])
+            return None if v is None else -v
+        if n.kind in ("add", "sub", "mul", "div", "pow"):
+            a, b = const_value(n.args[0]), const_value(n.args[1])
+            if a is None or b is None:
+                return None
+            try:
+                return {"add": a + b, "sub": a - b, "mul": a * b, "div": a / b, "pow": a ** b}[n.kind]
+            except (ZeroDivisionError, OverflowError, ValueError):
+                return None
+        return None
+
+    def gen(n: Node):
+        cv = const_value(n)
+        if cv is not None:
+            emit(OP_CONST, const_index(cv), +1)
+            return
+        k = n.kind
+        if k == "coord":
+            emit(OP_COORD, coord_index(n.name, d_in), +1)
+        elif k == "u":
+            emit(OP_JET, 0, +1)
+        elif k == "aux":
+            emit(OP_AUX, int(n.value), +1)
+        elif k == "du":
+            idx = tuple(sorted(coord_index(c, d_in) for c in n.name))
+            if len(idx) == 1:
+                ch = 1 + idx[0]
+            elif idx[0] == idx[1]:
+                ch = 1 + n1 + idx[0]
+            else:
+                ch = 1 + n1 + n2
+            emit(OP_JET, ch, +1)
+        elif k in ("add", "sub", "mul", "div"):
+            gen(n.args[0])
+            gen(n.args[1])
+            emit({"add": OP_ADD, "sub": OP_SUB, "mul": OP_MUL, "div": OP_DIV}[k], 0, -1)
+        elif k == "neg":
+            gen(n.args[0])
+            emit(OP_NEG)
+        elif k == "pow":
+            e = const_value(n.args[1])
+            if e is None:
+                raise EquationError("exponent must be a constant")
+            if float(e).is_integer() and 0 <= e <= 64:
+                gen(n.args[0])
+                emit(OP_POWI, int(e))
+            elif float(e).is_integer() and -64 <= e < 0:
+                emit(OP_CONST, const_index(1.0), +1)
+                gen(n.args[0])
+                emit(OP_POWI, int(-e))
+                emit(OP_DIV, 0, -1)
+            else:
+                gen(n.args[0])
+                emit(OP_POWF, const_index(e))
+        elif k == "call":
+            gen(n.args[0])
+            emit(_FUNC_OPS[n.name])
+        else:
+            raise EquationError(f"cannot compile node {k}")
+
+    gen(ast)
+    if len(ce.ops) > MAX_OPS:
+        raise EquationError(f"expression too long ({len(ce.ops)} ops > {MAX_OPS})")
+    if ce.max_stack > VM_STACK:
+        raise EquationError(f"expression too deep (stack {ce.max_stack} > {VM_STACK})")
+    return ce
+
+
+# the hard-coded residual of the reference (software.py:296), in its own language
+REFERENCE_POLAR_LAPLACE = "u_rr + 1/r*u_r + 1/(r**2)*u_tt"
+
+
+def evaluate_host(ce: CompiledEquation, z, jets, aux=None):
+    """Run the bytecode on the host with numpy (float64) -- used by tests to check
+    the compiler, never by the training path."""
+    import numpy as np
+
+    st = []
+    for w in ce.ops:
+        op, arg = w & 0xFF, w >> 8
+        if op == OP_CONST:
+            st.append(np.full(z.shape[0], ce.consts[arg]))
+        elif op == OP_COORD:
+            st.append(z[:, arg].astype(np.float64))
+        elif op == OP_JET:
+            st.append(jets[:, arg].astype(np.float64))
+        elif op == OP_AUX:
+            st.append(aux[:, arg].astype(np.float64))
+        elif op in (OP_ADD, OP_SUB, OP_MUL, OP_DIV):
+            b = st.pop()
+            a = st.pop()
+            st.append({OP_ADD: a + b, OP_SUB: a - b, OP_MUL: a * b, OP_DIV: a / b}[op])
+        elif op == OP_NEG:
+            st.append(-st.pop())
+        elif op == OP_POWI:
+            st.append(st.pop() ** arg)
+        elif op == OP_POWF:
+            st.append(st.pop() ** ce.consts[arg])
+        else:
+            f = {OP_SIN: np.sin, OP_COS: np.cos, OP_EXP: np.exp, OP_LOG: np.log, OP_TANH: np.tanh, OP_SQRT: np.sqrt}[op]
+            st.append(f(st.pop()))
+    assert len(st) == 1
+    return st[0]

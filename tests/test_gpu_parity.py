@@ -1,0 +1,53 @@
+"""GPU parity: the CUDA engine (through the C-ABI) against the float64 oracle on
+the same seeded weights and points.  Tolerance: 1e-5 relative (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_oracle as O
+from tests.helpers import engine_for, make_problem, oracle_loss_grad, rel_err
+
+TOL = 1e-5
+
+CASES = {
+    # id: kwargs for make_problem
+    "R0_polar_6x60": dict(n_hidden=6, width=60, d_in=2, expr="u_rr + 1/r*u_r + 1/(r**2)*u_tt", n_col=1500,
+                          n_bd=100, n_bc=2, lb=[0.1, 0.0], ub=[1.0, 1.0], feature_map="polar", lw=0.05,
+                          coord_names=("r", "t")),
+    "C1_poisson1d_3x20": dict(n_hidden=3, width=20, d_in=1, expr="u_xx + 2", n_col=1000, n_bd=1, n_bc=2,
+                              lb=[0.0], ub=[1.0]),
+    "C2_poisson2d_4x64": dict(n_hidden=4, width=64, d_in=2, expr="u_xx + u_yy + 2*y*(1-y) + 2*x*(1-x)", n_col=3000,
+                              n_bd=300, n_bc=4, lb=[0.0, 0.0], ub=[1.0, 1.0]),
+    "C3_burgers_8x50": dict(n_hidden=8, width=50, d_in=2, expr="u_y + u*u_x - 0.003183*u_xx", n_col=2000, n_bd=200,
+                            n_bc=3, lb=[-1.0, 0.0], ub=[1.0, 1.0]),
+    "C4_helmholtz_sin_6x128": dict(n_hidden=6, width=128, d_in=2, expr="u_xx + u_yy + 9*u - sin(3*x)*sin(2*y)",
+                                   n_col=1000, n_bd=100, n_bc=4, lb=[0.0, 0.0], ub=[1.0, 1.0], act_first=1,
+                                   act_hidden=1, scl=2.0),
+    "C5_heat3d_5x256": dict(n_hidden=5, width=256, d_in=3, expr="u_t - 0.1*(u_xx + u_yy)", n_col=600, n_bd=100,
+                            n_bc=5, lb=[0.0, 0.0, 0.0], ub=[1.0, 1.0, 1.0]),
+    "mixed_2x32": dict(n_hidden=2, width=32, d_in=2, expr="u_xx + 2*u_xy + 3*u_yy - u*u_y + x", n_col=700, n_bd=50,
+                       n_bc=1, lb=[0.0, -1.0], ub=[2.0, 1.0]),
+    "single_hidden_1x16": dict(n_hidden=1, width=16, d_in=2, expr="u_xx + u_y", n_col=300, n_bd=20, n_bc=1,
+                               lb=[0.0, 0.0], ub=[1.0, 1.0]),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_loss_and_grad_match_oracle(name):
+    pb = make_problem(**CASES[name])
+    g_ref, info_ref, f_u, residual = oracle_loss_grad(pb, lref=1.7)
+    eng = engine_for(pb, lref=1.7)
+    g, info = eng.loss_grad()
+    g = g.cpu().numpy()
+    assert info.shape == info_ref.shape
+    assert np.allclose(info, info_ref, rtol=TOL, atol=0), (info, info_ref)
+    assert rel_err(g, g_ref) < TOL, rel_err(g, g_ref)
+    # residual and solution on the collocation points
+    u, f, _ = eng.eval(pb["x_col"].numpy())
+    fu = lambda z: f_u(pb["params"], z)
+    u_ref = fu(pb["x_col"]).numpy()[:, 0]
+    f_ref = (O.gov_eqn(fu, pb["x_col"]) if residual is None else residual(fu, pb["x_col"])).numpy()[:, 0]
+    assert rel_err(u, u_ref) < TOL
+    assert rel_err(f, f_ref) < TOL
+    eng.close()

@@ -125,6 +125,11 @@ int pinn_engine_init_nccl(pinn_engine_t* h, const uint8_t id[128], int32_t rank,
  * returns achieved TFLOP/s; variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2 */
 int pinn_fma_peak(int device, int variant, double* tflops_out);
 
+/* roofline helper: average device time (ms) of the collocation kernel and of the
+ * boundary kernel launched alone, CUDA events on the engine stream, an L2 flush of
+ * flush_bytes between launches. */
+int pinn_engine_time_kernels(pinn_engine_t* h, int32_t reps, int64_t flush_bytes, double* col_ms, double* bc_ms);
+
 /* timing helper: device time (ms) of the last adam_steps / loss_grad call measured
  * with CUDA events on the engine stream */
 double pinn_engine_last_ms(pinn_engine_t* h);

@@ -641,6 +641,47 @@ extern "C" int pinn_engine_eval(pinn_engine_t* h, const float* z, int64_t n, con
   return 0;
 }
 
+// Time the two fused kernels alone (roofline numerator): each launch bracketed by CUDA
+// events on the engine stream, an L2 flush (memset of flush_bytes) between launches.
+extern "C" int pinn_engine_time_kernels(pinn_engine_t* h, int32_t reps, int64_t flush_bytes, double* col_ms,
+                                        double* bc_ms) {
+  CK(cudaSetDevice(h->device));
+  if (!h->points_set) return fail("set_points has not been called");
+  cudaStream_t st = h->stream;
+  const int P = h->fmap.n_params;
+  const int nb = std::max(h->grid_col, h->grid_bc);
+  void* flush = nullptr;
+  if (flush_bytes > 0) CK(cudaMalloc(&flush, (size_t)flush_bytes));
+  k_pack<<<(P + 255) / 256, 256, 0, st>>>(h->fmap, h->d_params, h->d_wpack);
+  double tc = 0.0, tb = 0.0;
+  for (int r = 0; r < reps; ++r) {
+    CK(cudaMemsetAsync(h->d_gacc, 0, sizeof(float) * (size_t)nb * h->net.pg, st));
+    CK(cudaMemsetAsync(h->d_loss_part, 0, sizeof(double) * (size_t)nb * h->n_slots, st));
+    if (flush) CK(cudaMemsetAsync(flush, r & 0xff, (size_t)flush_bytes, st));
+    float ms = 0.f;
+    if (h->Lbc.n_tiles > 0) {
+      CK(cudaEventRecord(h->ev0, st));
+      CK(h->kbc->launch(h->Lbc, true, h->grid_bc, st));
+      CK(cudaEventRecord(h->ev1, st));
+      CK(cudaEventSynchronize(h->ev1));
+      CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+      tb += ms;
+    }
+    if (flush) CK(cudaMemsetAsync(flush, (r + 1) & 0xff, (size_t)flush_bytes, st));
+    CK(cudaEventRecord(h->ev0, st));
+    CK(h->kcol->launch(h->Lcol, true, h->grid_col, st));
+    CK(cudaEventRecord(h->ev1, st));
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    tc += ms;
+  }
+  if (flush) cudaFree(flush);
+  h->timed = false;
+  if (col_ms) *col_ms = tc / reps;
+  if (bc_ms) *bc_ms = tb / reps;
+  return 0;
+}
+
 // ---------------------------------------------------------------- L-BFGS (software.py:499-514)
 namespace {
 struct Phi { double a, f, d; };  // step, value, directional derivative

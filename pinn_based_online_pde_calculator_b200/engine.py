@@ -32,7 +32,7 @@ EXPORTS = [
     "pinn_engine_get_params", "pinn_engine_set_points", "pinn_engine_set_global_counts",
     "pinn_engine_set_loss", "pinn_engine_loss_grad", "pinn_engine_adam_init", "pinn_engine_adam_steps",
     "pinn_engine_eval", "pinn_engine_lbfgs", "pinn_nccl_unique_id", "pinn_engine_init_nccl",
-    "pinn_fma_peak", "pinn_engine_last_ms",
+    "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels",
 ]
 
 
@@ -95,6 +95,8 @@ def load_library(path: Optional[str] = None):
     lib.pinn_fma_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     lib.pinn_engine_last_ms.argtypes = [C.c_void_p]
     lib.pinn_engine_last_ms.restype = C.c_double
+    lib.pinn_engine_time_kernels.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_double),
+                                             C.POINTER(C.c_double)]
     if path is None:
         _lib = lib
     return lib
@@ -286,6 +288,12 @@ class PinnEngine:
 
     def last_ms(self) -> float:
         return float(self.lib.pinn_engine_last_ms(self.h))
+
+    def time_kernels(self, reps: int = 5, flush_bytes: int = 256 << 20):
+        """(col_ms, bc_ms): average device time of each fused kernel launched alone."""
+        a, b = C.c_double(), C.c_double()
+        _check(self.lib, self.lib.pinn_engine_time_kernels(self.h, reps, flush_bytes, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     # ---- f_u / gov_eqn (software.py:213, 283)
     def eval(self, z, aux=None, base=None, want_u=True, want_f=True, want_jets=False):

@@ -132,7 +132,7 @@ def validate_reference(expr: Optional[str]) -> bool:
     except EquationError:
         return True
     if not toks:
-        return False
+        return True  # whitespace only: the regex fails on the stripped empty string
     # grammar: atom (op atom)* ; atom = num | var | '(' token (op token)* ')'
     pos = 0
 

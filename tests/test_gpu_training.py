@@ -1,0 +1,75 @@
+"""run_pinn_training through the same call the Dash callback makes (callbacks/training.py:83-105):
+files, keys, log lines, and convergence on the reference's smoke problem (software.py:1142-1201)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BOUNDARY = {"bd_x1_min": 0.1, "bd_x1_max": 0.1, "bd_y1_min": 0, "bd_y1_max": 1, "bd_u1": 1,
+            "bd_x2_min": 1, "bd_x2_max": 1, "bd_y2_min": 0, "bd_y2_max": 1, "bd_u2": 0}
+KW = dict(equation="test equation", boundary=BOUNDARY, domain={"x_min": 0.1, "x_max": 1, "y_min": 0, "y_max": 1},
+          scl=1, epsil=1, sample_points={"n_col": 3000, "n_bd": 1000, "n_add": 1000},
+          network_size={"depth": 60, "width": 6}, testing_size={"x": 111, "y": 111},
+          equation_weight={"f": 0.05, "df": 0})
+
+FILES = {  # result_graph.py:62-74 names, figures.py keys
+    "collocation_point_1.npz": {"U", "X_col", "limit"}, "collocation_point_2.npz": {"U", "X_col", "limit"},
+    "solution_residual_1.npz": {"r", "t_vec", "U", "F"}, "solution_residual_2.npz": {"r", "t", "U", "F"},
+    "error_1.npz": {"r", "t", "Error"}, "error_2.npz": {"r", "t", "Error"},
+    "loss_1.npz": {"loss"}, "loss_2.npz": {"loss"},
+    "boundary_loss_1.npz": {"loss_xy_l", "loss_xy_r"}, "boundary_loss_2.npz": {"loss_xy_l", "loss_xy_r"},
+    "frequency_spectrum.npz": {"freq_x", "freq_t", "log_mag"},
+}
+
+
+def test_reference_main_smoke_writes_all_outputs(tmp_path, capfd):
+    from pinn_based_online_pde_calculator_b200.software import run_pinn_training
+
+    out = tmp_path / "data" / "test"
+    run_pinn_training(**KW, epochs={"adam": 1, "lbfgs": 1}, output_dir=str(out))
+    for name, keys in FILES.items():
+        z = np.load(out / name)
+        assert set(z.files) == keys, name
+    z = np.load(out / "solution_residual_1.npz")
+    assert z["U"].shape == (111, 111) and z["F"].shape == (111, 111)
+    assert np.load(out / "collocation_point_1.npz")["X_col"].shape == (3000 + 1000 + 200 + 1000, 2)
+    assert np.load(out / "loss_1.npz")["loss"].shape[1] == 3 + 2 + 1
+    cap = capfd.readouterr()
+    assert "Step: 0 | Loss: " in cap.err and " | Loss_d: " in cap.err and " | Loss_e: " in cap.err
+    assert "Step: NaN | Loss: " in cap.out and " Total iterations: " in cap.out
+
+
+def test_training_converges_to_the_analytic_solution(tmp_path):
+    """Polar Laplace with u(0.1)=1, u(1)=0: u* = ln r / ln 0.1 (software.py:815)."""
+    from pinn_based_online_pde_calculator_b200.software import run_pinn_training
+
+    kw = dict(KW, network_size={"depth": 40, "width": 4})
+    res = run_pinn_training(**kw, epochs={"adam": 2000, "lbfgs": 600}, output_dir=str(tmp_path / "run"), stage2=False)
+    err = res["Error1"]
+    exact = np.log(np.linspace(0.1, 1, 111)) / np.log(0.1)
+    rel_l2 = np.sqrt(np.mean(err ** 2)) / np.sqrt(np.mean(exact ** 2))
+    assert rel_l2 < 2e-2, rel_l2
+    loss = res["loss_1"]
+    assert loss[-1, 0] < 1e-2 * loss[0, 0]
+
+
+def test_compiled_equation_is_used_when_it_parses(tmp_path):
+    """Cartesian Poisson u_xx + u_yy = -2 (y(1-y) + x(1-x)) with u=0 on the 4 edges."""
+    from pinn_based_online_pde_calculator_b200.software import run_pinn_training
+
+    bd = {}
+    edges = [(0, 0, 0, 1), (1, 1, 0, 1), (0, 1, 0, 0), (0, 1, 1, 1)]
+    for i, (a, b, c, d) in enumerate(edges, 1):
+        bd.update({f"bd_x{i}_min": a, f"bd_x{i}_max": b, f"bd_y{i}_min": c, f"bd_y{i}_max": d, f"bd_u{i}": 0})
+    exact = lambda X, Y: X * (1 - X) * Y * (1 - Y)
+    res = run_pinn_training(
+        equation="u_xx + u_yy + 2*y*(1-y) + 2*x*(1-x)", boundary=bd, domain={"x_min": 0, "x_max": 1, "y_min": 0, "y_max": 1},
+        scl=1, epsil=1, sample_points={"n_col": 4000, "n_bd": 500, "n_add": 500}, network_size={"depth": 32, "width": 3},
+        testing_size={"x": 51, "y": 51}, epochs={"adam": 1500, "lbfgs": 600}, equation_weight={"f": 1.0, "df": 0},
+        output_dir=str(tmp_path / "poisson"), feature_map="affine", exact_solution=exact, stage2=False)
+    assert res["loss_1"].shape[1] == 3 + 4 + 1
+    X, Y = np.meshgrid(np.linspace(0, 1, 51), np.linspace(0, 1, 51))
+    rel_l2 = np.sqrt(np.mean(res["Error1"] ** 2)) / np.sqrt(np.mean(exact(X, Y) ** 2))
+    assert rel_l2 < 5e-2, rel_l2

@@ -96,7 +96,7 @@ struct pinn_engine {
   LossMeta* d_meta = nullptr;
   int ring_cap = 4096;
   size_t stash_floats = 0;
-  int grid_max = 0;
+  int grid_max = 0, grid_max_col = 0, grid_max_bc = 0;
 
   // points
   PointSet col, bc;
@@ -169,6 +169,7 @@ static int build_layout(pinn_engine* h) {
   int o = 0;
   n.off_w0 = o; o += 4 * WP;
   n.off_b0 = o; o += WP;
+  n.off_b[0] = n.off_b0;
   for (int l = 1; l < s.n_hidden; ++l) {
     n.off_w[l] = o; o += WP * WP;
     n.off_b[l] = o; o += WP;
@@ -223,13 +224,16 @@ extern "C" int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engi
     delete h;
     return fail("no kernel instantiation for WP=%d jets (n1=%d,n2=%d,mix=%d)", wp, spec->n1, spec->n2, spec->mix);
   }
-  cudaError_t e = h->kcol->prepare();
-  if (e == cudaSuccess) e = h->kbc->prepare();
+  int occ_col = 1, occ_bc = 1;
+  cudaError_t e = h->kcol->prepare(&occ_col);
+  if (e == cudaSuccess) e = h->kbc->prepare(&occ_bc);
   if (e != cudaSuccess) { delete h; return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;
-  h->grid_max = h->num_sms;
+  h->grid_max_col = h->num_sms * occ_col;
+  h->grid_max_bc = h->num_sms * occ_bc;
+  h->grid_max = std::max(h->grid_max_col, h->grid_max_bc);
   h->n_slots = spec->n_bc + 1;
   h->n_info = 3 + h->n_slots;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -441,7 +445,7 @@ extern "C" int pinn_engine_set_points(pinn_engine_t* h, const float* x_col, int6
     const int tp = h->kcol->tile_points;
     L.n_tiles = (int)((n_col + tp - 1) / tp);
     L.seg_tile_end[0] = L.n_tiles; L.seg_pt_begin[0] = 0; L.seg_pt_end[0] = n_col; L.seg_slot[0] = h->n_slots - 1;
-    h->grid_col = std::min(L.n_tiles, h->grid_max);
+    h->grid_col = std::min(L.n_tiles, h->grid_max_col);
   }
   fill_launch(h, h->Lbc, h->kbc, h->prog_bc);
   {
@@ -459,7 +463,7 @@ extern "C" int pinn_engine_set_points(pinn_engine_t* h, const float* x_col, int6
       o += nb[i];
     }
     L.n_seg = ns; L.n_tiles = tiles;
-    h->grid_bc = std::min(tiles, h->grid_max);
+    h->grid_bc = std::min(tiles, h->grid_max_bc);
   }
   if (!on_device) CK(cudaStreamSynchronize(h->stream));  // host buffers may be reused by the caller
   h->points_set = true;
@@ -628,7 +632,7 @@ extern "C" int pinn_engine_eval(pinn_engine_t* h, const float* z, int64_t n, con
   const int tp = h->kcol->tile_points;
   L.n_tiles = (int)((n + tp - 1) / tp);
   L.seg_tile_end[0] = L.n_tiles; L.seg_pt_begin[0] = 0; L.seg_pt_end[0] = n; L.seg_slot[0] = 0;
-  cudaError_t e = h->kcol->launch(L, false, std::min(L.n_tiles, h->grid_max), st);
+  cudaError_t e = h->kcol->launch(L, false, std::min(L.n_tiles, h->grid_max_col), st);
   if (e != cudaSuccess) { cleanup(); return fail("eval launch: %s", cudaGetErrorString(e)); }
   if (!on_device) {
     if (u_out) cudaMemcpyAsync(u_out, du, sizeof(float) * n, cudaMemcpyDeviceToHost, st);

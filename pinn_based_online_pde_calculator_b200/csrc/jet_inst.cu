@@ -11,18 +11,23 @@ using Cfg = JetCfg<J_WP, J_N1, J_N2, J_MIX>;
 
 static cudaError_t launch_impl(const PinnLaunch& L, bool train, int grid, cudaStream_t stream) {
   if (train)
-    jet_mlp_kernel<Cfg, true><<<grid, PINN_NT, Cfg::smem_bytes(true), stream>>>(L);
+    jet_mlp_kernel<Cfg, true><<<grid, Cfg::NT, Cfg::smem_bytes(true), stream>>>(L);
   else
-    jet_mlp_kernel<Cfg, false><<<grid, PINN_NT, Cfg::smem_bytes(false), stream>>>(L);
+    jet_mlp_kernel<Cfg, false><<<grid, Cfg::NT, Cfg::smem_bytes(false), stream>>>(L);
   return cudaGetLastError();
 }
 
-static cudaError_t prepare_impl() {
+static cudaError_t prepare_impl(int* ctas_per_sm) {
   cudaError_t e = cudaFuncSetAttribute(jet_mlp_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg::smem_bytes(true));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(jet_mlp_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)Cfg::smem_bytes(false));
+  e = cudaFuncSetAttribute(jet_mlp_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)Cfg::smem_bytes(false));
+  if (e != cudaSuccess) return e;
+  int n = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, jet_mlp_kernel<Cfg, true>, Cfg::NT, Cfg::smem_bytes(true));
+  if (ctas_per_sm) *ctas_per_sm = n < 1 ? 1 : n;
+  return e;
 }
 
 #define CAT_(a, b, c, d) pinn_jet_info_##a##_##b##c##d

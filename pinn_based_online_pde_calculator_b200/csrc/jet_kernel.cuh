@@ -12,29 +12,31 @@
 #include <stdint.h>
 #include "pinn_common.h"
 
-template <int WP_, int N1_, int N2_, int MIX_>
+template <int WP_, int N1_, int N2_, int MIX_, int NT_ = PINN_NT>
 struct JetCfg {
   static constexpr int WP = WP_, N1 = N1_, N2 = N2_, MIX = MIX_;
   static constexpr int K = 1 + N1 + N2 + MIX;   // jet channels
-  static constexpr int NT = PINN_NT, TU = PINN_TU;
+  static constexpr int NT = NT_, TU = PINN_TU;
   static constexpr int UT = WP / TU;            // threads across units
   static constexpr int ROWS = NT / UT;          // thread rows across points
   static constexpr int PT = (K == 1) ? 8 : (K <= 4 ? 3 : 2);  // points per thread
   static constexpr int TP = ROWS * PT;          // points per tile
   static constexpr int SP = K * WP + 4;         // smem stride per point (== 4 mod 32)
-  static constexpr int KC = (2048 / WP) < WP ? (2048 / WP) : WP;  // weight rows per chunk
+  static constexpr int CHUNK_FLOATS = (K >= 6) ? 1024 : 2048;     // 4 KB / 8 KB weight chunks
+  static constexpr int KC = (CHUNK_FLOATS / WP) < WP ? (CHUNK_FLOATS / WP) : WP;  // weight rows per chunk
   static constexpr int NCH = WP / KC;
   static constexpr int WT8 = WP / 8;
   static constexpr int TILES = WT8 * WT8;       // 8x8 wgrad tiles
   static constexpr int NG = TILES <= NT ? NT / TILES : 1;
   static constexpr int NPASS = TILES <= NT ? 1 : TILES / NT;
+  static constexpr int BG = NT >= WP ? NT / WP : 1;   // bias-gradient point groups
   static constexpr int HS_FLOATS = TP * SP;
   static constexpr uint32_t CHUNK_BYTES = KC * WP * 4;
   static_assert(WP % 32 == 0, "padded width must be a multiple of 32");
   static_assert(NG == 1 || NG * WP * WP <= HS_FLOATS, "wgrad scratch must fit in Hs");
   static_assert(5 * NT * 8 + NT <= HS_FLOATS, "final scratch must fit in Hs");
   static constexpr size_t smem_bytes(bool train) {
-    return (size_t)(HS_FLOATS * (train ? 2 : 1) + 2 * KC * WP) * 4 + 64;
+    return (size_t)(HS_FLOATS * (train ? 2 : 1) + 2 * KC * WP + (NT > WP ? NT : WP)) * 4 + 64;
   }
 };
 
@@ -71,16 +73,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------- activations
+// Branch-free tanh, abs error ~1e-7: odd polynomial below 0.25, 1 - 2/(exp(2|x|)+1) above
+// (ex2.approx + rcp.approx, the two MUFU ops), sign restored with copysign.
+__device__ __forceinline__ float tanh_bf(float x) {
+  const float ax = fabsf(x);
+  const float x2 = ax * ax;
+  float p = fmaf(x2, 2.1869488536155203e-2f, -5.3968253968253968e-2f);
+  p = fmaf(x2, p, 1.3333333333333333e-1f);
+  p = fmaf(x2, p, -3.3333333333333333e-1f);
+  p = fmaf(x2 * ax, p, ax);
+  const float e = exp2f(ax * 2.8853900817779268f);
+  const float r = 1.0f - __fdividef(2.0f, e + 1.0f);
+  return copysignf(ax < 0.25f ? p : r, x);
+}
+
+// accurate sincos kept out of line: its slow range-reduction path is large and would be
+// replicated 16x per call site (instruction-cache footprint)
+static __device__ __noinline__ void sincos_ni(float x, float* s, float* c) { sincosf(x, s, c); }
+
 // forward: y = act(a0), d1 = act'(a0), d2 = act''(a0); s0 = value stashed for backward
 __device__ __forceinline__ void act_fwd(int act, float a0, float& y, float& d1, float& d2, float& s0) {
   if (act == PINN_TANH) {
-    y = tanhf(a0);
+    y = tanh_bf(a0);
     d1 = fmaf(-y, y, 1.0f);
     d2 = -2.0f * y * d1;
     s0 = y;
   } else {
     float s, c;
-    sincosf(a0, &s, &c);
+    sincos_ni(a0, &s, &c);
     y = s; d1 = c; d2 = -s; s0 = a0;
   }
 }
@@ -93,7 +113,7 @@ __device__ __forceinline__ void act_bwd(int act, float s0, float& y, float& d1, 
     d3 = d1 * fmaf(6.0f * y, y, -2.0f);
   } else {
     float s, c;
-    sincosf(s0, &s, &c);
+    sincos_ni(s0, &s, &c);
     y = s; d1 = c; d2 = -s; d3 = -c;
   }
 }
@@ -366,15 +386,22 @@ __device__ __forceinline__ int tile_idx(int t, int e) {
 }
 
 // hidden-layer weight gradient for one layer: gW[k][u] += sum_{pt,c} H[pt][c][k] * G[pt][c][u]
-// Hs doubles as cross-group scratch when NG > 1 (callers guarantee the barriers).
+// and gB[u] += sum_pt G[pt][0][u].  Hs doubles as cross-group scratch when NG > 1
+// (callers guarantee Hs/Gs are complete on entry; bsc is a small smem scratch).
 template <class C>
 __device__ __forceinline__ void wgrad_layer(float* __restrict__ Hs, const float* __restrict__ Gs,
-                                            float* __restrict__ gW, float* __restrict__ gB, int tid) {
-  // bias gradient: sum over points of the value-channel adjoint
-  float bsum = 0.f;
-  if (tid < C::WP) {
+                                            float* __restrict__ bsc, float* __restrict__ gW,
+                                            float* __restrict__ gB, int tid) {
+  // bias gradient partials: BG point groups x WP units
+  for (int idx = tid; idx < C::WP * C::BG; idx += C::NT) {
+    const int u = idx % C::WP, g = idx / C::WP;
+    constexpr int PB = C::TP / C::BG;
+    const float* gp = Gs + (g * PB) * C::SP + u;
+    float b0 = 0.f, b1 = 0.f;
 #pragma unroll 4
-    for (int pt = 0; pt < C::TP; ++pt) bsum += Gs[pt * C::SP + tid];
+    for (int pt = 0; pt + 1 < PB; pt += 2) { b0 += gp[pt * C::SP]; b1 += gp[(pt + 1) * C::SP]; }
+    if (PB & 1) b0 += gp[(PB - 1) * C::SP];
+    bsc[idx] = b0 + b1;
   }
 #pragma unroll 1
   for (int pass = 0; pass < C::NPASS; ++pass) {
@@ -442,18 +469,25 @@ __device__ __forceinline__ void wgrad_layer(float* __restrict__ Hs, const float*
       }
     }
   }
-  if (tid < C::WP) gB[tid] += bsum;
+  if (C::NG == 1) __syncthreads();  // bsc complete (the NG > 1 path has synchronised already)
+  for (int u = tid; u < C::WP; u += C::NT) {
+    float b = bsc[u];
+#pragma unroll
+    for (int g = 1; g < C::BG; ++g) b += bsc[g * C::WP + u];
+    gB[u] += b;
+  }
 }
 
 // ---------------------------------------------------------------- the kernel
 template <class C, bool TRAIN>
-__global__ void __launch_bounds__(PINN_NT, 1) jet_mlp_kernel(const __grid_constant__ PinnLaunch L) {
+__global__ void __launch_bounds__(C::NT, (C::NT <= 128) ? 2 : 1) jet_mlp_kernel(const __grid_constant__ PinnLaunch L) {
   constexpr int K = C::K, PT = C::PT, WP = C::WP, SP = C::SP, ROWS = C::ROWS, NCH = C::NCH, KC = C::KC;
   extern __shared__ __align__(128) float smem[];
   float* Hs = smem;
   float* Gs = Hs + C::HS_FLOATS;
   float* Wc = TRAIN ? (Gs + C::HS_FLOATS) : Gs;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(Wc + 2 * KC * WP);
+  float* bsc = Wc + 2 * KC * WP;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(bsc + (C::NT > WP ? C::NT : WP));
 
   const PinnNet& net = L.net;
   const int tid = threadIdx.x;
@@ -496,13 +530,26 @@ __global__ void __launch_bounds__(PINN_NT, 1) jet_mlp_kernel(const __grid_consta
 
   // persistent small-gradient accumulators (first layer, output layer)
   float w0acc[3][8], b0acc[8], wlacc[8], blacc = 0.f;
-  double lsum[PINN_MAX_SEG];
+  double lcur = 0.0;   // loss partial of the current slot
+  int cur_slot = -1;
   if (TRAIN) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { w0acc[0][j] = w0acc[1][j] = w0acc[2][j] = 0.f; b0acc[j] = 0.f; wlacc[j] = 0.f; }
-#pragma unroll
-    for (int s = 0; s < PINN_MAX_SEG; ++s) lsum[s] = 0.0;
   }
+  // per-slot loss partials are folded through smem (fixed order => deterministic)
+  auto flush_loss = [&](int slot) {
+    double* dsc = reinterpret_cast<double*>(Gs);
+    __syncthreads();
+    if (ut == 0) dsc[row] = lcur;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int r = 0; r < ROWS; ++r) t += dsc[r];
+      L.loss_part[(size_t)blockIdx.x * L.n_slots + slot] += t;
+    }
+    __syncthreads();
+    lcur = 0.0;
+  };
 
   // one consumed weight chunk: prefetch the next, wait for this one
   auto chunk_begin = [&]() -> const float* {
@@ -522,6 +569,10 @@ __global__ void __launch_bounds__(PINN_NT, 1) jet_mlp_kernel(const __grid_consta
     const long long rem = L.seg_pt_end[seg] - pbegin;
     const int cnt = rem < C::TP ? (int)rem : C::TP;
     const int slot = L.seg_slot[seg];
+    if (TRAIN && slot != cur_slot) {   // uniform across the CTA
+      if (cur_slot >= 0) flush_loss(cur_slot);
+      cur_slot = slot;
+    }
 
     float z[PT][3];
     long long gp[PT];
@@ -531,54 +582,56 @@ __global__ void __launch_bounds__(PINN_NT, 1) jet_mlp_kernel(const __grid_consta
       const int lp = row + p * ROWS;
       valid[p] = lp < cnt;
       gp[p] = pbegin + (valid[p] ? lp : 0);
-      z[p][0] = z[p][1] = z[p][2] = 0.f;
-      for (int d = 0; d < net.d_in; ++d) z[p][d] = __ldg(L.coords + gp[p] * net.d_in + d);
+      const float* zp = L.coords + gp[p] * net.d_in;
+      z[p][0] = __ldg(zp);
+      z[p][1] = (net.d_in > 1) ? __ldg(zp + 1) : 0.f;
+      z[p][2] = (net.d_in > 2) ? __ldg(zp + 2) : 0.f;
     }
 
     float acc[K][PT][8];
-    // ---------------- first layer: A_c = scl * hjet_c . W0
-    {
-      float w0[3][8];
+    // ---------------- forward through the hidden layers (layer 0 = feature layer)
+#pragma unroll 1
+    for (int l = 0; l < Lh; ++l) {
+      if (l == 0) {
+        // A_c = scl * hjet_c . W0  (software.py:178)
+        float w0[3][8];
 #pragma unroll
-      for (int f = 0; f < 3; ++f) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(L.wpack + net.off_w0 + f * WP + ua));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(L.wpack + net.off_w0 + f * WP + WP / 2 + ua));
-        w0[f][0] = a.x; w0[f][1] = a.y; w0[f][2] = a.z; w0[f][3] = a.w;
-        w0[f][4] = b.x; w0[f][5] = b.y; w0[f][6] = b.z; w0[f][7] = b.w;
-      }
+        for (int f = 0; f < 3; ++f) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(L.wpack + net.off_w0 + f * WP + ua));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(L.wpack + net.off_w0 + f * WP + WP / 2 + ua));
+          w0[f][0] = a.x; w0[f][1] = a.y; w0[f][2] = a.z; w0[f][3] = a.w;
+          w0[f][4] = b.x; w0[f][5] = b.y; w0[f][6] = b.z; w0[f][7] = b.w;
+        }
 #pragma unroll
-      for (int p = 0; p < PT; ++p) {
-        float hj[K][3];
-        feature_jets<C>(net, z[p], hj);
+        for (int p = 0; p < PT; ++p) {
+          float hj[K][3];
+          feature_jets<C>(net, z[p], hj);
+#pragma unroll
+          for (int c = 0; c < K; ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              acc[c][p][j] = net.scl * fmaf(hj[c][0], w0[0][j], fmaf(hj[c][1], w0[1][j], hj[c][2] * w0[2][j]));
+        }
+      } else {
+        __syncthreads();  // previous readers of Hs are done
+        store_tile<C>(Hs, acc, row, ua);
+        __syncthreads();
 #pragma unroll
         for (int c = 0; c < K; ++c)
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            acc[c][p][j] = net.scl * fmaf(hj[c][0], w0[0][j], fmaf(hj[c][1], w0[1][j], hj[c][2] * w0[2][j]));
-      }
-    }
-    act_forward<C, TRAIN>(acc, L.wpack + net.off_b0, net.act_first, stash, row, ua);
-
-    // ---------------- hidden layers
+          for (int p = 0; p < PT; ++p)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[c][p][j] = 0.f;
 #pragma unroll 1
-    for (int l = 1; l < Lh; ++l) {
-      __syncthreads();  // previous readers of Hs are done
-      store_tile<C>(Hs, acc, row, ua);
-      __syncthreads();
-#pragma unroll
-      for (int c = 0; c < K; ++c)
-#pragma unroll
-        for (int p = 0; p < PT; ++p)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[c][p][j] = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < NCH; ++ch) {
-        const float* wc = chunk_begin();
-        gemm_chunk<C>(acc, Hs + row * SP, wc, ua, ch * KC);
-        __syncthreads();
-        ++gpos;
+        for (int ch = 0; ch < NCH; ++ch) {
+          const float* wc = chunk_begin();
+          gemm_chunk<C>(acc, Hs + row * SP, wc, ua, ch * KC);
+          __syncthreads();
+          ++gpos;
+        }
       }
-      act_forward<C, TRAIN>(acc, L.wpack + net.off_b[l], net.act_hidden, stash + l * STL, row, ua);
+      act_forward<C, TRAIN>(acc, L.wpack + net.off_b[l], l == 0 ? net.act_first : net.act_hidden,
+                            stash + l * STL, row, ua);
     }
 
     // ---------------- output layer (software.py:183, 215) + residual program
@@ -609,7 +662,7 @@ __global__ void __launch_bounds__(PINN_NT, 1) jet_mlp_kernel(const __grid_consta
         const float sc = valid[p] ? __ldg(L.seg_scale + slot) : 0.f;
 #pragma unroll
         for (int c = 0; c < K; ++c) ubar[c][p] = sc * f * df[c];
-        if (ut == 0 && valid[p]) lsum[slot] += (double)f * (double)f;
+        if (ut == 0 && valid[p]) lcur += (double)f * (double)f;
       } else {
         if (ut == 0 && valid[p]) {
           if (L.out_u) L.out_u[gp[p]] = u[0];
@@ -635,15 +688,16 @@ __global__ void __launch_bounds__(PINN_NT, 1) jet_mlp_kernel(const __grid_consta
           }
         }
       }
-      // ---------------- backward through the hidden layers
+      // ---------------- backward through the layers
 #pragma unroll 1
-      for (int l = Lh - 1; l >= 1; --l) {
-        act_backward<C>(acc, net.act_hidden, stash + l * STL, row, ua);
+      for (int l = Lh - 1; l >= 0; --l) {
+        act_backward<C>(acc, l == 0 ? net.act_first : net.act_hidden, stash + l * STL, row, ua);
+        if (l == 0) break;
         __syncthreads();  // previous readers of Hs/Gs are done
         store_tile<C>(Gs, acc, row, ua);
         recompute_outputs<C>(Hs, (l - 1 == 0) ? net.act_first : net.act_hidden, stash + (l - 1) * STL, row, ua);
         __syncthreads();
-        wgrad_layer<C>(Hs, Gs, gacc + net.off_w[l], gacc + net.off_b[l], tid);
+        wgrad_layer<C>(Hs, Gs, bsc, gacc + net.off_w[l], gacc + net.off_b[l], tid);
 #pragma unroll
         for (int c = 0; c < K; ++c)
 #pragma unroll
@@ -658,8 +712,7 @@ __global__ void __launch_bounds__(PINN_NT, 1) jet_mlp_kernel(const __grid_consta
           ++gpos;
         }
       }
-      // ---------------- first layer gradients
-      act_backward<C>(acc, net.act_first, stash, row, ua);
+      // ---------------- first layer gradients (acc = adjoint of the first pre-activations)
 #pragma unroll
       for (int p = 0; p < PT; ++p) {
         float hj[K][3];
@@ -680,6 +733,7 @@ __global__ void __launch_bounds__(PINN_NT, 1) jet_mlp_kernel(const __grid_consta
   }
 
   if (TRAIN) {
+    if (cur_slot >= 0) flush_loss(cur_slot);
     // ---------------- fold the per-thread small accumulators (fixed order => deterministic)
     __syncthreads();
     float* sc = Hs;  // [5][ROWS][WP]
@@ -704,18 +758,6 @@ __global__ void __launch_bounds__(PINN_NT, 1) jet_mlp_kernel(const __grid_consta
       float s = 0.f;
       for (int r = 0; r < ROWS; ++r) s += sc2[r];
       gacc[net.off_bl] += s;
-    }
-    // loss partial sums per slot
-    double* dsc = reinterpret_cast<double*>(Gs);
-    for (int s = 0; s < L.n_slots; ++s) {
-      __syncthreads();
-      if (ut == 0) dsc[row] = lsum[s];
-      __syncthreads();
-      if (tid == 0) {
-        double t = 0.0;
-        for (int r = 0; r < ROWS; ++r) t += dsc[r];
-        L.loss_part[(size_t)blockIdx.x * L.n_slots + s] += t;
-      }
     }
   }
 }

@@ -11,7 +11,7 @@ struct JetKernelInfo {
   size_t smem_train, smem_eval;
   size_t stash_floats_per_layer;  // per CTA
   cudaError_t (*launch)(const PinnLaunch& L, bool train, int grid, cudaStream_t stream);
-  cudaError_t (*prepare)();       // opt in to large dynamic shared memory
+  cudaError_t (*prepare)(int* ctas_per_sm);  // opt in to large dynamic smem; resident CTAs per SM (train kernel)
 };
 
 // generated list (jet_registry.cu)

@@ -287,3 +287,132 @@ __global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float s
   for (int i = 0; i < 16; ++i) s += a[i];
   if (s == 12345.678f) out[0] = s;  // keep the loop alive
 }
+
+// GEMM-shaped register pattern: acc[10][8] += a[10] (x) b[8], operands rotated in registers
+// (no memory traffic) -- the FMA-issue ceiling of the fused kernel's inner loop.
+__global__ void __launch_bounds__(256) k_fma_outer(float* out, int iters, float seed) {
+  float acc[10][8], a[10], b[8];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    a[i] = seed + 0.001f * (float)(threadIdx.x + i);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = 1.0f + 1e-6f * (float)(threadIdx.x + j);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a[i] = a[i] * 0.999f;   // keep operands changing (10 FMUL per 80 FFMA)
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += acc[i][j];
+  if (s == 12345.678f) out[0] = s;
+}
+
+
+// same outer product with packed fma.rn.f32x2: acc pairs along j, a duplicated into a pair
+__global__ void __launch_bounds__(256) k_fma2_outer(float* out, int iters, float seed) {
+  unsigned long long acc[10][4], ad[10], bp[4];
+  float a[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    a[i] = seed + 0.001f * (float)(threadIdx.x + i);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float b0 = 1.0f + 1e-6f * (float)(threadIdx.x + 2 * j), b1 = 1.0f + 1e-6f * (float)(threadIdx.x + 2 * j + 1);
+    asm("mov.b64 %0, {%1, %2};" : "=l"(bp[j]) : "f"(b0), "f"(b1));
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) asm("mov.b64 %0, {%1, %1};" : "=l"(ad[i]) : "f"(a[i]));
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i][j]) : "l"(ad[i]), "l"(bp[j]));
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a[i] = a[i] * 0.999f;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x, y;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(acc[i][j]));
+      s += x + y;
+    }
+  if (s == 12345.678f) out[0] = s;
+}
+
+
+// arrangement B: accumulator pairs along the A index; the reused operand is the PAIR,
+// the per-instruction operand is a broadcast scalar
+__global__ void __launch_bounds__(256) k_fma2_outer_b(float* out, int iters, float seed) {
+  unsigned long long acc[5][8], ap[5];
+  float a[10], b[8];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) a[i] = seed + 0.001f * (float)(threadIdx.x + i);
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0ull;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = 1.0f + 1e-6f * (float)(threadIdx.x + j);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(ap[i]) : "f"(a[2 * i]), "f"(a[2 * i + 1]));
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        unsigned long long bb;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b[j]));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i][j]) : "l"(ap[i]), "l"(bb));
+      }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a[i] = a[i] * 0.999f;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x, y;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(acc[i][j]));
+      s += x + y;
+    }
+  if (s == 12345.678f) out[0] = s;
+}
+
+
+// legacy warp-level tensor-core probe: mma.sync m16n8k8 tf32 (SASS HMMA), 8 independent
+// accumulator tiles per warp, to size a 3xTF32 split-GEMM fallback
+__global__ void __launch_bounds__(256) k_mma_tf32_probe(float* out, int iters, float seed) {
+  float c[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f;
+  unsigned a0 = __float_as_uint(seed + threadIdx.x), a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+  unsigned b0 = __float_as_uint(1.0f + 0.001f * threadIdx.x), b1 = b0 + 7;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                   : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0 + i), "r"(b1 + i));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+  if (s == 12345.678f) out[0] = s;
+}

@@ -924,12 +924,18 @@ extern "C" int pinn_fma_peak(int device, int variant, double* tflops_out) {
   for (int rep = 0; rep < 5; ++rep) {
     CK(cudaEventRecord(a));
     if (variant == 0) k_fma_peak<0><<<grid, 256>>>(d, iters, 0.5f);
-    else k_fma_peak<1><<<grid, 256>>>(d, iters, 0.5f);
+    else if (variant == 1) k_fma_peak<1><<<grid, 256>>>(d, iters, 0.5f);
+    else if (variant <= 3) k_fma_outer<<<prop.multiProcessorCount * (variant == 2 ? 1 : 2), 256>>>(d, iters * 2, 0.5f);
+    else if (variant <= 5) k_fma2_outer<<<prop.multiProcessorCount * (variant == 4 ? 1 : 2), 256>>>(d, iters * 2, 0.5f);
+    else if (variant <= 7) k_fma2_outer_b<<<prop.multiProcessorCount * (variant == 6 ? 1 : 2), 256>>>(d, iters * 2, 0.5f);
+    else k_mma_tf32_probe<<<prop.multiProcessorCount * (variant == 8 ? 1 : 2), 256>>>(d, iters * 2, 0.5f);
     CK(cudaEventRecord(b));
     CK(cudaEventSynchronize(b));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, a, b));
-    const double flops = 2.0 * 16 * 8 * (double)iters * 256.0 * grid;
+    const double flops = (variant >= 8) ? 2.0 * 8 * 1024 * (double)(iters * 2) * 8.0 * prop.multiProcessorCount * (variant == 8 ? 1 : 2)
+                       : (variant <= 1) ? 2.0 * 16 * 8 * (double)iters * 256.0 * grid
+                                        : 2.0 * 80 * (double)(iters * 2) * 256.0 * prop.multiProcessorCount * ((variant == 2 || variant == 4 || variant == 6) ? 1 : 2);
     best = std::max(best, flops / (ms * 1e-3) / 1e12);
   }
   cudaEventDestroy(a);

@@ -7,7 +7,10 @@
 #error "compile with -DJ_WP= -DJ_N1= -DJ_N2= -DJ_MIX="
 #endif
 
-using Cfg = JetCfg<J_WP, J_N1, J_N2, J_MIX>;
+#include <type_traits>
+// 256-thread CTAs (4 warps per scheduler at 2 CTAs/SM) where the tile fits, else 128
+using Cfg256 = JetCfg<J_WP, J_N1, J_N2, J_MIX, 256>;
+using Cfg = std::conditional_t<Cfg256::OK, Cfg256, JetCfg<J_WP, J_N1, J_N2, J_MIX, 128>>;
 
 static cudaError_t launch_impl(const PinnLaunch& L, bool train, int grid, cudaStream_t stream) {
   if (train)

@@ -19,24 +19,29 @@ struct JetCfg {
   static constexpr int NT = NT_, TU = PINN_TU;
   static constexpr int UT = WP / TU;            // threads across units
   static constexpr int ROWS = NT / UT;          // thread rows across points
-  static constexpr int PT = (K == 1) ? 8 : (K <= 4 ? 3 : 2);  // points per thread
+  static constexpr int PT = (NT >= 256) ? ((K == 1) ? 4 : (K <= 2 ? 2 : 1))
+                                        : ((K == 1) ? 8 : (K <= 4 ? 3 : 2));  // points per thread
   static constexpr int TP = ROWS * PT;          // points per tile
   static constexpr int SP = K * WP + 4;         // smem stride per point (== 4 mod 32)
   static constexpr int CHUNK_FLOATS = (K >= 6) ? 1024 : 2048;     // 4 KB / 8 KB weight chunks
   static constexpr int KC = (CHUNK_FLOATS / WP) < WP ? (CHUNK_FLOATS / WP) : WP;  // weight rows per chunk
   static constexpr int NCH = WP / KC;
+  static constexpr int TWU = (NT >= 256) ? 4 : 8;  // wgrad thread tile: 8 (k) x TWU (u)
   static constexpr int WT8 = WP / 8;
-  static constexpr int TILES = WT8 * WT8;       // 8x8 wgrad tiles
+  static constexpr int WTU = WP / TWU;
+  static constexpr int TILES = WT8 * WTU;       // 8 x TWU wgrad tiles
   static constexpr int NG = TILES <= NT ? NT / TILES : 1;
   static constexpr int NPASS = TILES <= NT ? 1 : TILES / NT;
   static constexpr int BG = NT >= WP ? NT / WP : 1;   // bias-gradient point groups
   static constexpr int HS_FLOATS = TP * SP;
   static constexpr uint32_t CHUNK_BYTES = KC * WP * 4;
   static_assert(WP % 32 == 0, "padded width must be a multiple of 32");
-  static_assert(NG == 1 || NG * WP * WP <= HS_FLOATS, "wgrad scratch must fit in Hs");
-  static_assert(5 * NT * 8 + NT <= HS_FLOATS, "final scratch must fit in Hs");
+  // wgrad cross-group scratch must fit in Hs, the final small-gradient scratch in Hs+Gs,
+  // point groups must divide the tile
+  static constexpr bool OK = (NG == 1 || NG * WP * WP <= HS_FLOATS) && (5 * ROWS * WP + ROWS <= 2 * HS_FLOATS) &&
+                             (TP % NG == 0) && (TP % BG == 0) && (ROWS >= 1);
   static constexpr size_t smem_bytes(bool train) {
-    return (size_t)(HS_FLOATS * (train ? 2 : 1) + 2 * KC * WP + (NT > WP ? NT : WP)) * 4 + 64;
+    return (size_t)(HS_FLOATS * (train ? 2 : 1) + 2 * KC * WP + (NT > WP ? NT : WP) + PINN_MAX_OPS + PINN_MAX_CONSTS) * 4 + 64;
   }
 };
 
@@ -70,6 +75,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
       "}" ::"r"(smem_u32(b)),
       "r"(parity)
       : "memory");
+}
+
+// packed fp32x2 FMA (Blackwell FFMA2): d.xy = a.xy * b.xy + d.xy.  ptxas folds a {x,x}
+// pack into the scalar-broadcast operand form, so the broadcast costs no instruction.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float x, float y) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(f32x2_t& d, f32x2_t a, f32x2_t b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
 }
 
 // ---------------------------------------------------------------- activations
@@ -119,72 +139,102 @@ __device__ __forceinline__ void act_bwd(int act, float s0, float& y, float& d1, 
 }
 
 // ---------------------------------------------------------------- residual VM
-// Forward-mode dual numbers over the K network-output channels.
-template <int K>
-__device__ __noinline__ void vm_run(const PinnProgram& P, const float* z, const float* aux,
-                                    const float* u, float& f, float* df) {
-  float sv[PINN_VM_STACK];
-  float sd[PINN_VM_STACK][K];
+// Forward-mode dual numbers over the K network-output channels, evaluated for the PT
+// points of a thread in ONE pass over the bytecode (ops/consts staged in shared memory).
+template <int K, int PT>
+__device__ __noinline__ void vm_run(const int* __restrict__ ops, int n_ops, const float* __restrict__ consts,
+                                    const float (*z)[3], const float* const* aux, const float (*u)[PT],
+                                    float* f, float (*df)[PT]) {
+  float sv[PINN_VM_STACK][PT];
+  float sd[PINN_VM_STACK][K][PT];
   int sp = 0;
-  for (int i = 0; i < P.n_ops; ++i) {
-    const int w = P.ops[i];
+  for (int i = 0; i < n_ops; ++i) {
+    const int w = ops[i];
     const int op = w & 0xff, arg = w >> 8;
-    switch (op) {
-      case OP_CONST: sv[sp] = P.consts[arg];
-        for (int c = 0; c < K; ++c) sd[sp][c] = 0.f; ++sp; break;
-      case OP_COORD: sv[sp] = z[arg];
-        for (int c = 0; c < K; ++c) sd[sp][c] = 0.f; ++sp; break;
-      case OP_AUX: sv[sp] = aux[arg];
-        for (int c = 0; c < K; ++c) sd[sp][c] = 0.f; ++sp; break;
-      case OP_JET: sv[sp] = u[arg];
-        for (int c = 0; c < K; ++c) sd[sp][c] = (c == arg) ? 1.f : 0.f; ++sp; break;
-      case OP_ADD: --sp; sv[sp - 1] += sv[sp];
-        for (int c = 0; c < K; ++c) sd[sp - 1][c] += sd[sp][c]; break;
-      case OP_SUB: --sp; sv[sp - 1] -= sv[sp];
-        for (int c = 0; c < K; ++c) sd[sp - 1][c] -= sd[sp][c]; break;
-      case OP_MUL: { --sp; const float a = sv[sp - 1], b = sv[sp];
-        for (int c = 0; c < K; ++c) sd[sp - 1][c] = sd[sp - 1][c] * b + a * sd[sp][c];
-        sv[sp - 1] = a * b; break; }
-      case OP_DIV: { --sp; const float a = sv[sp - 1], b = sv[sp]; const float ib = 1.0f / b;
-        const float q = a * ib;
-        for (int c = 0; c < K; ++c) sd[sp - 1][c] = (sd[sp - 1][c] - q * sd[sp][c]) * ib;
-        sv[sp - 1] = q; break; }
-      case OP_NEG: sv[sp - 1] = -sv[sp - 1];
-        for (int c = 0; c < K; ++c) sd[sp - 1][c] = -sd[sp - 1][c]; break;
-      case OP_POWI: { const float a = sv[sp - 1]; float pm1 = 1.f;  // a^(n-1)
-        for (int q = 1; q < arg; ++q) pm1 *= a;
-        const float dv = (arg == 0) ? 0.f : (float)arg * pm1;
-        sv[sp - 1] = (arg == 0) ? 1.f : pm1 * a;
-        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= dv; break; }
-      case OP_POWF: { const float a = sv[sp - 1], e = P.consts[arg];
-        const float v = powf(a, e); const float dv = e * powf(a, e - 1.0f);
-        sv[sp - 1] = v;
-        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= dv; break; }
-      case OP_SIN: { float s, co; sincosf(sv[sp - 1], &s, &co); sv[sp - 1] = s;
-        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= co; break; }
-      case OP_COS: { float s, co; sincosf(sv[sp - 1], &s, &co); sv[sp - 1] = co;
-        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= -s; break; }
-      case OP_EXP: { const float v = expf(sv[sp - 1]); sv[sp - 1] = v;
-        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= v; break; }
-      case OP_LOG: { const float a = sv[sp - 1]; sv[sp - 1] = logf(a); const float dv = 1.0f / a;
-        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= dv; break; }
-      case OP_TANH: { const float v = tanhf(sv[sp - 1]); sv[sp - 1] = v; const float dv = 1.f - v * v;
-        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= dv; break; }
-      case OP_SQRT: { const float v = sqrtf(sv[sp - 1]); sv[sp - 1] = v; const float dv = 0.5f / v;
-        for (int c = 0; c < K; ++c) sd[sp - 1][c] *= dv; break; }
-      default: break;
+    if (op <= OP_AUX) {  // pushes
+#pragma unroll
+      for (int p = 0; p < PT; ++p) {
+        float v;
+        if (op == OP_CONST) v = consts[arg];
+        else if (op == OP_COORD) v = z[p][arg];
+        else if (op == OP_JET) v = u[arg][p];
+        else v = aux[p][arg];
+        sv[sp][p] = v;
+#pragma unroll
+        for (int c = 0; c < K; ++c) sd[sp][c][p] = (op == OP_JET && c == arg) ? 1.f : 0.f;
+      }
+      ++sp;
+    } else if (op <= OP_DIV) {  // binary
+      --sp;
+#pragma unroll
+      for (int p = 0; p < PT; ++p) {
+        const float a = sv[sp - 1][p], b = sv[sp][p];
+        if (op == OP_ADD) {
+          sv[sp - 1][p] = a + b;
+#pragma unroll
+          for (int c = 0; c < K; ++c) sd[sp - 1][c][p] += sd[sp][c][p];
+        } else if (op == OP_SUB) {
+          sv[sp - 1][p] = a - b;
+#pragma unroll
+          for (int c = 0; c < K; ++c) sd[sp - 1][c][p] -= sd[sp][c][p];
+        } else if (op == OP_MUL) {
+          sv[sp - 1][p] = a * b;
+#pragma unroll
+          for (int c = 0; c < K; ++c) sd[sp - 1][c][p] = fmaf(sd[sp - 1][c][p], b, a * sd[sp][c][p]);
+        } else {
+          const float ib = 1.0f / b, q = a * ib;
+          sv[sp - 1][p] = q;
+#pragma unroll
+          for (int c = 0; c < K; ++c) sd[sp - 1][c][p] = (sd[sp - 1][c][p] - q * sd[sp][c][p]) * ib;
+        }
+      }
+    } else {  // unary: value v and derivative factor dv
+#pragma unroll
+      for (int p = 0; p < PT; ++p) {
+        const float a = sv[sp - 1][p];
+        float v, dv;
+        switch (op) {
+          case OP_NEG: v = -a; dv = -1.f; break;
+          case OP_POWI: { float pm1 = 1.f;
+            for (int q = 1; q < arg; ++q) pm1 *= a;
+            v = (arg == 0) ? 1.f : pm1 * a; dv = (arg == 0) ? 0.f : (float)arg * pm1; break; }
+          case OP_POWF: { const float e = consts[arg]; v = powf(a, e); dv = e * powf(a, e - 1.0f); break; }
+          case OP_SIN: { float s, co; sincosf(a, &s, &co); v = s; dv = co; break; }
+          case OP_COS: { float s, co; sincosf(a, &s, &co); v = co; dv = -s; break; }
+          case OP_EXP: v = expf(a); dv = v; break;
+          case OP_LOG: v = logf(a); dv = 1.0f / a; break;
+          case OP_TANH: v = tanhf(a); dv = 1.f - v * v; break;
+          case OP_SQRT: v = sqrtf(a); dv = 0.5f / v; break;
+          default: v = a; dv = 1.f; break;
+        }
+        sv[sp - 1][p] = v;
+#pragma unroll
+        for (int c = 0; c < K; ++c) sd[sp - 1][c][p] *= dv;
+      }
     }
   }
-  f = sv[0];
-  for (int c = 0; c < K; ++c) df[c] = sd[0][c];
+#pragma unroll
+  for (int p = 0; p < PT; ++p) {
+    f[p] = sv[0][p];
+#pragma unroll
+    for (int c = 0; c < K; ++c) df[c][p] = sd[0][c][p];
+  }
 }
 
 // ---------------------------------------------------------------- building blocks
 // acc[c][p][j] += sum_{k in chunk} S[pt(p)][c][kbase+k] * wc[k][unit(j)]
 // S points at the thread-row's first point; wc at the chunk base (smem).
+// acc[c][p][j] += sum_{k in chunk} S[pt(p)][c][kbase+k] * wc[k][unit(j)]  (packed FFMA2)
 template <class C>
 __device__ __forceinline__ void gemm_chunk(float (&acc)[C::K][C::PT][8], const float* __restrict__ S,
                                            const float* __restrict__ wc, int ua, int kbase) {
+  f32x2_t acc2[C::K][C::PT][4];
+#pragma unroll
+  for (int c = 0; c < C::K; ++c)
+#pragma unroll
+    for (int p = 0; p < C::PT; ++p)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc2[c][p][j] = pack2(acc[c][p][2 * j], acc[c][p][2 * j + 1]);
 #pragma unroll 1
   for (int kk = 0; kk < C::KC; kk += 4) {
     float4 a[C::K][C::PT];
@@ -197,22 +247,26 @@ __device__ __forceinline__ void gemm_chunk(float (&acc)[C::K][C::PT][8], const f
     for (int q = 0; q < 4; ++q) {
       const float4 b0 = *reinterpret_cast<const float4*>(wc + (kk + q) * C::WP + ua);
       const float4 b1 = *reinterpret_cast<const float4*>(wc + (kk + q) * C::WP + C::WP / 2 + ua);
+      const f32x2_t bp0 = pack2(b0.x, b0.y), bp1 = pack2(b0.z, b0.w), bp2 = pack2(b1.x, b1.y), bp3 = pack2(b1.z, b1.w);
 #pragma unroll
       for (int c = 0; c < C::K; ++c)
 #pragma unroll
         for (int p = 0; p < C::PT; ++p) {
           const float av = (q == 0) ? a[c][p].x : (q == 1) ? a[c][p].y : (q == 2) ? a[c][p].z : a[c][p].w;
-          acc[c][p][0] = fmaf(av, b0.x, acc[c][p][0]);
-          acc[c][p][1] = fmaf(av, b0.y, acc[c][p][1]);
-          acc[c][p][2] = fmaf(av, b0.z, acc[c][p][2]);
-          acc[c][p][3] = fmaf(av, b0.w, acc[c][p][3]);
-          acc[c][p][4] = fmaf(av, b1.x, acc[c][p][4]);
-          acc[c][p][5] = fmaf(av, b1.y, acc[c][p][5]);
-          acc[c][p][6] = fmaf(av, b1.z, acc[c][p][6]);
-          acc[c][p][7] = fmaf(av, b1.w, acc[c][p][7]);
+          const f32x2_t aa = pack2(av, av);
+          ffma2(acc2[c][p][0], aa, bp0);
+          ffma2(acc2[c][p][1], aa, bp1);
+          ffma2(acc2[c][p][2], aa, bp2);
+          ffma2(acc2[c][p][3], aa, bp3);
         }
     }
   }
+#pragma unroll
+  for (int c = 0; c < C::K; ++c)
+#pragma unroll
+    for (int p = 0; p < C::PT; ++p)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) unpack2(acc2[c][p][j], acc[c][p][2 * j], acc[c][p][2 * j + 1]);
 }
 
 // store the thread's [K][PT][8] register tile to smem S (point-major, channel, unit)
@@ -407,13 +461,15 @@ __device__ __forceinline__ void wgrad_layer(float* __restrict__ Hs, const float*
   for (int pass = 0; pass < C::NPASS; ++pass) {
     const int tt = (C::NG > 1) ? (tid % C::TILES) : (tid + pass * C::NT);
     const int grp = (C::NG > 1) ? (tid / C::TILES) : 0;
-    const int ki = tt / C::WT8, ui = tt % C::WT8;
+    const int ki = tt / C::WTU, ui = tt % C::WTU;
     constexpr int PPG = C::TP / C::NG;  // points per group
-    float w[8][8];
+    constexpr int TWU = C::TWU;
+    float w[8][TWU];
+    f32x2_t w2[8][TWU / 2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) w[i][j] = 0.f;
+      for (int j = 0; j < TWU / 2; ++j) w2[i][j] = pack2(0.f, 0.f);
     const float* hp = Hs + (grp * PPG) * C::SP + 4 * ki;
     const float* gp = Gs + (grp * PPG) * C::SP + 4 * ui;
 #pragma unroll 1
@@ -423,26 +479,37 @@ __device__ __forceinline__ void wgrad_layer(float* __restrict__ Hs, const float*
         const float4 h0 = *reinterpret_cast<const float4*>(hp + pt * C::SP + c * C::WP);
         const float4 h1 = *reinterpret_cast<const float4*>(hp + pt * C::SP + c * C::WP + C::WP / 2);
         const float4 g0 = *reinterpret_cast<const float4*>(gp + pt * C::SP + c * C::WP);
-        const float4 g1 = *reinterpret_cast<const float4*>(gp + pt * C::SP + c * C::WP + C::WP / 2);
+        float4 g1 = g0;
+        if (TWU == 8) g1 = *reinterpret_cast<const float4*>(gp + pt * C::SP + c * C::WP + C::WP / 2);
         const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const f32x2_t gq[4] = {pack2(g0.x, g0.y), pack2(g0.z, g0.w), pack2(g1.x, g1.y), pack2(g1.z, g1.w)};
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 8; ++i) {
+          const f32x2_t hh = pack2(h[i], h[i]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) w[i][j] = fmaf(h[i], g[j], w[i][j]);
+          for (int j = 0; j < TWU / 2; ++j) ffma2(w2[i][j], hh, gq[j]);
+        }
       }
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < TWU / 2; ++j) unpack2(w2[i][j], w[i][2 * j], w[i][2 * j + 1]);
     if (C::NG == 1) {
       // read-modify-write the CTA-private accumulator directly
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float* d = gW + tile_idx<C>(ki, i) * C::WP;
         float4* d0 = reinterpret_cast<float4*>(d + 4 * ui);
-        float4* d1 = reinterpret_cast<float4*>(d + C::WP / 2 + 4 * ui);
-        float4 v0 = *d0, v1 = *d1;
+        float4 v0 = *d0;
         v0.x += w[i][0]; v0.y += w[i][1]; v0.z += w[i][2]; v0.w += w[i][3];
-        v1.x += w[i][4]; v1.y += w[i][5]; v1.z += w[i][6]; v1.w += w[i][7];
-        *d0 = v0; *d1 = v1;
+        *d0 = v0;
+        if (TWU == 8) {
+          float4* d1 = reinterpret_cast<float4*>(d + C::WP / 2 + 4 * ui);
+          float4 v1 = *d1;
+          v1.x += w[i][TWU - 4]; v1.y += w[i][TWU - 3]; v1.z += w[i][TWU - 2]; v1.w += w[i][TWU - 1];
+          *d1 = v1;
+        }
       }
     } else {
       __syncthreads();  // everyone finished reading Hs
@@ -451,7 +518,9 @@ __device__ __forceinline__ void wgrad_layer(float* __restrict__ Hs, const float*
       for (int i = 0; i < 8; ++i) {
         float* d = sc + tile_idx<C>(ki, i) * C::WP;
         *reinterpret_cast<float4*>(d + 4 * ui) = make_float4(w[i][0], w[i][1], w[i][2], w[i][3]);
-        *reinterpret_cast<float4*>(d + C::WP / 2 + 4 * ui) = make_float4(w[i][4], w[i][5], w[i][6], w[i][7]);
+        if (TWU == 8)
+          *reinterpret_cast<float4*>(d + C::WP / 2 + 4 * ui) =
+              make_float4(w[i][TWU - 4], w[i][TWU - 3], w[i][TWU - 2], w[i][TWU - 1]);
       }
       __syncthreads();
       constexpr int NV = C::WP * C::WP / 4;  // float4 outputs
@@ -480,14 +549,17 @@ __device__ __forceinline__ void wgrad_layer(float* __restrict__ Hs, const float*
 
 // ---------------------------------------------------------------- the kernel
 template <class C, bool TRAIN>
-__global__ void __launch_bounds__(C::NT, (C::NT <= 128) ? 2 : 1) jet_mlp_kernel(const __grid_constant__ PinnLaunch L) {
+__global__ void __launch_bounds__(C::NT, 2) jet_mlp_kernel(const __grid_constant__ PinnLaunch L) {
+  static_assert(C::OK, "invalid kernel configuration");
   constexpr int K = C::K, PT = C::PT, WP = C::WP, SP = C::SP, ROWS = C::ROWS, NCH = C::NCH, KC = C::KC;
   extern __shared__ __align__(128) float smem[];
   float* Hs = smem;
   float* Gs = Hs + C::HS_FLOATS;
   float* Wc = TRAIN ? (Gs + C::HS_FLOATS) : Gs;
   float* bsc = Wc + 2 * KC * WP;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(bsc + (C::NT > WP ? C::NT : WP));
+  int* s_ops = reinterpret_cast<int*>(bsc + (C::NT > WP ? C::NT : WP));
+  float* s_consts = reinterpret_cast<float*>(s_ops + PINN_MAX_OPS);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_consts + PINN_MAX_CONSTS);
 
   const PinnNet& net = L.net;
   const int tid = threadIdx.x;
@@ -516,6 +588,8 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 128) ? 2 : 1) jet_mlp_kernel(
     bulk_g2s(Wc + st * (KC * WP), src, C::CHUNK_BYTES, &mbar[st]);
   };
 
+  for (int i = tid; i < L.prog.n_ops; i += C::NT) s_ops[i] = L.prog.ops[i];
+  for (int i = tid; i < PINN_MAX_CONSTS; i += C::NT) s_consts[i] = L.prog.consts[i];
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
@@ -643,32 +717,36 @@ __global__ void __launch_bounds__(C::NT, (C::NT <= 128) ? 2 : 1) jet_mlp_kernel(
     }
     const float bl = __ldg(L.wpack + net.off_bl);
     float ubar[K][PT];
+    {
+      float u[K][PT], f[PT], df[K][PT];
+      const float* auxp[PT];
 #pragma unroll
-    for (int p = 0; p < PT; ++p) {
-      float u[K];
+      for (int p = 0; p < PT; ++p) {
+        auxp[p] = L.aux ? (L.aux + gp[p] * L.n_aux) : nullptr;
 #pragma unroll
-      for (int c = 0; c < K; ++c) {
-        float s = 0.f;
+        for (int c = 0; c < K; ++c) {
+          float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s = fmaf(acc[c][p][j], wl[j], s);
+          for (int j = 0; j < 8; ++j) s = fmaf(acc[c][p][j], wl[j], s);
 #pragma unroll
-        for (int o = C::UT / 2; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        u[c] = net.epsil * (s + (c == 0 ? bl : 0.f));
-        if (L.base) u[c] += __ldg(L.base + gp[p] * K + c);
+          for (int o = C::UT / 2; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          u[c][p] = net.epsil * (s + (c == 0 ? bl : 0.f));
+          if (L.base) u[c][p] += __ldg(L.base + gp[p] * K + c);
+        }
       }
-      float f, df[K];
-      vm_run<K>(L.prog, z[p], L.aux ? (L.aux + gp[p] * L.n_aux) : nullptr, u, f, df);
-      if (TRAIN) {
-        const float sc = valid[p] ? __ldg(L.seg_scale + slot) : 0.f;
+      vm_run<K, PT>(s_ops, L.prog.n_ops, s_consts, z, auxp, u, f, df);
 #pragma unroll
-        for (int c = 0; c < K; ++c) ubar[c][p] = sc * f * df[c];
-        if (ut == 0 && valid[p]) lcur += (double)f * (double)f;
-      } else {
-        if (ut == 0 && valid[p]) {
-          if (L.out_u) L.out_u[gp[p]] = u[0];
-          if (L.out_f) L.out_f[gp[p]] = f;
+      for (int p = 0; p < PT; ++p) {
+        if (TRAIN) {
+          const float sc = valid[p] ? __ldg(L.seg_scale + slot) : 0.f;
+#pragma unroll
+          for (int c = 0; c < K; ++c) ubar[c][p] = sc * f[p] * df[c][p];
+          if (ut == 0 && valid[p]) lcur += (double)f[p] * (double)f[p];
+        } else if (ut == 0 && valid[p]) {
+          if (L.out_u) L.out_u[gp[p]] = u[0][p];
+          if (L.out_f) L.out_f[gp[p]] = f[p];
           if (L.out_jets)
-            for (int c = 0; c < K; ++c) L.out_jets[gp[p] * K + c] = u[c];
+            for (int c = 0; c < K; ++c) L.out_jets[gp[p] * K + c] = u[c][p];
         }
       }
     }

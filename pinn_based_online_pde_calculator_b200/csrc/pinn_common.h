@@ -9,7 +9,7 @@
 #define PINN_MAX_CONSTS 48
 #define PINN_VM_STACK 12
 #define PINN_MAX_LAYERS 16   // hidden layers
-#define PINN_NT 128          // threads per CTA of the fused kernel (2 CTAs per SM)
+#define PINN_NT 256          // threads per CTA of the fused kernel (2 CTAs per SM, <=128 regs)
 #define PINN_TU 8            // units per thread
 
 enum PinnAct { PINN_TANH = 0, PINN_SIN = 1 };

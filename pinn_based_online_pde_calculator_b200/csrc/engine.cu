@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -138,7 +139,7 @@ static int pad_width(int w) {
   return -1;
 }
 
-static int build_layout(pinn_engine* h) {
+static int build_layout(pinn_engine* h, int ldw) {
   const pinn_spec_t& s = h->spec;
   PinnNet& n = h->net;
   const int WP = pad_width(s.width);
@@ -171,20 +172,20 @@ static int build_layout(pinn_engine* h) {
   n.off_b0 = o; o += WP;
   n.off_b[0] = n.off_b0;
   for (int l = 1; l < s.n_hidden; ++l) {
-    n.off_w[l] = o; o += WP * WP;
+    n.off_w[l] = o; o += WP * ldw;
     n.off_b[l] = o; o += WP;
   }
   n.off_wl = o; o += WP;
   n.off_bl = o; o += 4;
   n.pg = o;
   for (int l = 1; l < s.n_hidden; ++l) {
-    n.off_wt[l] = o; o += WP * WP;
+    n.off_wt[l] = o; o += WP * ldw;
   }
   n.pw = o;
 
   FlatMap& M = h->fmap;
   M.n_layers = s.n_hidden + 1;
-  M.wp = WP;
+  M.wp = ldw;  // row stride of the transposed copy
   int f = 0;
   for (int l = 0; l <= s.n_hidden; ++l) {
     M.in_dim[l] = (l == 0) ? n.n_feat : s.width;
@@ -193,7 +194,7 @@ static int build_layout(pinn_engine* h) {
     f += M.in_dim[l] * M.out_dim[l] + M.out_dim[l];
     if (l == 0) { M.p_w[l] = n.off_w0; M.p_b[l] = n.off_b0; M.ld[l] = WP; M.p_wt[l] = -1; }
     else if (l == s.n_hidden) { M.p_w[l] = n.off_wl; M.p_b[l] = n.off_bl; M.ld[l] = 1; M.p_wt[l] = -1; }
-    else { M.p_w[l] = n.off_w[l]; M.p_b[l] = n.off_b[l]; M.ld[l] = WP; M.p_wt[l] = n.off_wt[l]; }
+    else { M.p_w[l] = n.off_w[l]; M.p_b[l] = n.off_b[l]; M.ld[l] = ldw; M.p_wt[l] = n.off_wt[l]; }
   }
   M.n_params = f;
   return 0;
@@ -216,14 +217,25 @@ extern "C" int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engi
   h->consts.assign(spec->consts, spec->consts + spec->n_consts);
   h->spec.ops = h->ops.data();
   h->spec.consts = h->consts.data();
-  if (build_layout(h)) { delete h; return 1; }
-  h->kcol = pinn_find_kernel(h->net.wp, spec->n1, spec->n2, spec->mix);
-  h->kbc = pinn_find_kernel(h->net.wp, 0, 0, 0);
-  if (!h->kcol || !h->kbc) {
-    const int wp = h->net.wp;
-    delete h;
-    return fail("no kernel instantiation for WP=%d jets (n1=%d,n2=%d,mix=%d)", wp, spec->n1, spec->n2, spec->mix);
+  {
+    // kernel family: PINN_B200_KERNEL = simt | mma | auto (default: the 3xTF32 tensor-core kernel when
+    // it is instantiated for this width and jet structure, else the fp32 SIMT kernel)
+    const int wp = pad_width(spec->width);
+    if (wp < 0) { delete h; return fail("width %d > 256 not supported", spec->width); }
+    const char* env = getenv("PINN_B200_KERNEL");
+    const std::string want = env ? env : "auto";
+    const JetKernelInfo *c1 = pinn_find_kernel(wp, spec->n1, spec->n2, spec->mix, 1), *b1 = pinn_find_kernel(wp, 0, 0, 0, 1);
+    const JetKernelInfo *c0 = pinn_find_kernel(wp, spec->n1, spec->n2, spec->mix, 0), *b0 = pinn_find_kernel(wp, 0, 0, 0, 0);
+    if (want == "mma") { h->kcol = c1; h->kbc = b1; }
+    else if (want == "simt") { h->kcol = c0; h->kbc = b0; }
+    else if (c1 && b1 && wp <= 128) { h->kcol = c1; h->kbc = b1; }  // W=256: fp32 kernel (accumulation depth)
+    else { h->kcol = c0; h->kbc = b0; }
+    if (!h->kcol || !h->kbc) {
+      delete h;
+      return fail("no %s kernel instantiation for WP=%d jets (n1=%d,n2=%d,mix=%d)", want.c_str(), wp, spec->n1, spec->n2, spec->mix);
+    }
   }
+  if (build_layout(h, h->kcol->ldw)) { delete h; return 1; }
   int occ_col = 1, occ_bc = 1;
   cudaError_t e = h->kcol->prepare(&occ_col);
   if (e == cudaSuccess) e = h->kbc->prepare(&occ_bc);
@@ -319,6 +331,7 @@ extern "C" int64_t pinn_engine_num_params(pinn_engine_t* h) { return h->fmap.n_p
 extern "C" int32_t pinn_engine_num_loss_info(pinn_engine_t* h) { return h->n_info; }
 extern "C" int32_t pinn_engine_tile_points(pinn_engine_t* h) { return h->kcol->tile_points; }
 extern "C" int32_t pinn_engine_launches_per_eval(pinn_engine_t* h) { return 6; }
+extern "C" int32_t pinn_engine_kernel_kind(pinn_engine_t* h) { return h->kcol->kind; }
 
 extern "C" int pinn_engine_set_params(pinn_engine_t* h, const float* flat, int on_device) {
   CK(cudaSetDevice(h->device));

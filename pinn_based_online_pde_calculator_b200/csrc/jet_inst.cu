@@ -38,4 +38,4 @@ static cudaError_t prepare_impl(int* ctas_per_sm) {
 
 extern const JetKernelInfo CAT(J_WP, J_N1, J_N2, J_MIX) = {
     J_WP, J_N1, J_N2, J_MIX, Cfg::K, Cfg::TP, Cfg::smem_bytes(true), Cfg::smem_bytes(false),
-    (size_t)Cfg::TP * Cfg::K * Cfg::WP, launch_impl, prepare_impl};
+    (size_t)Cfg::TP * Cfg::K * Cfg::WP, launch_impl, prepare_impl, /*kind=*/0, /*ldw=*/Cfg::WP};

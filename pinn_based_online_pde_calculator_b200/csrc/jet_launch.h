@@ -12,9 +12,11 @@ struct JetKernelInfo {
   size_t stash_floats_per_layer;  // per CTA
   cudaError_t (*launch)(const PinnLaunch& L, bool train, int grid, cudaStream_t stream);
   cudaError_t (*prepare)(int* ctas_per_sm);  // opt in to large dynamic smem; resident CTAs per SM (train kernel)
+  int kind;          // 0: fp32 SIMT (FFMA2) kernel, 1: 3xTF32 mma.sync tensor-core kernel
+  int ldw;           // row stride of the hidden-layer matrices in the weight/gradient pack
 };
 
 // generated list (jet_registry.cu)
-const JetKernelInfo* pinn_find_kernel(int wp, int n1, int n2, int mix);
+const JetKernelInfo* pinn_find_kernel(int wp, int n1, int n2, int mix, int kind);
 int pinn_kernel_count();
 const JetKernelInfo* pinn_kernel_at(int i);

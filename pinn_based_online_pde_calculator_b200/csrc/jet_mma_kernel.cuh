@@ -1,0 +1,667 @@
+// Tensor-core variant of the fused jet-MLP kernel: the three hidden-layer GEMMs per layer
+// (forward A_c = Y_c W, data gradient Ybar = Abar W^T, weight gradient Wbar = Y^T Abar) run on
+// warp-level mma.sync m16n8k8 TF32 (SASS HMMA.1688.F32.TF32) with 3xTF32 error compensation:
+// every operand is split in REGISTERS after the shared-memory load (hi = top 19 bits,
+// lo = x - hi, exact) and a*b is accumulated as hi*hi + lo*hi + hi*lo in fp32.
+// Splitting in registers keeps ONE fp32 copy of the activations in shared memory, which is
+// what lets forward + backward of a point tile stay on chip.
+//
+// Same math, stash, gradient accumulators and launch interface as jet_kernel.cuh; only the
+// thread <-> element mapping follows the mma fragment layout:
+//   lane = 4*g + t ;  thread owns points {16*mw + g, +8} and units {32*nw + 8*nt + 2t, +1}, nt=0..3
+// Shared tiles are [pt][c][k ^ swz(pt)] with stride == 8 (mod 32) and swz = 4*((pt>>2)&1), which
+// makes every fragment load of the three GEMMs bank-conflict free.
+#pragma once
+#include "jet_kernel.cuh"
+
+template <int WP_, int N1_, int N2_, int MIX_, int NT_>
+struct MmaCfg {
+  static constexpr int WP = WP_, N1 = N1_, N2 = N2_, MIX = MIX_;
+  static constexpr int K = 1 + N1 + N2 + MIX;
+  static constexpr int NT = NT_;
+  static constexpr int PT = 2;                  // fragment rows g and g+8
+  static constexpr int NWARP = NT / 32;
+  static constexpr int NW = WP / 32;            // warps across units (32 units = 4 n-tiles each)
+  static constexpr int MW = NWARP / NW;         // warps across points (16 points each)
+  static constexpr int TP = MW * 16;            // points per tile
+  static constexpr int ROWS = TP / 2;           // thread rows (mw, g)
+  static constexpr int SP = K * WP + 8;         // smem point stride == 8 (mod 32)
+  static constexpr int WPS = WP + 8;            // weight row stride (smem chunk and pack)
+  static constexpr int KC = (K >= 6) ? (WP <= 64 ? 16 : 8) : (WP <= 64 ? 32 : (WP <= 128 ? 16 : 8));
+  static constexpr int NCH = WP / KC;
+  static constexpr uint32_t CHUNK_BYTES = KC * WPS * 4;
+  static constexpr int SCR_HALF = ((5 * ROWS * WP + ROWS + 1) / 2 + 3) / 4 * 4;  // final-fold scratch / 2
+  static constexpr int HS_FLOATS = (TP * SP > SCR_HALF) ? TP * SP : SCR_HALF;
+  // weight-gradient work items: (16 k-rows) x (8 n-tiles = 64 units)
+  static constexpr int WITEMS = (WP / 16) * (WP / 64);
+  static constexpr int WPASS = (WITEMS + NWARP - 1) / NWARP;
+  static constexpr bool OK = (WP >= 64) && (NWARP % NW == 0) && (MW >= 1) && (WITEMS % NWARP == 0 || WITEMS < NWARP) &&
+                             (5 * ROWS * WP + ROWS <= 2 * HS_FLOATS);
+  static constexpr size_t smem_bytes(bool train) {
+    return (size_t)(HS_FLOATS * (train ? 2 : 1) + 2 * KC * WPS + WP + PINN_MAX_OPS + PINN_MAX_CONSTS) * 4 + 64;
+  }
+  static constexpr int MINB = (2 * (smem_bytes(true) + 1024) <= 232448) ? 2 : 1;  // resident CTAs per SM
+};
+
+// ---------------------------------------------------------------- tensor-core helpers
+// Veltkamp split with round-to-nearest: hi keeps 11 significant bits (exactly a TF32 value),
+// lo = x - hi is exact.  Rounding (not truncating) keeps the split unbiased, so the residual
+// errors of the 3xTF32 product accumulate like a random walk instead of coherently.
+// __fmul_rn/__fadd_rn are never contracted into FMAs (which would break the split).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  const float t = __fmul_rn(x, 8193.0f);
+  const float h = __fadd_rn(t, -__fadd_rn(t, -x));
+  hi = __float_as_uint(h);
+  lo = __float_as_uint(__fadd_rn(x, -h));
+}
+__device__ __forceinline__ void mma_tf32(float& d0, float& d1, float& d2, float& d3, const uint32_t (&a)[4],
+                                         uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// d += a*b with 3xTF32 compensation
+__device__ __forceinline__ void mma3(float& d0, float& d1, float& d2, float& d3, const uint32_t (&ah)[4],
+                                     const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma_tf32(d0, d1, d2, d3, al, bh0, bh1);
+  mma_tf32(d0, d1, d2, d3, ah, bl0, bl1);
+  mma_tf32(d0, d1, d2, d3, ah, bh0, bh1);
+}
+
+// thread geometry of the fragment layout
+struct MmaGeo {
+  int lane, g, t, mw, nw, row;  // row = 8*mw + g (thread row over points)
+  int pt0;                      // first owned point (second = pt0 + 8)
+  int n0;                       // first unit of the warp (32*nw)
+  int swz;                      // column swizzle of the owned points
+};
+
+// unit index of register slot j8 (0..7): n-tile j8/2, column 2t + j8%2
+#define MMA_UNIT(geo, j8) ((geo).n0 + 8 * ((j8) >> 1) + 2 * (geo).t + ((j8) & 1))
+
+// acc[c][p][2nt+e] += sum_k S[pt(p)][c][kbase+k] * wc[k][n0 + 8nt + 2t'...]  (fragment layout)
+template <class C>
+__device__ __forceinline__ void mma_gemm_chunk(float (&acc)[C::K][2][8], const float* __restrict__ S,
+                                               const float* __restrict__ wc, int kbase, const MmaGeo& G) {
+  const int tA = G.t ^ G.swz, tB = tA ^ 4;
+#pragma unroll 1
+  for (int kk = 0; kk < C::KC; kk += 8) {
+    uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const float* bp = wc + (kk + G.t) * C::WPS + G.n0 + 8 * nt + G.g;
+      split_tf32(bp[0], bh[nt][0], bl[nt][0]);
+      split_tf32(bp[4 * C::WPS], bh[nt][1], bl[nt][1]);
+    }
+    // channels two at a time: 8 independent accumulator tiles per pass keep dependent mmas
+    // eight instructions apart (HMMA latency), small terms first
+#pragma unroll
+    for (int c0 = 0; c0 < C::K; c0 += 2) {
+      constexpr int K_ = C::K;
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        if (c0 + cc < K_) {
+          const float* sp = S + G.pt0 * C::SP + (c0 + cc) * C::WP + kbase + kk;
+          split_tf32(sp[tA], ah[cc][0], al[cc][0]);
+          split_tf32(sp[8 * C::SP + tA], ah[cc][1], al[cc][1]);
+          split_tf32(sp[tB], ah[cc][2], al[cc][2]);
+          split_tf32(sp[8 * C::SP + tB], ah[cc][3], al[cc][3]);
+        }
+      }
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          if (c0 + cc < K_) {
+            const int c = c0 + cc;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              if (pass == 0)
+                mma_tf32(acc[c][0][2 * nt], acc[c][0][2 * nt + 1], acc[c][1][2 * nt], acc[c][1][2 * nt + 1], al[cc], bh[nt][0], bh[nt][1]);
+              else if (pass == 1)
+                mma_tf32(acc[c][0][2 * nt], acc[c][0][2 * nt + 1], acc[c][1][2 * nt], acc[c][1][2 * nt + 1], ah[cc], bl[nt][0], bl[nt][1]);
+              else
+                mma_tf32(acc[c][0][2 * nt], acc[c][0][2 * nt + 1], acc[c][1][2 * nt], acc[c][1][2 * nt + 1], ah[cc], bh[nt][0], bh[nt][1]);
+            }
+          }
+        }
+    }
+  }
+}
+
+// register tile -> smem tile (float2 stores, swizzled columns)
+template <class C>
+__device__ __forceinline__ void mma_store_tile(float* __restrict__ S, const float (&acc)[C::K][2][8],
+                                               const MmaGeo& G) {
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int c = 0; c < C::K; ++c) {
+      float* d = S + (G.pt0 + 8 * p) * C::SP + c * C::WP;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        *reinterpret_cast<float2*>(d + ((G.n0 + 8 * nt + 2 * G.t) ^ G.swz)) =
+            make_float2(acc[c][p][2 * nt], acc[c][p][2 * nt + 1]);
+    }
+}
+
+// thread-private, warp-coalesced stash slot of (c, p, q): float4 holding j8 = 4q..4q+3
+template <class C>
+__device__ __forceinline__ float4* mma_stash_ptr(float* stash_l, int c, int p, int q, int tid) {
+  return reinterpret_cast<float4*>(stash_l) + ((size_t)((c * 2 + p) * 2 + q) * C::NT + tid);
+}
+
+// activation jets, forward (same math as act_forward in jet_kernel.cuh)
+template <class C, bool TRAIN>
+__device__ __forceinline__ void mma_act_forward(float (&acc)[C::K][2][8], const float* __restrict__ bias, int act,
+                                                float* __restrict__ stash_l, const MmaGeo& G, int tid) {
+  float b[8];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(bias + G.n0 + 8 * nt + 2 * G.t));
+    b[2 * nt] = v.x; b[2 * nt + 1] = v.y;
+  }
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    float y[8], d1[8], d2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s0;
+      act_fwd(act, acc[0][p][j] + b[j], y[j], d1[j], d2[j], s0);
+      acc[0][p][j] = s0;
+    }
+    if (TRAIN) {
+#pragma unroll
+      for (int c = 0; c < C::K; ++c) {
+        *mma_stash_ptr<C>(stash_l, c, p, 0, tid) = make_float4(acc[c][p][0], acc[c][p][1], acc[c][p][2], acc[c][p][3]);
+        *mma_stash_ptr<C>(stash_l, c, p, 1, tid) = make_float4(acc[c][p][4], acc[c][p][5], acc[c][p][6], acc[c][p][7]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int i = 0; i < C::N2; ++i) {
+        const float Ai = acc[1 + i][p][j];
+        acc[1 + C::N1 + i][p][j] = fmaf(d2[j] * Ai, Ai, d1[j] * acc[1 + C::N1 + i][p][j]);
+      }
+      if (C::MIX)
+        acc[C::K - 1][p][j] = fmaf(d2[j] * acc[1][p][j], acc[2][p][j], d1[j] * acc[C::K - 1][p][j]);
+#pragma unroll
+      for (int i = 0; i < C::N1; ++i) acc[1 + i][p][j] *= d1[j];
+      acc[0][p][j] = y[j];
+    }
+  }
+}
+
+template <class C>
+__device__ __forceinline__ void mma_load_stash(float (&st)[C::K][8], const float* __restrict__ stash_l, int p, int tid) {
+#pragma unroll
+  for (int c = 0; c < C::K; ++c) {
+    const float4 v0 = *mma_stash_ptr<C>(const_cast<float*>(stash_l), c, p, 0, tid);
+    const float4 v1 = *mma_stash_ptr<C>(const_cast<float*>(stash_l), c, p, 1, tid);
+    st[c][0] = v0.x; st[c][1] = v0.y; st[c][2] = v0.z; st[c][3] = v0.w;
+    st[c][4] = v1.x; st[c][5] = v1.y; st[c][6] = v1.z; st[c][7] = v1.w;
+  }
+}
+
+// adjoint of the activation jets (same math as act_backward)
+template <class C>
+__device__ __forceinline__ void mma_act_backward(float (&acc)[C::K][2][8], int act, const float* __restrict__ stash_l,
+                                                 int tid) {
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    float st[C::K][8];
+    mma_load_stash<C>(st, stash_l, p, tid);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y, d1, d2, d3;
+      act_bwd(act, st[0][j], y, d1, d2, d3);
+      float ab0 = d1 * acc[0][p][j];
+      float ab1[C::N1 > 0 ? C::N1 : 1];
+#pragma unroll
+      for (int i = 0; i < C::N1; ++i) {
+        const float yb = acc[1 + i][p][j];
+        ab1[i] = d1 * yb;
+        ab0 = fmaf(d2 * st[1 + i][j], yb, ab0);
+      }
+#pragma unroll
+      for (int i = 0; i < C::N2; ++i) {
+        const float yb = acc[1 + C::N1 + i][p][j];
+        const float Ai = st[1 + i][j], Aii = st[1 + C::N1 + i][j];
+        acc[1 + C::N1 + i][p][j] = d1 * yb;
+        ab1[i] = fmaf(2.0f * d2 * Ai, yb, ab1[i]);
+        ab0 = fmaf(fmaf(d3 * Ai, Ai, d2 * Aii), yb, ab0);
+      }
+      if (C::MIX) {
+        const float yb = acc[C::K - 1][p][j];
+        const float A0 = st[1][j], A1 = st[2][j], A01 = st[C::K - 1][j];
+        acc[C::K - 1][p][j] = d1 * yb;
+        ab1[0] = fmaf(d2 * A1, yb, ab1[0]);
+        ab1[C::N1 > 1 ? 1 : 0] = fmaf(d2 * A0, yb, ab1[C::N1 > 1 ? 1 : 0]);
+        ab0 = fmaf(fmaf(d3 * A0, A1, d2 * A01), yb, ab0);
+      }
+#pragma unroll
+      for (int i = 0; i < C::N1; ++i) acc[1 + i][p][j] = ab1[i];
+      acc[0][p][j] = ab0;
+    }
+  }
+}
+
+// recompute a layer's output jets from its stash into the smem tile S
+template <class C>
+__device__ __forceinline__ void mma_recompute_outputs(float* __restrict__ S, int act, const float* __restrict__ stash_l,
+                                                      const MmaGeo& G, int tid) {
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    float st[C::K][8];
+    mma_load_stash<C>(st, stash_l, p, tid);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y, d1, d2, d3;
+      act_bwd(act, st[0][j], y, d1, d2, d3);
+#pragma unroll
+      for (int i = 0; i < C::N2; ++i) {
+        const float Ai = st[1 + i][j];
+        st[1 + C::N1 + i][j] = fmaf(d2 * Ai, Ai, d1 * st[1 + C::N1 + i][j]);
+      }
+      if (C::MIX) st[C::K - 1][j] = fmaf(d2 * st[1][j], st[2][j], d1 * st[C::K - 1][j]);
+#pragma unroll
+      for (int i = 0; i < C::N1; ++i) st[1 + i][j] *= d1;
+      st[0][j] = y;
+    }
+#pragma unroll
+    for (int c = 0; c < C::K; ++c) {
+      float* d = S + (G.pt0 + 8 * p) * C::SP + c * C::WP;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        *reinterpret_cast<float2*>(d + ((G.n0 + 8 * nt + 2 * G.t) ^ G.swz)) = make_float2(st[c][2 * nt], st[c][2 * nt + 1]);
+    }
+  }
+}
+
+// weight gradient of one hidden layer on tensor cores:
+//   gW[k][u] += sum_{pt,c} H[pt][c][k] * G[pt][c][u],  gB[u] += sum_pt G[pt][0][u]
+template <class C>
+__device__ __forceinline__ void mma_wgrad_layer(const float* __restrict__ Hs, const float* __restrict__ Gs,
+                                                float* __restrict__ bsc, float* __restrict__ gW,
+                                                float* __restrict__ gB, int tid, const MmaGeo& G) {
+  // bias gradient: thread u sums the value-channel adjoint over the tile's points
+  for (int u = tid; u < C::WP; u += C::NT) {
+    float b0 = 0.f, b1 = 0.f;
+#pragma unroll 4
+    for (int pt = 0; pt < C::TP; pt += 2) {
+      b0 += Gs[pt * C::SP + (u ^ (((pt >> 2) & 1) << 2))];
+      b1 += Gs[(pt + 1) * C::SP + (u ^ ((((pt + 1) >> 2) & 1) << 2))];
+    }
+    gB[u] += b0 + b1;
+  }
+  (void)bsc;
+  const int warp = tid >> 5;
+#pragma unroll 1
+  for (int item = warp; item < C::WITEMS; item += C::NWARP) {
+    const int mt = item / (C::WP / 64), ng = item % (C::WP / 64);
+    const int k0 = 16 * mt, u0 = 64 * ng;
+    float w[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) w[nt][0] = w[nt][1] = w[nt][2] = w[nt][3] = 0.f;
+#pragma unroll 1
+    for (int ps = 0; ps < C::TP / 8; ++ps) {
+      const int pa = 8 * ps + G.t, pb = pa + 4;  // swizzle 0 for pa, 4 for pb
+#pragma unroll
+      for (int c = 0; c < C::K; ++c) {
+        const float* ha = Hs + pa * C::SP + c * C::WP;
+        const float* hb = Hs + pb * C::SP + c * C::WP;
+        uint32_t ah[4], al[4];
+        split_tf32(ha[k0 + G.g], ah[0], al[0]);
+        split_tf32(ha[k0 + G.g + 8], ah[1], al[1]);
+        split_tf32(hb[(k0 + G.g) ^ 4], ah[2], al[2]);
+        split_tf32(hb[(k0 + G.g + 8) ^ 4], ah[3], al[3]);
+        const float* ga = Gs + pa * C::SP + c * C::WP + u0 + G.g;
+        const float* gb = Gs + pb * C::SP + c * C::WP + ((u0 + G.g) ^ 4);
+        uint32_t bh[8][2], bl[8][2];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          split_tf32(ga[8 * nt], bh[nt][0], bl[nt][0]);
+          split_tf32(gb[8 * nt], bh[nt][1], bl[nt][1]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) mma_tf32(w[nt][0], w[nt][1], w[nt][2], w[nt][3], al, bh[nt][0], bh[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) mma_tf32(w[nt][0], w[nt][1], w[nt][2], w[nt][3], ah, bl[nt][0], bl[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) mma_tf32(w[nt][0], w[nt][1], w[nt][2], w[nt][3], ah, bh[nt][0], bh[nt][1]);
+      }
+    }
+    // read-modify-write the CTA-private accumulator (rows k0+g, k0+g+8; cols u0+8nt+2t, +1)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float2* d0 = reinterpret_cast<float2*>(gW + (size_t)(k0 + G.g) * C::WPS + u0 + 8 * nt + 2 * G.t);
+      float2* d1 = reinterpret_cast<float2*>(gW + (size_t)(k0 + G.g + 8) * C::WPS + u0 + 8 * nt + 2 * G.t);
+      float2 v0 = *d0, v1 = *d1;
+      v0.x += w[nt][0]; v0.y += w[nt][1];
+      v1.x += w[nt][2]; v1.y += w[nt][3];
+      *d0 = v0; *d1 = v1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- the kernel
+template <class C, bool TRAIN>
+__global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_constant__ PinnLaunch L) {
+  static_assert(C::OK, "invalid mma kernel configuration");
+  constexpr int K = C::K, WP = C::WP, NCH = C::NCH, KC = C::KC, WPS = C::WPS;
+  extern __shared__ __align__(128) float smem[];
+  float* Hs = smem;
+  float* Gs = Hs + C::HS_FLOATS;
+  float* Wc = TRAIN ? (Gs + C::HS_FLOATS) : Gs;
+  float* bsc = Wc + 2 * KC * WPS;
+  int* s_ops = reinterpret_cast<int*>(bsc + WP);
+  float* s_consts = reinterpret_cast<float*>(s_ops + PINN_MAX_OPS);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_consts + PINN_MAX_CONSTS);
+
+  const PinnNet& net = L.net;
+  const int tid = threadIdx.x;
+  MmaGeo G;
+  G.lane = tid & 31; G.g = G.lane >> 2; G.t = G.lane & 3;
+  const int warp = tid >> 5;
+  G.nw = warp % C::NW; G.mw = warp / C::NW;
+  G.row = 8 * G.mw + G.g;
+  G.pt0 = 16 * G.mw + G.g;
+  G.n0 = 32 * G.nw;
+  G.swz = ((G.g >> 2) & 1) << 2;
+  const int Lh = net.n_hidden;
+  const int nF = (Lh - 1) * NCH;
+  const int S = TRAIN ? 2 * nF : nF;
+  const int my_tiles = (L.n_tiles > (int)blockIdx.x) ? (L.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const long long total = (long long)my_tiles * S;
+  long long gpos = 0;
+
+  auto issue = [&](long long gq) {
+    const int p = (int)(gq % S);
+    const float* src;
+    if (p < nF) {
+      const int l = 1 + p / NCH, ch = p % NCH;
+      src = L.wpack + net.off_w[l] + ch * (KC * WPS);
+    } else {
+      const int q = p - nF;
+      const int l = (Lh - 1) - q / NCH, ch = q % NCH;
+      src = L.wpack + net.off_wt[l] + ch * (KC * WPS);
+    }
+    const int st = (int)(gq & 1);
+    mbar_expect_tx(&mbar[st], C::CHUNK_BYTES);
+    bulk_g2s(Wc + st * (KC * WPS), src, C::CHUNK_BYTES, &mbar[st]);
+  };
+
+  for (int i = tid; i < L.prog.n_ops; i += C::NT) s_ops[i] = L.prog.ops[i];
+  for (int i = tid; i < PINN_MAX_CONSTS; i += C::NT) s_consts[i] = L.prog.consts[i];
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0 && total > 0) issue(0);
+
+  constexpr size_t STL = (size_t)C::TP * K * WP;  // stash floats per layer (= K*16*NT)
+  float* stash = TRAIN ? (L.stash + (size_t)blockIdx.x * Lh * STL) : nullptr;
+  float* gacc = TRAIN ? (L.gacc + (size_t)blockIdx.x * net.pg) : nullptr;
+
+  float w0acc[3][8], b0acc[8], wlacc[8], blacc = 0.f;
+  double lcur = 0.0;
+  int cur_slot = -1;
+  if (TRAIN) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { w0acc[0][j] = w0acc[1][j] = w0acc[2][j] = 0.f; b0acc[j] = 0.f; wlacc[j] = 0.f; }
+  }
+  auto flush_loss = [&](int slot) {
+    double* dsc = reinterpret_cast<double*>(Gs);
+    __syncthreads();
+    if (G.t == 0 && G.nw == 0) { dsc[2 * G.row] = lcur; }
+    __syncthreads();
+    if (tid == 0) {
+      double tsum = 0.0;
+      for (int r = 0; r < C::ROWS; ++r) tsum += dsc[2 * r];
+      L.loss_part[(size_t)blockIdx.x * L.n_slots + slot] += tsum;
+    }
+    __syncthreads();
+    lcur = 0.0;
+  };
+  auto chunk_begin = [&]() -> const float* {
+    if (tid == 0 && gpos + 1 < total) issue(gpos + 1);
+    const int st = (int)(gpos & 1);
+    mbar_wait(&mbar[st], (uint32_t)((gpos >> 1) & 1));
+    return Wc + st * (KC * WPS);
+  };
+
+#pragma unroll 1
+  for (int it = 0; it < my_tiles; ++it) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    int seg = 0;
+    while (seg + 1 < L.n_seg && tile >= L.seg_tile_end[seg]) ++seg;
+    const int tile0 = seg ? L.seg_tile_end[seg - 1] : 0;
+    const long long pbegin = L.seg_pt_begin[seg] + (long long)(tile - tile0) * C::TP;
+    const long long rem = L.seg_pt_end[seg] - pbegin;
+    const int cnt = rem < C::TP ? (int)rem : C::TP;
+    const int slot = L.seg_slot[seg];
+    if (TRAIN && slot != cur_slot) {
+      if (cur_slot >= 0) flush_loss(cur_slot);
+      cur_slot = slot;
+    }
+
+    float z[2][3];
+    long long gp[2];
+    bool valid[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const int lp = G.pt0 + 8 * p;
+      valid[p] = lp < cnt;
+      gp[p] = pbegin + (valid[p] ? lp : 0);
+      const float* zp = L.coords + gp[p] * net.d_in;
+      z[p][0] = __ldg(zp);
+      z[p][1] = (net.d_in > 1) ? __ldg(zp + 1) : 0.f;
+      z[p][2] = (net.d_in > 2) ? __ldg(zp + 2) : 0.f;
+    }
+
+    float acc[K][2][8];
+#pragma unroll 1
+    for (int l = 0; l < Lh; ++l) {
+      if (l == 0) {
+        float w0[3][8];
+#pragma unroll
+        for (int f = 0; f < 3; ++f)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(L.wpack + net.off_w0 + f * WP + G.n0 + 8 * nt + 2 * G.t));
+            w0[f][2 * nt] = v.x; w0[f][2 * nt + 1] = v.y;
+          }
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          float hj[K][3];
+          feature_jets<C>(net, z[p], hj);
+#pragma unroll
+          for (int c = 0; c < K; ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              acc[c][p][j] = net.scl * fmaf(hj[c][0], w0[0][j], fmaf(hj[c][1], w0[1][j], hj[c][2] * w0[2][j]));
+        }
+      } else {
+        __syncthreads();
+        mma_store_tile<C>(Hs, acc, G);
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+          for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[c][p][j] = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+          const float* wc = chunk_begin();
+          mma_gemm_chunk<C>(acc, Hs, wc, ch * KC, G);
+          __syncthreads();
+          ++gpos;
+        }
+      }
+      mma_act_forward<C, TRAIN>(acc, L.wpack + net.off_b[l], l == 0 ? net.act_first : net.act_hidden,
+                                stash + l * STL, G, tid);
+    }
+
+    // ---------------- output layer + residual program
+    float wl[8];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(L.wpack + net.off_wl + G.n0 + 8 * nt + 2 * G.t));
+      wl[2 * nt] = v.x; wl[2 * nt + 1] = v.y;
+    }
+    const float bl = __ldg(L.wpack + net.off_bl);
+    float ubar[K][2];
+    {
+      // partial dots over the thread's 8 units -> reduce over the 4 t-lanes (shuffle) and the NW warps (smem)
+      float u[K][2], f[2], df[K][2];
+      const float* auxp[2];
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s = fmaf(acc[c][p][j], wl[j], s);
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          u[c][p] = s;
+        }
+      if (C::NW > 1) {
+        // cross-warp fold through smem: part[nw][pt][c]
+        float* part = Hs;  // the last GEMM that read Hs has completed (barrier after its last chunk)
+        __syncthreads();
+        if (G.t == 0) {
+#pragma unroll
+          for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int c = 0; c < K; ++c) part[(G.nw * C::TP + G.pt0 + 8 * p) * K + c] = u[c][p];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+          for (int c = 0; c < K; ++c) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < C::NW; ++w) s += part[(w * C::TP + G.pt0 + 8 * p) * K + c];
+            u[c][p] = s;
+          }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        auxp[p] = L.aux ? (L.aux + gp[p] * L.n_aux) : nullptr;
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          u[c][p] = net.epsil * (u[c][p] + (c == 0 ? bl : 0.f));
+          if (L.base) u[c][p] += __ldg(L.base + gp[p] * K + c);
+        }
+      }
+      vm_run<K, 2>(s_ops, L.prog.n_ops, s_consts, z, auxp, u, f, df);
+      const bool owner = (G.t == 0 && G.nw == 0);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        if (TRAIN) {
+          const float sc = valid[p] ? __ldg(L.seg_scale + slot) : 0.f;
+#pragma unroll
+          for (int c = 0; c < K; ++c) ubar[c][p] = sc * f[p] * df[c][p];
+          if (owner && valid[p]) lcur += (double)f[p] * (double)f[p];
+        } else if (owner && valid[p]) {
+          if (L.out_u) L.out_u[gp[p]] = u[0][p];
+          if (L.out_f) L.out_f[gp[p]] = f[p];
+          if (L.out_jets)
+            for (int c = 0; c < K; ++c) L.out_jets[gp[p] * K + c] = u[c][p];
+        }
+      }
+    }
+
+    if (TRAIN) {
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        if (G.t == 0 && G.nw == 0) blacc += net.epsil * ubar[0][p];
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const float e = net.epsil * ubar[c][p];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            wlacc[j] = fmaf(e, acc[c][p][j], wlacc[j]);
+            acc[c][p][j] = e * wl[j];
+          }
+        }
+      }
+#pragma unroll 1
+      for (int l = Lh - 1; l >= 0; --l) {
+        mma_act_backward<C>(acc, l == 0 ? net.act_first : net.act_hidden, stash + l * STL, tid);
+        if (l == 0) break;
+        __syncthreads();
+        mma_store_tile<C>(Gs, acc, G);
+        mma_recompute_outputs<C>(Hs, (l - 1 == 0) ? net.act_first : net.act_hidden, stash + (l - 1) * STL, G, tid);
+        __syncthreads();
+        mma_wgrad_layer<C>(Hs, Gs, bsc, gacc + net.off_w[l], gacc + net.off_b[l], tid, G);
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+          for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[c][p][j] = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+          const float* wc = chunk_begin();
+          mma_gemm_chunk<C>(acc, Gs, wc, ch * KC, G);
+          __syncthreads();
+          ++gpos;
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        float hj[K][3];
+        feature_jets<C>(net, z[p], hj);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          b0acc[j] += acc[0][p][j];
+#pragma unroll
+          for (int c = 0; c < K; ++c) {
+            const float a = net.scl * acc[c][p][j];
+            w0acc[0][j] = fmaf(hj[c][0], a, w0acc[0][j]);
+            w0acc[1][j] = fmaf(hj[c][1], a, w0acc[1][j]);
+            w0acc[2][j] = fmaf(hj[c][2], a, w0acc[2][j]);
+          }
+        }
+      }
+    }
+  }
+
+  if (TRAIN) {
+    if (cur_slot >= 0) flush_loss(cur_slot);
+    __syncthreads();
+    float* sc = Hs;  // [5][ROWS][WP], folded over the ROWS thread rows in fixed order
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const float* src = (q < 3) ? w0acc[q] : (q == 3 ? b0acc : wlacc);
+      float* d = sc + (q * C::ROWS + G.row) * WP;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        *reinterpret_cast<float2*>(d + G.n0 + 8 * nt + 2 * G.t) = make_float2(src[2 * nt], src[2 * nt + 1]);
+    }
+    float* sc2 = sc + 5 * C::ROWS * WP;
+    if (G.t == 0 && G.nw == 0) sc2[G.row] = blacc;
+    __syncthreads();
+    for (int idx = tid; idx < 5 * WP; idx += C::NT) {
+      const int q = idx / WP, u = idx % WP;
+      float s = 0.f;
+      for (int r = 0; r < C::ROWS; ++r) s += sc[(q * C::ROWS + r) * WP + u];
+      const int dst = (q < 3) ? (net.off_w0 + q * WP + u) : (q == 3 ? net.off_b0 + u : net.off_wl + u);
+      gacc[dst] += s;
+    }
+    if (tid == 0) {
+      float s = 0.f;
+      for (int r = 0; r < C::ROWS; ++r) s += sc2[r];
+      gacc[net.off_bl] += s;
+    }
+  }
+}

@@ -32,7 +32,7 @@ EXPORTS = [
     "pinn_engine_get_params", "pinn_engine_set_points", "pinn_engine_set_global_counts",
     "pinn_engine_set_loss", "pinn_engine_loss_grad", "pinn_engine_adam_init", "pinn_engine_adam_steps",
     "pinn_engine_eval", "pinn_engine_lbfgs", "pinn_nccl_unique_id", "pinn_engine_init_nccl",
-    "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels",
+    "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels", "pinn_engine_kernel_kind",
 ]
 
 
@@ -76,6 +76,7 @@ def load_library(path: Optional[str] = None):
     lib.pinn_engine_num_loss_info.argtypes = [C.c_void_p]
     lib.pinn_engine_tile_points.argtypes = [C.c_void_p]
     lib.pinn_engine_launches_per_eval.argtypes = [C.c_void_p]
+    lib.pinn_engine_kernel_kind.argtypes = [C.c_void_p]
     lib.pinn_engine_set_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.pinn_engine_get_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.pinn_engine_set_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
@@ -193,6 +194,7 @@ class PinnEngine:
         self.n_params = int(self.lib.pinn_engine_num_params(h))
         self.n_info = int(self.lib.pinn_engine_num_loss_info(h))
         self.K = eq.K
+        self.kernel = ("simt_fp32", "mma_3xtf32")[int(self.lib.pinn_engine_kernel_kind(h))]
         self._keep = []  # device tensors borrowed by the engine
         self.lref = 1.0
         self.lw = 1.0

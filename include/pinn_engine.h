@@ -40,8 +40,13 @@ typedef struct pinn_spec {
   const int32_t* ops;
   int32_t n_consts;
   const float* consts;
-  int32_t n_aux_col;   /* per-point aux columns of the collocation set (source terms)  */
+  int32_t n_aux_col;   /* aux columns the residual program reads per collocation point:
+                          n_aux_user caller-supplied columns followed by hoisted columns   */
   int32_t n_bc;        /* boundary/initial-condition groups = data loss terms (sw:334) */
+  int32_t n_aux_user;  /* caller-supplied aux columns (source terms, data)             */
+  int32_t n_aux_ops;   /* "aux program": evaluated ONCE per point when points are set;  */
+  const int32_t* aux_ops; /* fills the hoisted columns (jet-free sub-expressions such as
+                          source terms / variable coefficients) from coords and user aux */
 } pinn_spec_t;
 
 typedef struct pinn_lbfgs_result {

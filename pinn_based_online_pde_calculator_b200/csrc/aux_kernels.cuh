@@ -126,6 +126,42 @@ __global__ void k_adam(int n, float* __restrict__ p, const float* __restrict__ g
 
 __global__ void k_set_f32(float* dst, float v) { *dst = v; }
 
+// Aux program: scalar stack VM, one thread per point, run once per set_points/eval.
+// out[pt][0..n_user) = user aux; hoisted columns are written by OP_STORE_AUX.
+__global__ void k_eval_aux(const PinnProgram P, const float* __restrict__ coords, int d_in,
+                           const float* __restrict__ user, int n_user, float* __restrict__ out, int n_total,
+                           long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float* row = out + i * n_total;
+  for (int k = 0; k < n_user; ++k) row[k] = user[i * n_user + k];
+  float st[PINN_VM_STACK];
+  int sp = 0;
+  for (int q = 0; q < P.n_ops; ++q) {
+    const int w = P.ops[q], op = w & 0xff, arg = w >> 8;
+    switch (op) {
+      case OP_CONST: st[sp++] = P.consts[arg]; break;
+      case OP_COORD: st[sp++] = coords[i * d_in + arg]; break;
+      case OP_AUX: st[sp++] = row[arg]; break;
+      case OP_ADD: --sp; st[sp - 1] += st[sp]; break;
+      case OP_SUB: --sp; st[sp - 1] -= st[sp]; break;
+      case OP_MUL: --sp; st[sp - 1] *= st[sp]; break;
+      case OP_DIV: --sp; st[sp - 1] /= st[sp]; break;
+      case OP_NEG: st[sp - 1] = -st[sp - 1]; break;
+      case OP_POWI: { const float a = st[sp - 1]; float r = 1.f; for (int e = 0; e < arg; ++e) r *= a; st[sp - 1] = r; break; }
+      case OP_POWF: st[sp - 1] = powf(st[sp - 1], P.consts[arg]); break;
+      case OP_SIN: st[sp - 1] = sinf(st[sp - 1]); break;
+      case OP_COS: st[sp - 1] = cosf(st[sp - 1]); break;
+      case OP_EXP: st[sp - 1] = expf(st[sp - 1]); break;
+      case OP_LOG: st[sp - 1] = logf(st[sp - 1]); break;
+      case OP_TANH: st[sp - 1] = tanhf(st[sp - 1]); break;
+      case OP_SQRT: st[sp - 1] = sqrtf(st[sp - 1]); break;
+      case OP_STORE_AUX: row[arg] = st[--sp]; break;
+      default: break;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- L-BFGS helpers
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll

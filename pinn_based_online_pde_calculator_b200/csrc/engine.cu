@@ -80,14 +80,14 @@ struct pinn_engine {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   pinn_spec_t spec{};
-  std::vector<int32_t> ops;
+  std::vector<int32_t> ops, aux_ops;
   std::vector<float> consts;
   PinnNet net{};
   FlatMap fmap{};
   int n_info = 0, n_slots = 0;
   const JetKernelInfo* kcol = nullptr;
   const JetKernelInfo* kbc = nullptr;
-  PinnProgram prog_col{}, prog_bc{};
+  PinnProgram prog_col{}, prog_bc{}, prog_aux{};
 
   // device state
   float *d_params = nullptr, *d_fused = nullptr, *d_m = nullptr, *d_v = nullptr, *d_wpack = nullptr;
@@ -217,6 +217,11 @@ extern "C" int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engi
   h->consts.assign(spec->consts, spec->consts + spec->n_consts);
   h->spec.ops = h->ops.data();
   h->spec.consts = h->consts.data();
+  if (spec->n_aux_ops < 0 || spec->n_aux_ops > PINN_MAX_OPS) { delete h; return fail("aux program too long"); }
+  if (spec->n_aux_user < 0 || spec->n_aux_user > spec->n_aux_col) { delete h; return fail("n_aux_user out of range"); }
+  if (spec->n_aux_ops == 0 && spec->n_aux_user != spec->n_aux_col) { delete h; return fail("hoisted columns need an aux program"); }
+  if (spec->n_aux_ops > 0) h->aux_ops.assign(spec->aux_ops, spec->aux_ops + spec->n_aux_ops);
+  h->spec.aux_ops = h->aux_ops.data();
   {
     // kernel family: PINN_B200_KERNEL = simt | mma | auto (default: the 3xTF32 tensor-core kernel when
     // it is instantiated for this width and jet structure, else the fp32 SIMT kernel)
@@ -257,6 +262,9 @@ extern "C" int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engi
   h->prog_col.n_ops = spec->n_ops;
   memcpy(h->prog_col.ops, spec->ops, sizeof(int32_t) * spec->n_ops);
   memcpy(h->prog_col.consts, spec->consts, sizeof(float) * spec->n_consts);
+  h->prog_aux.n_ops = spec->n_aux_ops;
+  if (spec->n_aux_ops > 0) memcpy(h->prog_aux.ops, spec->aux_ops, sizeof(int32_t) * spec->n_aux_ops);
+  memcpy(h->prog_aux.consts, spec->consts, sizeof(float) * spec->n_consts);
   h->prog_bc.n_ops = 3;  // u - aux0   (software.py:344)
   h->prog_bc.ops[0] = OP_JET | (0 << 8);
   h->prog_bc.ops[1] = OP_AUX | (0 << 8);
@@ -400,28 +408,49 @@ extern "C" int pinn_engine_set_points(pinn_engine_t* h, const float* x_col, int6
   CK(cudaSetDevice(h->device));
   if (n_bc != h->spec.n_bc) return fail("n_bc %d != spec.n_bc %d", n_bc, h->spec.n_bc);
   if (n_col <= 0) return fail("n_col must be > 0");
-  if (h->spec.n_aux_col > 0 && !aux_col) return fail("aux_col required (n_aux_col=%d)", h->spec.n_aux_col);
   const int d = h->spec.d_in, K = h->kcol->k;
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   // collocation set
+  const int na = h->spec.n_aux_col, na_user = h->spec.n_aux_user;
+  const bool has_aux_prog = h->spec.n_aux_ops > 0;
+  if (na_user > 0 && !aux_col) return fail("aux_col required (n_aux_user=%d)", na_user);
+  float* tmp_user = nullptr;  // device copy of host user aux when the aux program needs it
   if (on_device) {
     if (h->col.own_coords && h->col.coords) cudaFree(h->col.coords);
     h->col.coords = const_cast<float*>(x_col); h->col.own_coords = false; h->col.cap_coords = 0;
-    if (h->col.own_aux && h->col.aux) cudaFree(h->col.aux);
-    h->col.aux = const_cast<float*>(aux_col); h->col.own_aux = false; h->col.cap_aux = 0;
+    if (!has_aux_prog) {
+      if (h->col.own_aux && h->col.aux) cudaFree(h->col.aux);
+      h->col.aux = const_cast<float*>(aux_col); h->col.own_aux = false; h->col.cap_aux = 0;
+    }
     if (h->col.own_base && h->col.base) cudaFree(h->col.base);
     h->col.base = const_cast<float*>(base_col); h->col.own_base = false; h->col.cap_base = 0;
   } else {
     if (ensure(&h->col.coords, &h->col.cap_coords, &h->col.own_coords, (size_t)n_col * d)) return 1;
     CK(cudaMemcpyAsync(h->col.coords, x_col, sizeof(float) * n_col * d, kind, h->stream));
-    if (aux_col) {
-      if (ensure(&h->col.aux, &h->col.cap_aux, &h->col.own_aux, (size_t)n_col * h->spec.n_aux_col)) return 1;
-      CK(cudaMemcpyAsync(h->col.aux, aux_col, sizeof(float) * n_col * h->spec.n_aux_col, kind, h->stream));
-    } else if (h->col.own_aux) { /* keep buffer, unused */ } else h->col.aux = nullptr;
+    if (!has_aux_prog) {
+      if (aux_col) {
+        if (ensure(&h->col.aux, &h->col.cap_aux, &h->col.own_aux, (size_t)n_col * na)) return 1;
+        CK(cudaMemcpyAsync(h->col.aux, aux_col, sizeof(float) * n_col * na, kind, h->stream));
+      } else if (!h->col.own_aux) h->col.aux = nullptr;
+    }
     if (base_col) {
       if (ensure(&h->col.base, &h->col.cap_base, &h->col.own_base, (size_t)n_col * K)) return 1;
       CK(cudaMemcpyAsync(h->col.base, base_col, sizeof(float) * n_col * K, kind, h->stream));
     } else { if (h->col.own_base && h->col.base) cudaFree(h->col.base); h->col.base = nullptr; h->col.own_base = false; h->col.cap_base = 0; }
+  }
+  if (has_aux_prog) {
+    // engine-owned combined aux buffer [n_col][na]: user columns copied, hoisted columns evaluated once
+    if (ensure(&h->col.aux, &h->col.cap_aux, &h->col.own_aux, (size_t)n_col * na)) return 1;
+    const float* user_dev = aux_col;
+    if (na_user > 0 && !on_device) {
+      CK(cudaMalloc(&tmp_user, sizeof(float) * n_col * na_user));
+      CK(cudaMemcpyAsync(tmp_user, aux_col, sizeof(float) * n_col * na_user, cudaMemcpyHostToDevice, h->stream));
+      user_dev = tmp_user;
+    }
+    k_eval_aux<<<(unsigned)((n_col + 255) / 256), 256, 0, h->stream>>>(h->prog_aux, h->col.coords, d, user_dev, na_user,
+                                                                       h->col.aux, na, n_col);
+    CK(cudaGetLastError());
+    if (tmp_user) { CK(cudaStreamSynchronize(h->stream)); cudaFree(tmp_user); }
   }
   const bool shape_changed = (n_col != h->n_col);
   h->n_col = n_col;
@@ -615,8 +644,9 @@ extern "C" int pinn_engine_eval(pinn_engine_t* h, const float* z, int64_t n, con
                                 float* u_out, float* f_out, float* jets_out, int on_device) {
   CK(cudaSetDevice(h->device));
   if (n <= 0) return 0;
-  const int d = h->spec.d_in, K = h->kcol->k, na = h->spec.n_aux_col;
-  if (na > 0 && !aux) return fail("aux required");
+  const int d = h->spec.d_in, K = h->kcol->k, na = h->spec.n_aux_col, na_user = h->spec.n_aux_user;
+  const bool has_aux_prog = h->spec.n_aux_ops > 0;
+  if (na_user > 0 && !aux) return fail("aux required");
   cudaStream_t st = h->stream;
   std::vector<void*> tmp;
   auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr; tmp.push_back(p); return p; };
@@ -627,13 +657,19 @@ extern "C" int pinn_engine_eval(pinn_engine_t* h, const float* z, int64_t n, con
     float* t = (float*)dalloc(sizeof(float) * n * d);
     if (!t) { cleanup(); return fail("cudaMalloc failed"); }
     cudaMemcpyAsync(t, z, sizeof(float) * n * d, cudaMemcpyHostToDevice, st); dz = t;
-    if (aux) { t = (float*)dalloc(sizeof(float) * n * na); if (!t) { cleanup(); return fail("cudaMalloc failed"); }
-      cudaMemcpyAsync(t, aux, sizeof(float) * n * na, cudaMemcpyHostToDevice, st); daux = t; }
+    if (aux && na_user > 0) { t = (float*)dalloc(sizeof(float) * n * na_user); if (!t) { cleanup(); return fail("cudaMalloc failed"); }
+      cudaMemcpyAsync(t, aux, sizeof(float) * n * na_user, cudaMemcpyHostToDevice, st); daux = t; }
     if (base) { t = (float*)dalloc(sizeof(float) * n * K); if (!t) { cleanup(); return fail("cudaMalloc failed"); }
       cudaMemcpyAsync(t, base, sizeof(float) * n * K, cudaMemcpyHostToDevice, st); dbase = t; }
     if (u_out) { du = (float*)dalloc(sizeof(float) * n); if (!du) { cleanup(); return fail("cudaMalloc failed"); } }
     if (f_out) { df = (float*)dalloc(sizeof(float) * n); if (!df) { cleanup(); return fail("cudaMalloc failed"); } }
     if (jets_out) { dj = (float*)dalloc(sizeof(float) * n * K); if (!dj) { cleanup(); return fail("cudaMalloc failed"); } }
+  }
+  if (has_aux_prog) {
+    float* comb = (float*)dalloc(sizeof(float) * n * na);
+    if (!comb) { cleanup(); return fail("cudaMalloc failed"); }
+    k_eval_aux<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->prog_aux, dz, d, daux, na_user, comb, na, n);
+    daux = comb;
   }
   const int P = h->fmap.n_params;
   k_pack<<<(P + 255) / 256, 256, 0, st>>>(h->fmap, h->d_params, h->d_wpack);
@@ -652,6 +688,10 @@ extern "C" int pinn_engine_eval(pinn_engine_t* h, const float* z, int64_t n, con
     if (f_out) cudaMemcpyAsync(f_out, df, sizeof(float) * n, cudaMemcpyDeviceToHost, st);
     if (jets_out) cudaMemcpyAsync(jets_out, dj, sizeof(float) * n * K, cudaMemcpyDeviceToHost, st);
     e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess) return fail("eval: %s", cudaGetErrorString(e));
+  } else if (!tmp.empty()) {
+    e = cudaStreamSynchronize(st);  // the combined aux buffer is a temporary
     cleanup();
     if (e != cudaSuccess) return fail("eval: %s", cudaGetErrorString(e));
   }

@@ -24,7 +24,8 @@ enum PinnOp {
   OP_ADD = 4, OP_SUB = 5, OP_MUL = 6, OP_DIV = 7, OP_NEG = 8,
   OP_POWI = 9,   // integer power arg >= 0
   OP_POWF = 10,  // real power consts[arg]
-  OP_SIN = 11, OP_COS = 12, OP_EXP = 13, OP_LOG = 14, OP_TANH = 15, OP_SQRT = 16
+  OP_SIN = 11, OP_COS = 12, OP_EXP = 13, OP_LOG = 14, OP_TANH = 15, OP_SQRT = 16,
+  OP_STORE_AUX = 17  // aux program only: pop -> aux column arg
 };
 
 struct PinnProgram {

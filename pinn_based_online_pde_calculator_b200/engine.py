@@ -43,6 +43,7 @@ class PinnSpecC(C.Structure):
         ("lb", C.c_float * 3), ("ub", C.c_float * 3), ("n1", C.c_int32), ("n2", C.c_int32), ("mix", C.c_int32),
         ("n_ops", C.c_int32), ("ops", C.POINTER(C.c_int32)), ("n_consts", C.c_int32),
         ("consts", C.POINTER(C.c_float)), ("n_aux_col", C.c_int32), ("n_bc", C.c_int32),
+        ("n_aux_user", C.c_int32), ("n_aux_ops", C.c_int32), ("aux_ops", C.POINTER(C.c_int32)),
     ]
 
 
@@ -188,6 +189,8 @@ class PinnEngine:
         spec.n_ops, spec.ops = len(eq.ops), self._ops
         spec.n_consts, spec.consts = len(eq.consts), self._consts
         spec.n_aux_col, spec.n_bc = eq.n_aux, n_bc
+        self._aux_ops = (C.c_int32 * max(1, len(eq.aux_ops)))(*(eq.aux_ops or [0]))
+        spec.n_aux_user, spec.n_aux_ops, spec.aux_ops = eq.n_aux_user, len(eq.aux_ops), self._aux_ops
         h = C.c_void_p()
         _check(self.lib, self.lib.pinn_engine_create(C.byref(spec), device, C.byref(h)))
         self.h = h

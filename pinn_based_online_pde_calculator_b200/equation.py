@@ -27,6 +27,7 @@ OP_CONST, OP_COORD, OP_JET, OP_AUX = 0, 1, 2, 3
 OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG = 4, 5, 6, 7, 8
 OP_POWI, OP_POWF = 9, 10
 OP_SIN, OP_COS, OP_EXP, OP_LOG, OP_TANH, OP_SQRT = 11, 12, 13, 14, 15, 16
+OP_STORE_AUX = 17  # aux program only: pop -> aux column arg
 MAX_OPS, MAX_CONSTS, VM_STACK = 192, 48, 12
 
 _FUNC_OPS = {"sin": OP_SIN, "cos": OP_COS, "exp": OP_EXP, "log": OP_LOG, "tanh": OP_TANH, "sqrt": OP_SQRT}
@@ -322,8 +323,10 @@ class CompiledEquation:
     mix: int
     ops: List[int] = field(default_factory=list)
     consts: List[float] = field(default_factory=list)
-    n_aux: int = 0
+    n_aux: int = 0            # total aux columns the residual program reads (user + hoisted)
     max_stack: int = 0
+    n_aux_user: int = 0       # columns supplied by the caller (aux0..)
+    aux_ops: List[int] = field(default_factory=list)  # program filling the hoisted columns from coords/user aux
 
     @property
     def K(self) -> int:
@@ -365,13 +368,82 @@ def choose_jets(d_in: int, firsts: set, seconds: set) -> Tuple[int, int, int]:
         f"derivative set first={sorted(firsts)} second={sorted(seconds)} has no kernel instantiation for d_in={d_in}")
 
 
-def compile_equation(expr: str, d_in: int = 2, extended: bool = True) -> CompiledEquation:
+def _jet_free(n: Node) -> bool:
+    return n.kind not in ("u", "du") and all(_jet_free(a) for a in n.args)
+
+
+def _has_point_data(n: Node) -> bool:
+    return n.kind in ("coord", "aux") or any(_has_point_data(a) for a in n.args)
+
+
+def _add_terms(n: Node, sign: int, out: list):
+    """Flatten a +/- chain into (sign, term) pairs."""
+    if n.kind == "add":
+        _add_terms(n.args[0], sign, out)
+        _add_terms(n.args[1], sign, out)
+    elif n.kind == "sub":
+        _add_terms(n.args[0], sign, out)
+        _add_terms(n.args[1], -sign, out)
+    elif n.kind == "neg":
+        _add_terms(n.args[0], -sign, out)
+    else:
+        out.append((sign, n))
+
+
+def _chain(terms) -> Node:
+    node = None
+    for sg, t in terms:
+        if node is None:
+            node = t if sg > 0 else Node("neg", args=(t,))
+        else:
+            node = Node("add" if sg > 0 else "sub", args=(node, t))
+    return node
+
+
+def hoist_point_terms(ast: Node, n_user_aux: int):
+    """Move every maximal sub-expression that does not depend on u or its derivatives (source
+    terms, variable coefficients) out of the per-step residual program: it is evaluated once per
+    point when the points are set and read back as an aux column.  Additive jet-free terms of one
+    sum are merged into a single column."""
+    hoisted: List[Node] = []
+
+    def lift(n: Node) -> Node:
+        idx = n_user_aux + len(hoisted)
+        hoisted.append(n)
+        return Node("aux", value=float(idx))
+
+    def walk(n: Node) -> Node:
+        if _jet_free(n):
+            if _has_point_data(n) and n.kind not in ("coord", "aux"):
+                return lift(n)
+            return n
+        if n.kind in ("add", "sub"):
+            terms: list = []
+            _add_terms(n, +1, terms)
+            free = [(sg, t) for sg, t in terms if _jet_free(t)]
+            dep = [(sg, walk(t)) for sg, t in terms if not _jet_free(t)]
+            if free and any(_has_point_data(t) for _, t in free):
+                dep.append((+1, lift(_chain(free))))
+            else:
+                dep.extend(free)
+            return _chain(dep)
+        return Node(n.kind, n.value, n.name, tuple(walk(a) for a in n.args))
+
+    return walk(ast), hoisted
+
+
+def compile_equation(expr: str, d_in: int = 2, extended: bool = True, hoist: bool = True) -> CompiledEquation:
     ast = parse(expr, extended)
     firsts, seconds, aux = set(), set(), set()
     _collect(ast, d_in, firsts, seconds, aux)
     n1, n2, mix = choose_jets(d_in, firsts, seconds)
-    ce = CompiledEquation(expr, d_in, n1, n2, mix, n_aux=(max(aux) + 1 if aux else 0))
+    n_user = max(aux) + 1 if aux else 0
+    hoisted: List[Node] = []
+    if hoist:
+        ast, hoisted = hoist_point_terms(ast, n_user)
+    ce = CompiledEquation(expr, d_in, n1, n2, mix, n_aux=n_user + len(hoisted), n_aux_user=n_user)
     depth = 0
+    target = ce.ops
 
     def const_index(v: float) -> int:
         v = float(v)
@@ -385,7 +457,7 @@ def compile_equation(expr: str, d_in: int = 2, extended: bool = True) -> Compile
 
     def emit(op: int, arg: int = 0, delta: int = 0):
         nonlocal depth
-        ce.ops.append((op & 0xFF) | (int(arg) << 8))
+        target.append((op & 0xFF) | (int(arg) << 8))
         depth += delta
         ce.max_stack = max(ce.max_stack, depth)
 
@@ -456,8 +528,13 @@ def compile_equation(expr: str, d_in: int = 2, extended: bool = True) -> Compile
             raise EquationError(f"cannot compile node {k}")
 
     gen(ast)
-    if len(ce.ops) > MAX_OPS:
-        raise EquationError(f"expression too long ({len(ce.ops)} ops > {MAX_OPS})")
+    target = ce.aux_ops
+    for i, sub in enumerate(hoisted):
+        depth = 0
+        gen(sub)
+        emit(OP_STORE_AUX, n_user + i, -1)
+    if len(ce.ops) > MAX_OPS or len(ce.aux_ops) > MAX_OPS:
+        raise EquationError(f"expression too long ({max(len(ce.ops), len(ce.aux_ops))} ops > {MAX_OPS})")
     if ce.max_stack > VM_STACK:
         raise EquationError(f"expression too deep (stack {ce.max_stack} > {VM_STACK})")
     return ce
@@ -472,8 +549,13 @@ def evaluate_host(ce: CompiledEquation, z, jets, aux=None):
     the compiler, never by the training path."""
     import numpy as np
 
+    if ce.aux_ops:
+        full = np.zeros((z.shape[0], ce.n_aux))
+        if ce.n_aux_user:
+            full[:, :ce.n_aux_user] = aux[:, :ce.n_aux_user]
+        aux = full
     st = []
-    for w in ce.ops:
+    for w in list(ce.aux_ops) + list(ce.ops):
         op, arg = w & 0xFF, w >> 8
         if op == OP_CONST:
             st.append(np.full(z.shape[0], ce.consts[arg]))
@@ -489,6 +571,8 @@ def evaluate_host(ce: CompiledEquation, z, jets, aux=None):
             st.append({OP_ADD: a + b, OP_SUB: a - b, OP_MUL: a * b, OP_DIV: a / b}[op])
         elif op == OP_NEG:
             st.append(-st.pop())
+        elif op == OP_STORE_AUX:
+            aux[:, arg] = st.pop()
         elif op == OP_POWI:
             st.append(st.pop() ** arg)
         elif op == OP_POWF:

@@ -86,6 +86,19 @@ def test_program_limits_are_enforced():
         compile_equation("+".join(["u*x"] * 80), d_in=2)          # too long
     deep = "u"
     for _ in range(14):
-        deep = f"(x+({deep}*y))"
+        deep = f"u*(x+{deep})"
     with pytest.raises(EquationError):
-        compile_equation("x+(x+(x+(x+(x+(x+(x+(x+(x+(x+(x+(x+(x+u))))))))))))", d_in=2)  # stack too deep
+        compile_equation(deep, d_in=2)  # stack too deep
+
+
+def test_point_terms_are_hoisted_out_of_the_step_program():
+    ce = compile_equation("u_xx + u_yy + 2*y*(1-y) + 2*x*(1-x)", d_in=2)
+    assert len(ce.ops) == 5 and ce.n_aux == 1 and ce.n_aux_user == 0 and len(ce.aux_ops) > 0
+    ce = compile_equation("u_rr + 1/r*u_r + 1/(r**2)*u_tt", d_in=2)
+    assert ce.n_aux == 2 and len(ce.ops) == 9          # the variable coefficients become columns
+    ce = compile_equation("u_t + u*u_x - 0.003183*u_xx", d_in=2)
+    assert ce.n_aux == 0 and not ce.aux_ops             # nothing to hoist
+    ce = compile_equation("u_xx + aux0*u + x*aux1 - 3", d_in=2)
+    assert ce.n_aux_user == 2 and ce.n_aux == 3
+    raw = compile_equation("u_xx + u_yy + 2*y*(1-y) + 2*x*(1-x)", d_in=2, hoist=False)
+    assert len(raw.ops) == 19 and raw.n_aux == 0

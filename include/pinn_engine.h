@@ -139,6 +139,10 @@ int pinn_fma_peak(int device, int variant, double* tflops_out);
  * flush_bytes between launches. */
 int pinn_engine_time_kernels(pinn_engine_t* h, int32_t reps, int64_t flush_bytes, double* col_ms, double* bc_ms);
 
+/* phase profile of the collocation kernel (tensor-core kernel only): clock64 totals of CTA 0 for
+ * {fwd GEMM, activation fwd, output+residual, activation bwd, smem restage, wgrad, dgrad, rest} */
+int pinn_engine_phase_profile(pinn_engine_t* h, int64_t* out8);
+
 /* timing helper: device time (ms) of the last adam_steps / loss_grad call measured
  * with CUDA events on the engine stream */
 double pinn_engine_last_ms(pinn_engine_t* h);

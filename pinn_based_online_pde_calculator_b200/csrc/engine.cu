@@ -739,6 +739,31 @@ extern "C" int pinn_engine_time_kernels(pinn_engine_t* h, int32_t reps, int64_t 
   return 0;
 }
 
+// Phase profile of the collocation kernel: clock64 totals of CTA 0 / thread 0 per phase
+// (0 fwd GEMM, 1 activation fwd, 2 output+residual, 3 activation bwd, 4 smem restage, 5 wgrad,
+//  6 dgrad, 7 rest).  Only the tensor-core kernel is instrumented.
+extern "C" int pinn_engine_phase_profile(pinn_engine_t* h, int64_t* out8) {
+  CK(cudaSetDevice(h->device));
+  if (!h->points_set) return fail("set_points has not been called");
+  cudaStream_t st = h->stream;
+  const int P = h->fmap.n_params;
+  long long* d = nullptr;
+  CK(cudaMalloc(&d, 8 * sizeof(long long)));
+  CK(cudaMemsetAsync(d, 0, 8 * sizeof(long long), st));
+  k_pack<<<(P + 255) / 256, 256, 0, st>>>(h->fmap, h->d_params, h->d_wpack);
+  CK(cudaMemsetAsync(h->d_gacc, 0, sizeof(float) * (size_t)h->grid_col * h->net.pg, st));
+  CK(cudaMemsetAsync(h->d_loss_part, 0, sizeof(double) * (size_t)h->grid_col * h->n_slots, st));
+  PinnLaunch L = h->Lcol;
+  L.phase_clk = d;
+  CK(h->kcol->launch(L, true, h->grid_col, st));
+  long long host[8];
+  CK(cudaMemcpyAsync(host, d, sizeof host, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(d);
+  for (int i = 0; i < 8; ++i) out8[i] = host[i];
+  return 0;
+}
+
 // ---------------------------------------------------------------- L-BFGS (software.py:499-514)
 namespace {
 struct Phi { double a, f, d; };  // step, value, directional derivative

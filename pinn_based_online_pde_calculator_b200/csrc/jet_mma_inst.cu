@@ -7,7 +7,10 @@
 #error "compile with -DJ_WP= -DJ_N1= -DJ_N2= -DJ_MIX="
 #endif
 
-using Cfg = MmaCfg<J_WP, J_N1, J_N2, J_MIX, (J_WP <= 64 ? 128 : 256)>;
+#ifndef J_NT
+#define J_NT (J_WP <= 64 ? 128 : 256)
+#endif
+using Cfg = MmaCfg<J_WP, J_N1, J_N2, J_MIX, J_NT>;
 
 static cudaError_t launch_impl(const PinnLaunch& L, bool train, int grid, cudaStream_t stream) {
   if (train)

@@ -27,7 +27,7 @@ struct MmaCfg {
   static constexpr int ROWS = TP / 2;           // thread rows (mw, g)
   static constexpr int SP = K * WP + 8;         // smem point stride == 8 (mod 32)
   static constexpr int WPS = WP + 8;            // weight row stride (smem chunk and pack)
-  static constexpr int KC = (K >= 6) ? (WP <= 64 ? 16 : 8) : (WP <= 64 ? 32 : (WP <= 128 ? 16 : 8));
+  static constexpr int KC = (NT <= 64) ? 16 : (K >= 6) ? (WP <= 64 ? 16 : 8) : (WP <= 64 ? 32 : (WP <= 128 ? 16 : 8));
   static constexpr int NCH = WP / KC;
   static constexpr uint32_t CHUNK_BYTES = KC * WPS * 4;
   static constexpr int SCR_HALF = ((5 * ROWS * WP + ROWS + 1) / 2 + 3) / 4 * 4;  // final-fold scratch / 2
@@ -40,7 +40,9 @@ struct MmaCfg {
   static constexpr size_t smem_bytes(bool train) {
     return (size_t)(HS_FLOATS * (train ? 2 : 1) + 2 * KC * WPS + WP + PINN_MAX_OPS + PINN_MAX_CONSTS) * 4 + 64;
   }
-  static constexpr int MINB = (2 * (smem_bytes(true) + 1024) <= 232448) ? 2 : 1;  // resident CTAs per SM
+  static constexpr int MINB_S = (int)(232448 / (smem_bytes(true) + 1024));            // smem-limited CTAs per SM
+  static constexpr int MINB_R = 65536 / (NT * 256);                                     // at 255 registers per thread
+  static constexpr int MINB = MINB_S < 1 ? 1 : (MINB_S < MINB_R ? MINB_S : MINB_R);   // resident CTAs per SM
 };
 
 // ---------------------------------------------------------------- tensor-core helpers
@@ -427,6 +429,12 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
     __syncthreads();
     lcur = 0.0;
   };
+  const bool prof = (L.phase_clk != nullptr) && blockIdx.x == 0 && tid == 0;
+  long long pclk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tmark = prof ? clock64() : 0;
+  auto lap = [&](int ph) {
+    if (prof) { const long long now = clock64(); pclk[ph] += now - tmark; tmark = now; }
+  };
   auto chunk_begin = [&]() -> const float* {
     if (tid == 0 && gpos + 1 < total) issue(gpos + 1);
     const int st = (int)(gpos & 1);
@@ -503,8 +511,10 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
           ++gpos;
         }
       }
+      lap(0);
       mma_act_forward<C, TRAIN>(acc, L.wpack + net.off_b[l], l == 0 ? net.act_first : net.act_hidden,
                                 stash + l * STL, G, tid);
+      lap(1);
     }
 
     // ---------------- output layer + residual program
@@ -580,6 +590,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
       }
     }
 
+    lap(2);
     if (TRAIN) {
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
@@ -597,12 +608,15 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
 #pragma unroll 1
       for (int l = Lh - 1; l >= 0; --l) {
         mma_act_backward<C>(acc, l == 0 ? net.act_first : net.act_hidden, stash + l * STL, tid);
+        lap(3);
         if (l == 0) break;
         __syncthreads();
         mma_store_tile<C>(Gs, acc, G);
         mma_recompute_outputs<C>(Hs, (l - 1 == 0) ? net.act_first : net.act_hidden, stash + (l - 1) * STL, G, tid);
         __syncthreads();
+        lap(4);
         mma_wgrad_layer<C>(Hs, Gs, bsc, gacc + net.off_w[l], gacc + net.off_b[l], tid, G);
+        lap(5);
 #pragma unroll
         for (int c = 0; c < K; ++c)
 #pragma unroll
@@ -616,6 +630,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
           __syncthreads();
           ++gpos;
         }
+        lap(6);
       }
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
@@ -636,6 +651,11 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
     }
   }
 
+  lap(7);
+  if (prof) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) L.phase_clk[i] = pclk[i];
+  }
   if (TRAIN) {
     if (cur_slot >= 0) flush_loss(cur_slot);
     __syncthreads();

@@ -71,5 +71,6 @@ struct PinnLaunch {
   float* out_f;            // eval: [n]
   float* out_jets;         // eval: [n][K] or null
   int n_tiles;
+  long long* phase_clk;    // optional [8] clock64 totals per phase (CTA 0, thread 0), else null
   PinnProgram prog;
 };

@@ -32,7 +32,7 @@ EXPORTS = [
     "pinn_engine_get_params", "pinn_engine_set_points", "pinn_engine_set_global_counts",
     "pinn_engine_set_loss", "pinn_engine_loss_grad", "pinn_engine_adam_init", "pinn_engine_adam_steps",
     "pinn_engine_eval", "pinn_engine_lbfgs", "pinn_nccl_unique_id", "pinn_engine_init_nccl",
-    "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels", "pinn_engine_kernel_kind",
+    "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels", "pinn_engine_kernel_kind", "pinn_engine_phase_profile",
 ]
 
 
@@ -78,6 +78,7 @@ def load_library(path: Optional[str] = None):
     lib.pinn_engine_tile_points.argtypes = [C.c_void_p]
     lib.pinn_engine_launches_per_eval.argtypes = [C.c_void_p]
     lib.pinn_engine_kernel_kind.argtypes = [C.c_void_p]
+    lib.pinn_engine_phase_profile.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     lib.pinn_engine_set_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.pinn_engine_get_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.pinn_engine_set_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
@@ -299,6 +300,13 @@ class PinnEngine:
         a, b = C.c_double(), C.c_double()
         _check(self.lib, self.lib.pinn_engine_time_kernels(self.h, reps, flush_bytes, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def phase_profile(self):
+        """clock64 totals of CTA 0 per phase of the (tensor-core) collocation kernel."""
+        out = (C.c_int64 * 8)()
+        _check(self.lib, self.lib.pinn_engine_phase_profile(self.h, out))
+        names = ["fwd_gemm", "act_fwd", "output_residual", "act_bwd", "restage", "wgrad", "dgrad", "rest"]
+        return dict(zip(names, [int(v) for v in out]))
 
     # ---- f_u / gov_eqn (software.py:213, 283)
     def eval(self, z, aux=None, base=None, want_u=True, want_f=True, want_jets=False):

@@ -96,7 +96,7 @@ struct pinn_engine {
   int *d_ring_pos = nullptr, *d_adam_count = nullptr;
   LossMeta* d_meta = nullptr;
   int ring_cap = 4096;
-  size_t stash_floats = 0;
+  size_t stash_floats = 0, gacc_floats = 0;
   int grid_max = 0, grid_max_col = 0, grid_max_bc = 0;
 
   // points
@@ -130,6 +130,8 @@ struct pinn_engine {
   float *d_x = nullptr, *d_g = nullptr, *d_d = nullptr, *d_xt = nullptr, *d_S = nullptr, *d_Y = nullptr;
   double *d_rho = nullptr, *d_alpha = nullptr, *d_scal = nullptr;
 };
+
+static void apply_l2_policy(pinn_engine* h);
 
 static int pad_width(int w) {
   if (w <= 32) return 32;
@@ -281,10 +283,12 @@ extern "C" int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engi
   CK(cudaMemset(h->d_params, 0, sizeof(float) * P));
   CK(cudaMemset(h->d_m, 0, sizeof(float) * P));
   CK(cudaMemset(h->d_v, 0, sizeof(float) * P));
-  h->stash_floats = (size_t)h->grid_max * spec->n_hidden *
-                    std::max(h->kcol->stash_floats_per_layer, h->kbc->stash_floats_per_layer);
-  CK(cudaMalloc(&h->d_stash, sizeof(float) * h->stash_floats));
-  CK(cudaMalloc(&h->d_gacc, sizeof(float) * (size_t)h->grid_max * h->net.pg));
+  h->stash_floats = ((size_t)h->grid_max * spec->n_hidden *
+                     std::max(h->kcol->stash_floats_per_layer, h->kbc->stash_floats_per_layer) + 31) / 32 * 32;
+  // stash and gradient accumulators share one allocation so that one persisting L2 window covers both
+  h->gacc_floats = ((size_t)h->grid_max * h->net.pg + 31) / 32 * 32;
+  CK(cudaMalloc(&h->d_stash, sizeof(float) * (h->stash_floats + h->gacc_floats)));
+  h->d_gacc = h->d_stash + h->stash_floats;
   CK(cudaMalloc(&h->d_loss_part, sizeof(double) * (size_t)h->grid_max * h->n_slots));
   CK(cudaMalloc(&h->d_seg_scale, sizeof(float) * PINN_MAX_SEG));
   CK(cudaMalloc(&h->d_lr, sizeof(float)));
@@ -295,6 +299,7 @@ extern "C" int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engi
   CK(cudaMalloc(&h->d_meta, sizeof(LossMeta)));
   CK(cudaMemset(h->d_ring_pos, 0, sizeof(int)));
   CK(cudaMemset(h->d_adam_count, 0, sizeof(int)));
+  if (!getenv("PINN_B200_NO_L2_WINDOW")) apply_l2_policy(h);
   *out = h;
   return 0;
 }
@@ -312,7 +317,7 @@ extern "C" void pinn_engine_destroy(pinn_engine_t* h) {
   cudaDeviceSynchronize();
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  void* bufs[] = {h->d_params, h->d_fused, h->d_m, h->d_v, h->d_wpack, h->d_stash, h->d_gacc, h->d_seg_scale,
+  void* bufs[] = {h->d_params, h->d_fused, h->d_m, h->d_v, h->d_wpack, h->d_stash, h->d_seg_scale,
                   h->d_lr, h->d_adam_c, h->d_loss_part, h->d_ring, h->d_ring_pos, h->d_adam_count, h->d_meta,
                   h->d_x, h->d_g, h->d_d, h->d_xt, h->d_S, h->d_Y, h->d_rho, h->d_alpha, h->d_scal};
   for (void* b : bufs)
@@ -325,6 +330,29 @@ extern "C" void pinn_engine_destroy(pinn_engine_t* h) {
   delete h;
 }
 
+// Keep the per-CTA stash (rewritten every tile, read back once) resident in L2: a persisting
+// access-policy window on the engine stream, so dirty stash lines are overwritten in place
+// instead of being evicted to HBM.
+static void apply_l2_policy(pinn_engine* h) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return;
+  if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
+  const size_t bytes = (h->stash_floats + h->gacc_floats) * sizeof(float);
+  const size_t carve = std::min<size_t>(bytes, (size_t)prop.persistingL2CacheMaxSize);
+  if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof attr);
+  attr.accessPolicyWindow.base_ptr = h->d_stash;
+  attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+  attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)attr.accessPolicyWindow.num_bytes);
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+  if (getenv("PINN_B200_DEBUG"))
+    fprintf(stderr, "[pinn] L2 window: %.1f MB of %.1f MB (persisting max %.1f MB, window max %.1f MB, L2 %.1f MB)\n",
+            carve / 1e6, bytes / 1e6, prop.persistingL2CacheMaxSize / 1e6, prop.accessPolicyMaxWindowSize / 1e6, prop.l2CacheSize / 1e6);
+}
+
 extern "C" int pinn_engine_set_stream(pinn_engine_t* h, void* s) {
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
@@ -332,6 +360,7 @@ extern "C" int pinn_engine_set_stream(pinn_engine_t* h, void* s) {
   h->stream = (cudaStream_t)s;
   h->own_stream = false;
   h->graph_valid = false;
+  if (!getenv("PINN_B200_NO_L2_WINDOW")) apply_l2_policy(h);
   return 0;
 }
 

@@ -55,3 +55,33 @@ for h in hist:
 for thr in (1e-2, 1e-3):
     hit = [h for h in hist if h[3] < thr]
     print(f"time-to-L2<{thr:g}:", f"{hit[0][0]:.3f} s ({hit[0][1]} {hit[0][2]})" if hit else "not reached")
+
+# ---- the same schedule on the CPU oracle (float64), bounded to the Adam part: time to the same thresholds
+if "--cpu" in sys.argv:
+    import torch
+    from oracle import reference_oracle as O
+    from pinn_based_online_pde_calculator_b200.workloads import unflatten
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = wl.net
+    params = [[torch.tensor(W, dtype=torch.float64), torch.tensor(b, dtype=torch.float64)] for W, b in unflatten(net, init_params(net))]
+    limit = [torch.tensor(net.lb, dtype=torch.float64), torch.tensor(net.ub, dtype=torch.float64)]
+    f_u = O.sol_pred_create(limit, net.scl, net.epsil, act_s=net.act_first, feature_map=net.feature_map)
+    residual = None if net.feature_map == "polar" else O.make_gov_eqn_expr(wl.expr, {1: ("x",), 2: ("x", "y")}[net.d_in])
+    lossf = O.loss_create(f_u, torch.tensor([wl.lw, 0.0], dtype=torch.float64), 1.0, residual=residual)
+    data = dict(x_col=torch.tensor(x_col, dtype=torch.float64), cond_bd=[[torch.tensor(a, dtype=torch.float64) for a in x_bd],
+                [torch.tensor(a, dtype=torch.float64)[:, None] for a in u_bd]])
+    lossf.ref = float(lossf(params, data)[1][0])
+    st = O.AdamState(params)
+    g = torch.tensor(grid, dtype=torch.float64)
+    t0 = time.perf_counter()
+    hits = {}
+    for k in range(n_adam):
+        params, info, st = O.adam_minimizer(lossf, params, data, 1e-3, st)
+        if (k + 1) % 50 == 0:
+            e = float(np.linalg.norm(f_u(params, g).numpy()[:, 0] - exact) / np.linalg.norm(exact))
+            for thr in (1e-2, 1e-3):
+                if e < thr and thr not in hits:
+                    hits[thr] = (time.perf_counter() - t0, k + 1)
+            if len(hits) == 2:
+                break
+    print(f"CPU oracle ({os.cpu_count()} cores, float64): time-to-L2 {hits}; {time.perf_counter() - t0:.1f} s for {k + 1} Adam steps")

@@ -35,7 +35,9 @@ typedef struct pinn_spec {
   float lb[3], ub[3];  /* domain bounds (sw:705-707)                                   */
   int32_t n1, n2, mix; /* jet channels of the collocation term: u, first derivatives
                           wrt inputs 0..n1-1, pure second derivatives wrt inputs
-                          0..n2-1, and (mix) the 0-1 mixed derivative                  */
+                          0..n2-1, and (mix==1) the 0-1 mixed derivative;
+                          mix==2 (n2==0): ONE combined second-order channel
+                          L = sum_i lap_beta_i d^2/dz_i^2 (Laplacian-type operators)   */
   int32_t n_ops;       /* residual bytecode (see csrc/pinn_common.h, PinnOp)           */
   const int32_t* ops;
   int32_t n_consts;
@@ -47,6 +49,8 @@ typedef struct pinn_spec {
   int32_t n_aux_ops;   /* "aux program": evaluated ONCE per point when points are set;  */
   const int32_t* aux_ops; /* fills the hoisted columns (jet-free sub-expressions such as
                           source terms / variable coefficients) from coords and user aux */
+  float lap_beta[3];   /* mix==2: constant coefficient of d_ii ...                      */
+  int32_t lap_aux[3];  /* ... or (>= 0) the aux column holding the per-point coefficient */
 } pinn_spec_t;
 
 typedef struct pinn_lbfgs_result {

@@ -159,6 +159,7 @@ static int build_layout(pinn_engine* h, int ldw) {
   n.act_hidden = s.act_hidden;
   n.scl = s.scl;
   n.epsil = s.epsil;
+  for (int i = 0; i < 3; ++i) { n.lap_beta[i] = s.lap_beta[i]; n.lap_aux[i] = (s.mix == 2) ? s.lap_aux[i] : -1; }
   for (int i = 0; i < 3; ++i) {
     const double lb = s.lb[i], ub = s.ub[i];
     if (i < s.d_in && ub != lb) {

@@ -15,7 +15,8 @@
 template <int WP_, int N1_, int N2_, int MIX_, int NT_ = PINN_NT>
 struct JetCfg {
   static constexpr int WP = WP_, N1 = N1_, N2 = N2_, MIX = MIX_;
-  static constexpr int K = 1 + N1 + N2 + MIX;   // jet channels
+  static constexpr bool LAP = (MIX == 2);       // one combined second-order channel sum_i beta_i d_ii
+  static constexpr int K = 1 + N1 + N2 + (MIX ? 1 : 0);   // jet channels
   static constexpr int NT = NT_, TU = PINN_TU;
   static constexpr int UT = WP / TU;            // threads across units
   static constexpr int ROWS = NT / UT;          // thread rows across points
@@ -286,7 +287,8 @@ __device__ __forceinline__ void store_tile(float* __restrict__ S, const float (&
 
 // feature jets of the network input (software.py:172-175 for 'polar')
 template <class C>
-__device__ __forceinline__ void feature_jets(const PinnNet& net, const float (&z)[3], float (&hj)[C::K][3]) {
+__device__ __forceinline__ void feature_jets(const PinnNet& net, const float (&z)[3], const float (&beta)[3],
+                                             float (&hj)[C::K][3]) {
 #pragma unroll
   for (int c = 0; c < C::K; ++c) hj[c][0] = hj[c][1] = hj[c][2] = 0.f;
   if (net.feat_mode == PINN_FEAT_POLAR) {
@@ -296,6 +298,7 @@ __device__ __forceinline__ void feature_jets(const PinnNet& net, const float (&z
     if (C::N1 >= 1) hj[1][0] = net.fa[0];
     if (C::N1 >= 2) { hj[2][1] = -s; hj[2][2] = co; }
     if (C::N2 >= 2) { hj[1 + C::N1 + 1][1] = -co; hj[1 + C::N1 + 1][2] = -s; }
+    if (C::LAP) { hj[C::K - 1][1] = -beta[1] * co; hj[C::K - 1][2] = -beta[1] * s; }
   } else {
 #pragma unroll
     for (int f = 0; f < 3; ++f) hj[0][f] = (f < net.d_in) ? fmaf(net.fa[f], z[f], net.fb[f]) : 0.f;
@@ -307,7 +310,8 @@ __device__ __forceinline__ void feature_jets(const PinnNet& net, const float (&z
 // pre-activation jets A_c (bias NOT yet added) -> output jets Y_c, in place; optional stash
 template <class C, bool TRAIN>
 __device__ __forceinline__ void act_forward(float (&acc)[C::K][C::PT][8], const float* __restrict__ bias,
-                                            int act, float* __restrict__ stash_l, int row, int ua) {
+                                            int act, float* __restrict__ stash_l, int row, int ua,
+                                            const float (&beta)[C::PT][3]) {
   const float4 ba = __ldg(reinterpret_cast<const float4*>(bias + ua));
   const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + C::WP / 2 + ua));
   const float b[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
@@ -336,8 +340,14 @@ __device__ __forceinline__ void act_forward(float (&acc)[C::K][C::PT][8], const 
         const float Ai = acc[1 + i][p][j];
         acc[1 + C::N1 + i][p][j] = fmaf(d2[j] * Ai, Ai, d1[j] * acc[1 + C::N1 + i][p][j]);
       }
-      if (C::MIX)
+      if (C::MIX == 1)
         acc[C::K - 1][p][j] = fmaf(d2[j] * acc[1][p][j], acc[2][p][j], d1[j] * acc[C::K - 1][p][j]);
+      if (C::LAP) {
+        float S = 0.f;
+#pragma unroll
+        for (int i = 0; i < C::N1; ++i) S = fmaf(beta[p][i] * acc[1 + i][p][j], acc[1 + i][p][j], S);
+        acc[C::K - 1][p][j] = fmaf(d2[j], S, d1[j] * acc[C::K - 1][p][j]);
+      }
 #pragma unroll
       for (int i = 0; i < C::N1; ++i) acc[1 + i][p][j] *= d1[j];
       acc[0][p][j] = y[j];
@@ -348,7 +358,8 @@ __device__ __forceinline__ void act_forward(float (&acc)[C::K][C::PT][8], const 
 // adjoint of act_forward: acc holds Ybar_c on entry, Abar_c on exit (reads the stash)
 template <class C>
 __device__ __forceinline__ void act_backward(float (&acc)[C::K][C::PT][8], int act,
-                                             const float* __restrict__ stash_l, int row, int ua) {
+                                             const float* __restrict__ stash_l, int row, int ua,
+                                             const float (&beta)[C::PT][3]) {
 #pragma unroll
   for (int p = 0; p < C::PT; ++p) {
     float st[C::K][8];
@@ -380,13 +391,25 @@ __device__ __forceinline__ void act_backward(float (&acc)[C::K][C::PT][8], int a
         ab1[i] = fmaf(2.0f * d2 * Ai, yb, ab1[i]);
         ab0 = fmaf(fmaf(d3 * Ai, Ai, d2 * Aii), yb, ab0);
       }
-      if (C::MIX) {
+      if (C::MIX == 1) {
         const float yb = acc[C::K - 1][p][j];
         const float A0 = st[1][j], A1 = st[2][j], A01 = st[C::K - 1][j];
         acc[C::K - 1][p][j] = d1 * yb;
         ab1[0] = fmaf(d2 * A1, yb, ab1[0]);
         ab1[C::N1 > 1 ? 1 : 0] = fmaf(d2 * A0, yb, ab1[C::N1 > 1 ? 1 : 0]);
         ab0 = fmaf(fmaf(d3 * A0, A1, d2 * A01), yb, ab0);
+      }
+      if (C::LAP) {
+        const float yb = acc[C::K - 1][p][j];
+        float S = 0.f;
+#pragma unroll
+        for (int i = 0; i < C::N1; ++i) {
+          const float bA = beta[p][i] * st[1 + i][j];
+          S = fmaf(bA, st[1 + i][j], S);
+          ab1[i] = fmaf(2.0f * d2 * bA, yb, ab1[i]);
+        }
+        acc[C::K - 1][p][j] = d1 * yb;
+        ab0 = fmaf(fmaf(d3, S, d2 * st[C::K - 1][j]), yb, ab0);
       }
 #pragma unroll
       for (int i = 0; i < C::N1; ++i) acc[1 + i][p][j] = ab1[i];
@@ -398,7 +421,8 @@ __device__ __forceinline__ void act_backward(float (&acc)[C::K][C::PT][8], int a
 // recompute a layer's OUTPUT jets Y_c from its stash and write them to smem S
 template <class C>
 __device__ __forceinline__ void recompute_outputs(float* __restrict__ S, int act,
-                                                  const float* __restrict__ stash_l, int row, int ua) {
+                                                  const float* __restrict__ stash_l, int row, int ua,
+                                                  const float (&beta)[C::PT][3]) {
 #pragma unroll
   for (int p = 0; p < C::PT; ++p) {
     float st[C::K][8];
@@ -419,7 +443,13 @@ __device__ __forceinline__ void recompute_outputs(float* __restrict__ S, int act
         const float Ai = st[1 + i][j];
         st[1 + C::N1 + i][j] = fmaf(d2 * Ai, Ai, d1 * st[1 + C::N1 + i][j]);
       }
-      if (C::MIX) st[C::K - 1][j] = fmaf(d2 * st[1][j], st[2][j], d1 * st[C::K - 1][j]);
+      if (C::MIX == 1) st[C::K - 1][j] = fmaf(d2 * st[1][j], st[2][j], d1 * st[C::K - 1][j]);
+      if (C::LAP) {
+        float Sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < C::N1; ++i) Sq = fmaf(beta[p][i] * st[1 + i][j], st[1 + i][j], Sq);
+        st[C::K - 1][j] = fmaf(d2, Sq, d1 * st[C::K - 1][j]);
+      }
 #pragma unroll
       for (int i = 0; i < C::N1; ++i) st[1 + i][j] *= d1;
       st[0][j] = y;
@@ -661,6 +691,12 @@ __global__ void __launch_bounds__(C::NT, 2) jet_mlp_kernel(const __grid_constant
       z[p][1] = (net.d_in > 1) ? __ldg(zp + 1) : 0.f;
       z[p][2] = (net.d_in > 2) ? __ldg(zp + 2) : 0.f;
     }
+    float beta[PT][3];
+#pragma unroll
+    for (int p = 0; p < PT; ++p)
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        beta[p][i] = (C::LAP && net.lap_aux[i] >= 0) ? __ldg(L.aux + gp[p] * L.n_aux + net.lap_aux[i]) : net.lap_beta[i];
 
     float acc[K][PT][8];
     // ---------------- forward through the hidden layers (layer 0 = feature layer)
@@ -679,7 +715,7 @@ __global__ void __launch_bounds__(C::NT, 2) jet_mlp_kernel(const __grid_constant
 #pragma unroll
         for (int p = 0; p < PT; ++p) {
           float hj[K][3];
-          feature_jets<C>(net, z[p], hj);
+          feature_jets<C>(net, z[p], beta[p], hj);
 #pragma unroll
           for (int c = 0; c < K; ++c)
 #pragma unroll
@@ -705,7 +741,7 @@ __global__ void __launch_bounds__(C::NT, 2) jet_mlp_kernel(const __grid_constant
         }
       }
       act_forward<C, TRAIN>(acc, L.wpack + net.off_b[l], l == 0 ? net.act_first : net.act_hidden,
-                            stash + l * STL, row, ua);
+                            stash + l * STL, row, ua, beta);
     }
 
     // ---------------- output layer (software.py:183, 215) + residual program
@@ -769,11 +805,11 @@ __global__ void __launch_bounds__(C::NT, 2) jet_mlp_kernel(const __grid_constant
       // ---------------- backward through the layers
 #pragma unroll 1
       for (int l = Lh - 1; l >= 0; --l) {
-        act_backward<C>(acc, l == 0 ? net.act_first : net.act_hidden, stash + l * STL, row, ua);
+        act_backward<C>(acc, l == 0 ? net.act_first : net.act_hidden, stash + l * STL, row, ua, beta);
         if (l == 0) break;
         __syncthreads();  // previous readers of Hs/Gs are done
         store_tile<C>(Gs, acc, row, ua);
-        recompute_outputs<C>(Hs, (l - 1 == 0) ? net.act_first : net.act_hidden, stash + (l - 1) * STL, row, ua);
+        recompute_outputs<C>(Hs, (l - 1 == 0) ? net.act_first : net.act_hidden, stash + (l - 1) * STL, row, ua, beta);
         __syncthreads();
         wgrad_layer<C>(Hs, Gs, bsc, gacc + net.off_w[l], gacc + net.off_b[l], tid);
 #pragma unroll
@@ -794,7 +830,7 @@ __global__ void __launch_bounds__(C::NT, 2) jet_mlp_kernel(const __grid_constant
 #pragma unroll
       for (int p = 0; p < PT; ++p) {
         float hj[K][3];
-        feature_jets<C>(net, z[p], hj);
+        feature_jets<C>(net, z[p], beta[p], hj);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           b0acc[j] += acc[0][p][j];

@@ -17,7 +17,8 @@
 template <int WP_, int N1_, int N2_, int MIX_, int NT_>
 struct MmaCfg {
   static constexpr int WP = WP_, N1 = N1_, N2 = N2_, MIX = MIX_;
-  static constexpr int K = 1 + N1 + N2 + MIX;
+  static constexpr bool LAP = (MIX == 2);
+  static constexpr int K = 1 + N1 + N2 + (MIX ? 1 : 0);
   static constexpr int NT = NT_;
   static constexpr int PT = 2;                  // fragment rows g and g+8
   static constexpr int NWARP = NT / 32;
@@ -157,7 +158,8 @@ __device__ __forceinline__ float4* mma_stash_ptr(float* stash_l, int c, int p, i
 // activation jets, forward (same math as act_forward in jet_kernel.cuh)
 template <class C, bool TRAIN>
 __device__ __forceinline__ void mma_act_forward(float (&acc)[C::K][2][8], const float* __restrict__ bias, int act,
-                                                float* __restrict__ stash_l, const MmaGeo& G, int tid) {
+                                                float* __restrict__ stash_l, const MmaGeo& G, int tid,
+                                                const float (&beta)[2][3]) {
   float b[8];
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
@@ -187,8 +189,14 @@ __device__ __forceinline__ void mma_act_forward(float (&acc)[C::K][2][8], const 
         const float Ai = acc[1 + i][p][j];
         acc[1 + C::N1 + i][p][j] = fmaf(d2[j] * Ai, Ai, d1[j] * acc[1 + C::N1 + i][p][j]);
       }
-      if (C::MIX)
+      if (C::MIX == 1)
         acc[C::K - 1][p][j] = fmaf(d2[j] * acc[1][p][j], acc[2][p][j], d1[j] * acc[C::K - 1][p][j]);
+      if (C::LAP) {
+        float S = 0.f;
+#pragma unroll
+        for (int i = 0; i < C::N1; ++i) S = fmaf(beta[p][i] * acc[1 + i][p][j], acc[1 + i][p][j], S);
+        acc[C::K - 1][p][j] = fmaf(d2[j], S, d1[j] * acc[C::K - 1][p][j]);
+      }
 #pragma unroll
       for (int i = 0; i < C::N1; ++i) acc[1 + i][p][j] *= d1[j];
       acc[0][p][j] = y[j];
@@ -210,7 +218,7 @@ __device__ __forceinline__ void mma_load_stash(float (&st)[C::K][8], const float
 // adjoint of the activation jets (same math as act_backward)
 template <class C>
 __device__ __forceinline__ void mma_act_backward(float (&acc)[C::K][2][8], int act, const float* __restrict__ stash_l,
-                                                 int tid) {
+                                                 int tid, const float (&beta)[2][3]) {
 #pragma unroll
   for (int p = 0; p < 2; ++p) {
     float st[C::K][8];
@@ -235,13 +243,25 @@ __device__ __forceinline__ void mma_act_backward(float (&acc)[C::K][2][8], int a
         ab1[i] = fmaf(2.0f * d2 * Ai, yb, ab1[i]);
         ab0 = fmaf(fmaf(d3 * Ai, Ai, d2 * Aii), yb, ab0);
       }
-      if (C::MIX) {
+      if (C::MIX == 1) {
         const float yb = acc[C::K - 1][p][j];
         const float A0 = st[1][j], A1 = st[2][j], A01 = st[C::K - 1][j];
         acc[C::K - 1][p][j] = d1 * yb;
         ab1[0] = fmaf(d2 * A1, yb, ab1[0]);
         ab1[C::N1 > 1 ? 1 : 0] = fmaf(d2 * A0, yb, ab1[C::N1 > 1 ? 1 : 0]);
         ab0 = fmaf(fmaf(d3 * A0, A1, d2 * A01), yb, ab0);
+      }
+      if (C::LAP) {
+        const float yb = acc[C::K - 1][p][j];
+        float S = 0.f;
+#pragma unroll
+        for (int i = 0; i < C::N1; ++i) {
+          const float bA = beta[p][i] * st[1 + i][j];
+          S = fmaf(bA, st[1 + i][j], S);
+          ab1[i] = fmaf(2.0f * d2 * bA, yb, ab1[i]);
+        }
+        acc[C::K - 1][p][j] = d1 * yb;
+        ab0 = fmaf(fmaf(d3, S, d2 * st[C::K - 1][j]), yb, ab0);
       }
 #pragma unroll
       for (int i = 0; i < C::N1; ++i) acc[1 + i][p][j] = ab1[i];
@@ -253,7 +273,7 @@ __device__ __forceinline__ void mma_act_backward(float (&acc)[C::K][2][8], int a
 // recompute a layer's output jets from its stash into the smem tile S
 template <class C>
 __device__ __forceinline__ void mma_recompute_outputs(float* __restrict__ S, int act, const float* __restrict__ stash_l,
-                                                      const MmaGeo& G, int tid) {
+                                                      const MmaGeo& G, int tid, const float (&beta)[2][3]) {
 #pragma unroll
   for (int p = 0; p < 2; ++p) {
     float st[C::K][8];
@@ -267,7 +287,13 @@ __device__ __forceinline__ void mma_recompute_outputs(float* __restrict__ S, int
         const float Ai = st[1 + i][j];
         st[1 + C::N1 + i][j] = fmaf(d2 * Ai, Ai, d1 * st[1 + C::N1 + i][j]);
       }
-      if (C::MIX) st[C::K - 1][j] = fmaf(d2 * st[1][j], st[2][j], d1 * st[C::K - 1][j]);
+      if (C::MIX == 1) st[C::K - 1][j] = fmaf(d2 * st[1][j], st[2][j], d1 * st[C::K - 1][j]);
+      if (C::LAP) {
+        float Sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < C::N1; ++i) Sq = fmaf(beta[p][i] * st[1 + i][j], st[1 + i][j], Sq);
+        st[C::K - 1][j] = fmaf(d2, Sq, d1 * st[C::K - 1][j]);
+      }
 #pragma unroll
       for (int i = 0; i < C::N1; ++i) st[1 + i][j] *= d1;
       st[0][j] = y;
@@ -470,6 +496,12 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
       z[p][1] = (net.d_in > 1) ? __ldg(zp + 1) : 0.f;
       z[p][2] = (net.d_in > 2) ? __ldg(zp + 2) : 0.f;
     }
+    float beta[2][3];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        beta[p][i] = (C::LAP && net.lap_aux[i] >= 0) ? __ldg(L.aux + gp[p] * L.n_aux + net.lap_aux[i]) : net.lap_beta[i];
 
     float acc[K][2][8];
 #pragma unroll 1
@@ -486,7 +518,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
           float hj[K][3];
-          feature_jets<C>(net, z[p], hj);
+          feature_jets<C>(net, z[p], beta[p], hj);
 #pragma unroll
           for (int c = 0; c < K; ++c)
 #pragma unroll
@@ -513,7 +545,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
       }
       lap(0);
       mma_act_forward<C, TRAIN>(acc, L.wpack + net.off_b[l], l == 0 ? net.act_first : net.act_hidden,
-                                stash + l * STL, G, tid);
+                                stash + l * STL, G, tid, beta);
       lap(1);
     }
 
@@ -607,12 +639,12 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
       }
 #pragma unroll 1
       for (int l = Lh - 1; l >= 0; --l) {
-        mma_act_backward<C>(acc, l == 0 ? net.act_first : net.act_hidden, stash + l * STL, tid);
+        mma_act_backward<C>(acc, l == 0 ? net.act_first : net.act_hidden, stash + l * STL, tid, beta);
         lap(3);
         if (l == 0) break;
         __syncthreads();
         mma_store_tile<C>(Gs, acc, G);
-        mma_recompute_outputs<C>(Hs, (l - 1 == 0) ? net.act_first : net.act_hidden, stash + (l - 1) * STL, G, tid);
+        mma_recompute_outputs<C>(Hs, (l - 1 == 0) ? net.act_first : net.act_hidden, stash + (l - 1) * STL, G, tid, beta);
         __syncthreads();
         lap(4);
         mma_wgrad_layer<C>(Hs, Gs, bsc, gacc + net.off_w[l], gacc + net.off_b[l], tid, G);
@@ -635,7 +667,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         float hj[K][3];
-        feature_jets<C>(net, z[p], hj);
+        feature_jets<C>(net, z[p], beta[p], hj);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           b0acc[j] += acc[0][p][j];

@@ -46,6 +46,10 @@ struct PinnNet {
   int off_w0, off_b0;
   int off_w[PINN_MAX_LAYERS], off_wt[PINN_MAX_LAYERS], off_b[PINN_MAX_LAYERS];
   int off_wl, off_bl;
+  // combined second-order channel (MIX == 2): L = sum_i lap_beta_i d_ii ; beta_i from aux column
+  // lap_aux[i] (>= 0) or the constant lap_beta[i]
+  float lap_beta[3];
+  int lap_aux[3];
   int pg;      // gpack size (floats)
   int pw;      // weight pack size (floats) = pg + (L-1)*WP*WP
 };

@@ -44,6 +44,7 @@ class PinnSpecC(C.Structure):
         ("n_ops", C.c_int32), ("ops", C.POINTER(C.c_int32)), ("n_consts", C.c_int32),
         ("consts", C.POINTER(C.c_float)), ("n_aux_col", C.c_int32), ("n_bc", C.c_int32),
         ("n_aux_user", C.c_int32), ("n_aux_ops", C.c_int32), ("aux_ops", C.POINTER(C.c_int32)),
+        ("lap_beta", C.c_float * 3), ("lap_aux", C.c_int32 * 3),
     ]
 
 
@@ -192,6 +193,9 @@ class PinnEngine:
         spec.n_aux_col, spec.n_bc = eq.n_aux, n_bc
         self._aux_ops = (C.c_int32 * max(1, len(eq.aux_ops)))(*(eq.aux_ops or [0]))
         spec.n_aux_user, spec.n_aux_ops, spec.aux_ops = eq.n_aux_user, len(eq.aux_ops), self._aux_ops
+        for i in range(3):
+            spec.lap_beta[i] = float(eq.lap_beta[i])
+            spec.lap_aux[i] = int(eq.lap_aux[i])
         h = C.c_void_p()
         _check(self.lib, self.lib.pinn_engine_create(C.byref(spec), device, C.byref(h)))
         self.h = h

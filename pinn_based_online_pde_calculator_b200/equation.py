@@ -35,6 +35,8 @@ _LETTERS = set(string.ascii_lowercase)
 
 # jet structures with a kernel instantiation (csrc/jet_configs.txt)
 SUPPORTED_JETS = {1: [(1, 1, 0)], 2: [(2, 1, 0), (2, 2, 0), (2, 2, 1)], 3: [(3, 2, 0)]}
+# (n1, 0, 2): one combined second-order channel  L = sum_i beta_i u_ii  (Laplacian-type operators)
+SUPPORTED_LAP = {2: (2, 0, 2), 3: (3, 0, 2)}
 
 
 class EquationError(ValueError):
@@ -327,15 +329,19 @@ class CompiledEquation:
     max_stack: int = 0
     n_aux_user: int = 0       # columns supplied by the caller (aux0..)
     aux_ops: List[int] = field(default_factory=list)  # program filling the hoisted columns from coords/user aux
+    lap_beta: List[float] = field(default_factory=lambda: [0.0, 0.0, 0.0])  # mix == 2: constant coefficients ...
+    lap_aux: List[int] = field(default_factory=lambda: [-1, -1, -1])        # ... or aux columns of beta_i
 
     @property
     def K(self) -> int:
-        return 1 + self.n1 + self.n2 + self.mix
+        return 1 + self.n1 + self.n2 + (1 if self.mix else 0)
 
     def channel_names(self, names: Sequence[str] = ("x", "y", "t")) -> List[str]:
         out = ["u"] + [f"u_{names[i]}" for i in range(self.n1)] + [f"u_{names[i]}{names[i]}" for i in range(self.n2)]
-        if self.mix:
+        if self.mix == 1:
             out.append(f"u_{names[0]}{names[1]}")
+        elif self.mix == 2:
+            out.append("L[u]")
         return out
 
 
@@ -369,7 +375,7 @@ def choose_jets(d_in: int, firsts: set, seconds: set) -> Tuple[int, int, int]:
 
 
 def _jet_free(n: Node) -> bool:
-    return n.kind not in ("u", "du") and all(_jet_free(a) for a in n.args)
+    return n.kind not in ("u", "du", "lap") and all(_jet_free(a) for a in n.args)
 
 
 def _has_point_data(n: Node) -> bool:
@@ -432,12 +438,92 @@ def hoist_point_terms(ast: Node, n_user_aux: int):
     return walk(ast), hoisted
 
 
-def compile_equation(expr: str, d_in: int = 2, extended: bool = True, hoist: bool = True) -> CompiledEquation:
+class _NotLinear(Exception):
+    pass
+
+
+def _has_second(n: Node) -> bool:
+    return (n.kind == "du" and len(n.name) == 2) or any(_has_second(a) for a in n.args)
+
+
+def _scale(coef: Optional[Node], by: Node, div: bool = False) -> Node:
+    if coef is None:
+        return Node("div", args=(Node("num", value=1.0), by)) if div else by
+    return Node("div" if div else "mul", args=(coef, by) if div else (by, coef))
+
+
+def linear_second_order(n: Node, d_in: int):
+    """Decompose n = sum_i coef_i * u_ii + rest with jet-free coef_i and a rest free of second
+    derivatives.  Returns ({dim: coef AST or None for 1}, rest AST or None) or raises _NotLinear."""
+    if not _has_second(n):
+        return {}, n
+    k = n.kind
+    if k == "du":
+        idx = sorted(coord_index(c, d_in) for c in n.name)
+        if idx[0] != idx[1]:
+            raise _NotLinear
+        return {idx[0]: None}, None
+    if k in ("add", "sub"):
+        da, ra = linear_second_order(n.args[0], d_in)
+        db, rb = linear_second_order(n.args[1], d_in)
+        if k == "sub":
+            db = {i: Node("neg", args=(c if c is not None else Node("num", value=1.0),)) for i, c in db.items()}
+            rb = None if rb is None else Node("neg", args=(rb,))
+        out = dict(da)
+        for i, c in db.items():
+            if i in out:
+                a = out[i] if out[i] is not None else Node("num", value=1.0)
+                b = c if c is not None else Node("num", value=1.0)
+                out[i] = Node("add", args=(a, b))
+            else:
+                out[i] = c
+        rest = ra if rb is None else (rb if ra is None else Node("add", args=(ra, rb)))
+        return out, rest
+    if k == "neg":
+        d, r = linear_second_order(n.args[0], d_in)
+        return ({i: Node("neg", args=(c if c is not None else Node("num", value=1.0),)) for i, c in d.items()},
+                None if r is None else Node("neg", args=(r,)))
+    if k == "mul":
+        a, b = n.args
+        if _has_second(a) and _has_second(b):
+            raise _NotLinear
+        lin, other = (a, b) if _has_second(a) else (b, a)
+        if not _jet_free(other):
+            raise _NotLinear  # quasi-linear coefficients depend on the network output
+        d, r = linear_second_order(lin, d_in)
+        return ({i: _scale(c, other) for i, c in d.items()}, None if r is None else Node("mul", args=(other, r)))
+    if k == "div":
+        a, b = n.args
+        if _has_second(b) or not _jet_free(b):
+            raise _NotLinear
+        d, r = linear_second_order(a, d_in)
+        return ({i: _scale(c, b, div=True) for i, c in d.items()}, None if r is None else Node("div", args=(r, b)))
+    raise _NotLinear
+
+
+def compile_equation(expr: str, d_in: int = 2, extended: bool = True, hoist: bool = True,
+                     combine_second: bool = True) -> CompiledEquation:
     ast = parse(expr, extended)
     firsts, seconds, aux = set(), set(), set()
     _collect(ast, d_in, firsts, seconds, aux)
-    n1, n2, mix = choose_jets(d_in, firsts, seconds)
     n_user = max(aux) + 1 if aux else 0
+    # Laplacian-type operators: second derivatives enter only through L = sum_i beta_i(x) u_ii with
+    # jet-free beta_i  ->  propagate ONE combined second-order channel (K = 1 + n1 + 1)
+    lap_coefs = None
+    if combine_second and hoist and d_in in SUPPORTED_LAP and len({p for p in seconds if p[0] == p[1]}) >= 2 \
+            and all(p[0] == p[1] for p in seconds):
+        try:
+            coefs, rest = linear_second_order(ast, d_in)
+            if len(coefs) >= 2:
+                lap_coefs = coefs
+                lap_node = Node("lap")
+                ast = lap_node if rest is None else Node("add", args=(rest, lap_node))
+        except _NotLinear:
+            lap_coefs = None
+    if lap_coefs is not None:
+        n1, n2, mix = SUPPORTED_LAP[d_in]
+    else:
+        n1, n2, mix = choose_jets(d_in, firsts, seconds)
     hoisted: List[Node] = []
     if hoist:
         ast, hoisted = hoist_point_terms(ast, n_user)
@@ -488,6 +574,8 @@ def compile_equation(expr: str, d_in: int = 2, extended: bool = True, hoist: boo
             emit(OP_COORD, coord_index(n.name, d_in), +1)
         elif k == "u":
             emit(OP_JET, 0, +1)
+        elif k == "lap":
+            emit(OP_JET, 1 + n1, +1)
         elif k == "aux":
             emit(OP_AUX, int(n.value), +1)
         elif k == "du":
@@ -528,6 +616,16 @@ def compile_equation(expr: str, d_in: int = 2, extended: bool = True, hoist: boo
             raise EquationError(f"cannot compile node {k}")
 
     gen(ast)
+    # coefficients of the combined second-order channel: constants or extra hoisted columns
+    if lap_coefs is not None:
+        for dim, coef in lap_coefs.items():
+            cv = 1.0 if coef is None else const_value(coef)
+            if cv is not None:
+                ce.lap_beta[dim] = float(cv)
+            else:
+                ce.lap_aux[dim] = n_user + len(hoisted)
+                hoisted.append(coef)
+        ce.n_aux = n_user + len(hoisted)
     target = ce.aux_ops
     for i, sub in enumerate(hoisted):
         depth = 0

@@ -34,11 +34,14 @@ class Workload:
     def flops_per_point(self) -> Dict[str, float]:
         """Algorithmic FLOPs per collocation point per train step: 2K(2 M1 + M2)
         (SURVEY.md section 8d); boundary points the same with K=1."""
-        eq = self.eq
+        eq_full = compile_equation(self.expr, d_in=self.net.d_in, combine_second=False)
         F, W, L = self.net.n_feat, self.net.width, self.net.n_hidden
         m1 = F * W + (L - 1) * W * W + W
         m2 = (L - 1) * W * W + W
-        return dict(col=2.0 * eq.K * (2 * m1 + m2), bc=2.0 * (2 * m1 + m2), K=eq.K)
+        # K = channels of the SURVEY's accounting (one per derivative); K_exec = channels the kernel
+        # propagates (Laplacian-type operators need one combined second-order channel)
+        return dict(col=2.0 * eq_full.K * (2 * m1 + m2), bc=2.0 * (2 * m1 + m2), K=eq_full.K,
+                    K_exec=self.eq.K, col_exec=2.0 * self.eq.K * (2 * m1 + m2))
 
 
 def truncated_normal(rng: np.random.RandomState, shape, lo=-2.0, hi=2.0) -> np.ndarray:

@@ -35,23 +35,48 @@ def test_strict_parser_rejects_what_the_validator_rejects():
     parse("u_xx + 3*u_yy - 5", extended=False)
 
 
-@pytest.mark.parametrize("expr,d_in,jets", [
-    ("u_xx + 2", 1, (1, 1, 0)),
-    ("u_xx + u_yy + 2*y*(1-y) + 2*x*(1-x)", 2, (2, 2, 0)),
-    ("u_t + u*u_x - 0.003183*u_xx", 2, (2, 1, 0)),
-    ("u_rr + 1/r*u_r + 1/(r**2)*u_tt", 2, (2, 2, 0)),
-    ("u_xx + 2*u_xy + u_yy", 2, (2, 2, 1)),
-    ("u_t - 0.1*(u_xx + u_yy)", 3, (3, 2, 0)),
-    ("u_x + u_y", 2, (2, 1, 0)),
+@pytest.mark.parametrize("expr,d_in,jets,jets_lap", [
+    ("u_xx + 2", 1, (1, 1, 0), (1, 1, 0)),
+    ("u_xx + u_yy + 2*y*(1-y) + 2*x*(1-x)", 2, (2, 2, 0), (2, 0, 2)),
+    ("u_t + u*u_x - 0.003183*u_xx", 2, (2, 1, 0), (2, 1, 0)),
+    ("u_rr + 1/r*u_r + 1/(r**2)*u_tt", 2, (2, 2, 0), (2, 0, 2)),
+    ("u_xx + 2*u_xy + u_yy", 2, (2, 2, 1), (2, 2, 1)),
+    ("u_t - 0.1*(u_xx + u_yy)", 3, (3, 2, 0), (3, 0, 2)),
+    ("u_x + u_y", 2, (2, 1, 0), (2, 1, 0)),
+    ("u*u_xx + u_yy", 2, (2, 2, 0), (2, 2, 0)),            # quasi-linear: coefficient depends on u
+    ("(u_xx + u_yy)**2 - 1", 2, (2, 2, 0), (2, 2, 0)),     # not linear at top level
 ])
-def test_jet_structure_selection(expr, d_in, jets):
-    ce = compile_equation(expr, d_in=d_in)
+def test_jet_structure_selection(expr, d_in, jets, jets_lap):
+    ce = compile_equation(expr, d_in=d_in, combine_second=False)
     assert (ce.n1, ce.n2, ce.mix) == jets
+    ce = compile_equation(expr, d_in=d_in)
+    assert (ce.n1, ce.n2, ce.mix) == jets_lap
+
+
+def test_combined_second_order_channel_coefficients():
+    ce = compile_equation("u_xx + 3*u_yy - 5", d_in=2)
+    assert ce.K == 4 and ce.lap_beta[:2] == [1.0, 3.0] and ce.lap_aux == [-1, -1, -1]
+    ce = compile_equation("u_rr + 1/r*u_r + 1/(r**2)*u_tt", d_in=2)
+    assert ce.lap_beta[0] == 1.0 and ce.lap_aux[1] >= 0          # 1/r**2 is a per-point column
+    ce = compile_equation("u_t - 0.1*(u_xx + u_yy)", d_in=3)
+    assert ce.K == 5 and ce.lap_beta[:2] == [-0.1, -0.1]
+    # residual value with L = sum beta_i u_ii equals the full expression
+    rng = np.random.RandomState(1)
+    z = rng.rand(32, 2) + 0.5
+    full = compile_equation("x*u_xx/2 - (1+y)*u_yy + u_x*u", d_in=2, combine_second=False)
+    lap = compile_equation("x*u_xx/2 - (1+y)*u_yy + u_x*u", d_in=2)
+    jets = rng.rand(32, 5)
+    want = evaluate_host(full, z, jets)
+    L = z[:, 0] / 2 * jets[:, 3] - (1 + z[:, 1]) * jets[:, 4]
+    got = evaluate_host(lap, z, np.column_stack([jets[:, 0], jets[:, 1], jets[:, 2], L]))
+    assert np.allclose(got, want, rtol=1e-12)
 
 
 def test_unsupported_derivative_sets_raise():
+    ce = compile_equation("u_xx + u_yy + u_zz", d_in=3)   # 3-D Laplacian: one combined second-order channel
+    assert (ce.n1, ce.n2, ce.mix) == (3, 0, 2) and ce.lap_beta == [1.0, 1.0, 1.0]
     with pytest.raises(EquationError):
-        compile_equation("u_xx + u_yy + u_zz", d_in=3)   # K=7 has no kernel instantiation
+        compile_equation("u_xx*u_yy + u_zz", d_in=3)       # three separate second derivatives: K=7, no kernel
     with pytest.raises(EquationError):
         compile_equation("u_xt", d_in=3)
     with pytest.raises(EquationError):
@@ -64,7 +89,7 @@ def test_unsupported_derivative_sets_raise():
     "((x + y) * (x - (y - u))) / (1 + x*x)",
 ])
 def test_bytecode_matches_python_eval(expr):
-    ce = compile_equation(expr, d_in=2)
+    ce = compile_equation(expr, d_in=2, combine_second=False)
     rng = np.random.RandomState(0)
     n = 64
     z = rng.rand(n, 2) + 0.5
@@ -92,9 +117,9 @@ def test_program_limits_are_enforced():
 
 
 def test_point_terms_are_hoisted_out_of_the_step_program():
-    ce = compile_equation("u_xx + u_yy + 2*y*(1-y) + 2*x*(1-x)", d_in=2)
+    ce = compile_equation("u_xx + u_yy + 2*y*(1-y) + 2*x*(1-x)", d_in=2, combine_second=False)
     assert len(ce.ops) == 5 and ce.n_aux == 1 and ce.n_aux_user == 0 and len(ce.aux_ops) > 0
-    ce = compile_equation("u_rr + 1/r*u_r + 1/(r**2)*u_tt", d_in=2)
+    ce = compile_equation("u_rr + 1/r*u_r + 1/(r**2)*u_tt", d_in=2, combine_second=False)
     assert ce.n_aux == 2 and len(ce.ops) == 9          # the variable coefficients become columns
     ce = compile_equation("u_t + u*u_x - 0.003183*u_xx", d_in=2)
     assert ce.n_aux == 0 and not ce.aux_ops             # nothing to hoist

@@ -12,6 +12,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pinn_based_online_pde_calculator_b200 import PinnEngine
 from pinn_based_online_pde_calculator_b200.workloads import init_params, make_points, make_workload
 
+_cpu = "--cpu" in sys.argv
+sys.argv = [a for a in sys.argv if a != "--cpu"]
 name = sys.argv[1] if len(sys.argv) > 1 else "C1"
 n_adam = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 n_lbfgs = int(sys.argv[3]) if len(sys.argv) > 3 else 500
@@ -44,10 +46,12 @@ eng.adam_init()
 hist = []
 for k in range(0, n_adam, 250):
     eng.adam_steps(250, 1e-3, want_rows=False)
-    hist.append((time.perf_counter() - t0, "adam", k + 250, l2()))
+    e = l2()  # synchronises
+    hist.append((time.perf_counter() - t0, "adam", k + 250, e))
 for k in range(0, n_lbfgs, 50):
     res, rows = eng.lbfgs(50, 1e-10)
-    hist.append((time.perf_counter() - t0, "lbfgs", k + 50, l2(), res["evaluations"], res["failed"], rows[-1][0] if rows else None))
+    e = l2()
+    hist.append((time.perf_counter() - t0, "lbfgs", k + 50, e, res["evaluations"], res["failed"], rows[-1][0] if rows else None))
     if res["failed"] or res["converged"]:
         break
 for h in hist:
@@ -57,7 +61,7 @@ for thr in (1e-2, 1e-3):
     print(f"time-to-L2<{thr:g}:", f"{hit[0][0]:.3f} s ({hit[0][1]} {hit[0][2]})" if hit else "not reached")
 
 # ---- the same schedule on the CPU oracle (float64), bounded to the Adam part: time to the same thresholds
-if "--cpu" in sys.argv:
+if _cpu:
     import torch
     from oracle import reference_oracle as O
     from pinn_based_online_pde_calculator_b200.workloads import unflatten

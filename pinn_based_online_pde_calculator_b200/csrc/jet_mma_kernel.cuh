@@ -87,7 +87,7 @@ template <class C>
 __device__ __forceinline__ void mma_gemm_chunk(float (&acc)[C::K][2][8], const float* __restrict__ S,
                                                const float* __restrict__ wc, int kbase, const MmaGeo& G) {
   const int tA = G.t ^ G.swz, tB = tA ^ 4;
-#pragma unroll 1
+#pragma unroll 2
   for (int kk = 0; kk < C::KC; kk += 8) {
     uint32_t bh[4][2], bl[4][2];
 #pragma unroll

@@ -134,6 +134,15 @@ int pinn_engine_lbfgs(pinn_engine_t* h, int32_t max_iter, double tol, int32_t va
 int pinn_nccl_unique_id(uint8_t id_out[128]);
 int pinn_engine_init_nccl(pinn_engine_t* h, const uint8_t id[128], int32_t rank, int32_t world);
 
+/* Device-side samplers.  pinn_sample_lhs: Latin-hypercube points, the
+ * device counterpart of pyDOE.lhs (sw:553,562): out[i][col0+j] = lo_j + (perm_j(i)+U)/n*(hi_j-lo_j),
+ * row stride ld.  pinn_sample_cdf2d: colloc2D_set (sw:87-136): cum_host = [0, cumsum(F cells)]
+ * over ncy x ncx cells (row-major), lower-left grid corner (x0,y0), cell size (dx,dy). */
+int pinn_sample_lhs(int device, void* stream, uint32_t seed, int64_t n, int32_t d, const float* lo,
+                    const float* hi, float* out_dev, int32_t ld, int32_t col0);
+int pinn_sample_cdf2d(int device, void* stream, uint32_t seed, int64_t n, const double* cum_host, int32_t ncy,
+                      int32_t ncx, float x0, float y0, float dx, float dy, float* out_dev, int32_t ld);
+
 /* fp32 FMA-pipe microbenchmark (roofline denominator of the SIMT path):
  * returns achieved TFLOP/s; variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2 */
 int pinn_fma_peak(int device, int variant, double* tflops_out);

@@ -14,6 +14,7 @@
 
 #include "../../include/pinn_engine.h"
 #include "aux_kernels.cuh"
+#include "sampler_kernels.cuh"
 #include "jet_launch.h"
 #include "pinn_common.h"
 
@@ -1014,6 +1015,39 @@ extern "C" int pinn_engine_init_nccl(pinn_engine_t* h, const uint8_t id[128], in
   h->rank = rank;
   h->world = world;
   h->graph_valid = false;
+  return 0;
+}
+
+// ---------------------------------------------------------------- device samplers
+extern "C" int pinn_sample_lhs(int device, void* stream, uint32_t seed, int64_t n, int32_t d, const float* lo,
+                               const float* hi, float* out_dev, int32_t ld, int32_t col0) {
+  CK(cudaSetDevice(device));
+  if (n <= 0) return 0;
+  if (d < 1 || d > 3) return fail("d must be 1..3");
+  if (n >= (1ll << 32)) return fail("n too large");
+  uint32_t bits = 1;
+  while ((1ull << (2 * bits)) < (unsigned long long)n) ++bits;
+  const float3 l3 = make_float3(lo[0], d > 1 ? lo[1] : 0.f, d > 2 ? lo[2] : 0.f);
+  const float3 h3 = make_float3(hi[0], d > 1 ? hi[1] : 0.f, d > 2 ? hi[2] : 0.f);
+  k_sample_lhs<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out_dev, n, d, ld, col0, l3, h3, seed, bits);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pinn_sample_cdf2d(int device, void* stream, uint32_t seed, int64_t n, const double* cum_host,
+                                 int32_t ncy, int32_t ncx, float x0, float y0, float dx, float dy, float* out_dev,
+                                 int32_t ld) {
+  CK(cudaSetDevice(device));
+  if (n <= 0) return 0;
+  const int ncell = ncy * ncx;
+  double* d_cum = nullptr;
+  CK(cudaMalloc(&d_cum, sizeof(double) * (ncell + 1)));
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(d_cum, cum_host, sizeof(double) * (ncell + 1), cudaMemcpyHostToDevice, st));
+  k_sample_cdf2d<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out_dev, n, ld, d_cum, ncell, ncx, x0, y0, dx, dy, seed);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  cudaFree(d_cum);
   return 0;
 }
 

@@ -32,7 +32,7 @@ EXPORTS = [
     "pinn_engine_get_params", "pinn_engine_set_points", "pinn_engine_set_global_counts",
     "pinn_engine_set_loss", "pinn_engine_loss_grad", "pinn_engine_adam_init", "pinn_engine_adam_steps",
     "pinn_engine_eval", "pinn_engine_lbfgs", "pinn_nccl_unique_id", "pinn_engine_init_nccl",
-    "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels", "pinn_engine_kernel_kind", "pinn_engine_phase_profile",
+    "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels", "pinn_engine_kernel_kind", "pinn_engine_phase_profile", "pinn_sample_lhs", "pinn_sample_cdf2d",
 ]
 
 
@@ -80,6 +80,10 @@ def load_library(path: Optional[str] = None):
     lib.pinn_engine_launches_per_eval.argtypes = [C.c_void_p]
     lib.pinn_engine_kernel_kind.argtypes = [C.c_void_p]
     lib.pinn_engine_phase_profile.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    lib.pinn_sample_lhs.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_int64, C.c_int32, C.POINTER(C.c_float),
+                                    C.POINTER(C.c_float), C.c_void_p, C.c_int32, C.c_int32]
+    lib.pinn_sample_cdf2d.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int32]
     lib.pinn_engine_set_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.pinn_engine_get_params.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.pinn_engine_set_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
@@ -358,6 +362,36 @@ class PinnEngine:
         buf = (C.c_uint8 * 128)()
         _check(lib, lib.pinn_nccl_unique_id(buf))
         return bytes(buf)
+
+
+def sample_lhs_device(n: int, lo: Sequence[float], hi: Sequence[float], seed: int, device: int = 0, out=None, col0: int = 0):
+    """Latin-hypercube points on the device (pyDOE.lhs, software.py:553,562): torch CUDA tensor [n, d]."""
+    import torch
+
+    lib = load_library()
+    d = len(lo)
+    if out is None:
+        out = torch.empty((n, d), dtype=torch.float32, device=f"cuda:{device}")
+    lo_c, hi_c = (C.c_float * 3)(*([float(v) for v in lo] + [0.0] * (3 - d))), (C.c_float * 3)(*([float(v) for v in hi] + [0.0] * (3 - d)))
+    st = torch.cuda.current_stream(device).cuda_stream
+    _check(lib, lib.pinn_sample_lhs(device, C.c_void_p(st), seed & 0xFFFFFFFF, n, d, lo_c, hi_c, C.c_void_p(out.data_ptr()),
+                                    out.stride(0), col0))
+    return out
+
+
+def sample_cdf2d_device(n: int, X: np.ndarray, Y: np.ndarray, F: np.ndarray, seed: int, device: int = 0):
+    """colloc2D_set (software.py:87-136) on the device: n points from the cell distribution F on grid X, Y."""
+    import torch
+
+    lib = load_library()
+    Fc = np.asarray(F, dtype=np.float64)[0:-1, 0:-1]
+    cum = np.ascontiguousarray(np.hstack([0.0, np.cumsum(Fc.reshape(-1))]))
+    out = torch.empty((n, 2), dtype=torch.float32, device=f"cuda:{device}")
+    st = torch.cuda.current_stream(device).cuda_stream
+    _check(lib, lib.pinn_sample_cdf2d(device, C.c_void_p(st), seed & 0xFFFFFFFF, n, cum.ctypes.data_as(C.c_void_p),
+                                      Fc.shape[0], Fc.shape[1], float(X[0, 0]), float(Y[0, 0]), float(X[0, 1] - X[0, 0]),
+                                      float(Y[1, 0] - Y[0, 0]), C.c_void_p(out.data_ptr()), 2))
+    return out
 
 
 def fma_peak_tflops(device: int = 0, variant: int = 0) -> float:

@@ -92,9 +92,12 @@ def colloc2D_set(key: Key, X: np.ndarray, Y: np.ndarray, F: np.ndarray, Ns: int)
     return np.hstack((Px[:, None], Py[:, None]))
 
 
-def data_func_create(N_col: Sequence[int], N_bd: int, boundary: Dict[str, float], domain: Dict[str, float]):
+def data_func_create(N_col: Sequence[int], N_bd: int, boundary: Dict[str, float], domain: Dict[str, float],
+                     sampler: str = "host", device: int = 0):
     """sw:521-577. N_col = [n_col (LHS interior), n_bd (border-ring collocation), n_add
-    (residual-adaptive)]; N_bd = points per boundary condition (sw:694)."""
+    (residual-adaptive)]; N_bd = points per boundary condition (sw:694).
+    sampler='device' draws the collocation set with the CUDA samplers (pinn_sample_lhs /
+    pinn_sample_cdf2d) and returns x_col as a CUDA tensor; boundary groups stay on the host."""
     r = np.linspace(domain["x_min"], domain["x_max"], 111)
     t = np.linspace(domain["y_min"], domain["y_max"], 111)
     R, T = np.meshgrid(r, t)
@@ -114,6 +117,17 @@ def data_func_create(N_col: Sequence[int], N_bd: int, boundary: Dict[str, float]
             hi = np.array([boundary[f"bd_x{i + 1}_max"], boundary[f"bd_y{i + 1}_max"]], dtype=np.float64)
             x_bd.append(lhs(2, N_bd) * (hi - lo) + lo)
             u_bd.append(boundary[f"bd_u{i + 1}"] * np.ones((N_bd, 1)))
+        if sampler == "device":
+            import torch
+
+            from .engine import sample_cdf2d_device, sample_lhs_device
+
+            s0, s1, s2 = (int(k.rng().integers(0, 2 ** 31)) for k in key.split(3))
+            parts = [sample_lhs_device(int(N_col[0]), org, org + span, s0, device),
+                     sample_cdf2d_device(int(N_col[1]), R, T, F_bd, s1, device)]
+            parts += [torch.as_tensor(a, dtype=torch.float32, device=f"cuda:{device}") for a in x_bd]
+            parts.append(sample_cdf2d_device(int(N_col[2]), R_add, T_add, np.asarray(F), s2, device))
+            return dict(x_col=torch.cat(parts, 0), cond_bd=[x_bd, u_bd])
         x_col = lhs(2, int(N_col[0])) * span + org
         xc_bd = colloc2D_set(keys[0], R, T, F_bd, N_col[1])
         xc_add = colloc2D_set(keys[1], R_add, T_add, np.asarray(F), N_col[2])
@@ -147,9 +161,18 @@ class Model:
         return self.engine.eval(z, base=self._base_jets(z), want_jets=want_jets)
 
     def set_data(self, data):
-        x_col = np.ascontiguousarray(data["x_col"], dtype=np.float32)
         x_bd = [np.ascontiguousarray(a, dtype=np.float32) for a in data["cond_bd"][0]]
         u_bd = [np.ascontiguousarray(a, dtype=np.float32).reshape(-1) for a in data["cond_bd"][1]]
+        if not isinstance(data["x_col"], np.ndarray) and getattr(data["x_col"], "is_cuda", False):
+            import torch  # device-resident collocation set (sampler='device')
+
+            x_col = data["x_col"].contiguous()
+            dev = lambda a: torch.as_tensor(a, dtype=torch.float32, device=x_col.device)
+            base_col = self.base.engine.eval(x_col, want_u=False, want_f=False, want_jets=True)[2] if self.base is not None else None
+            base_bd = [dev(self.base.predict(a)[0]) for a in x_bd] if self.base is not None else None
+            self.engine.set_points(x_col, [dev(a) for a in x_bd], [dev(a) for a in u_bd], base_col=base_col, base_bd=base_bd)
+            return
+        x_col = np.ascontiguousarray(data["x_col"], dtype=np.float32)
         base_col = self._base_jets(x_col)
         base_bd = None
         if self.base is not None:
@@ -280,6 +303,7 @@ def run_pinn_training(
         device: int = 0,
         seed: int = 1234,
         n_bd_points: int = 100,
+        sampler: str = "auto",
 ):
     """Same 11 kwargs as the reference (sw:626-638); keyword-only extras are extensions."""
     m_x_min, m_x_max = domain["x_min"], domain["x_max"]
@@ -291,6 +315,9 @@ def run_pinn_training(
     mode = equation_mode or os.environ.get("PINN_B200_EQUATION_MODE", "compile")
     exact = exact_solution or _exact_default
 
+    if sampler == "auto":  # host numpy streams for reference-sized sets, CUDA samplers for large ones
+        sampler = "device" if sample_points["n_col"] >= 200_000 else "host"
+    as_np = lambda a: a if isinstance(a, np.ndarray) else a.cpu().numpy()
     base_dir = Path(output_dir)
     base_dir.mkdir(parents=True, exist_ok=True)
 
@@ -317,14 +344,14 @@ def run_pinn_training(
                        feature_map=feature_map, d_in=2)
     model1 = Model(net1, eq, n_bc, lw_eqn=m_f, device=device)
     model1.engine.set_params(init_params(net1, seed))
-    dataf1 = data_func_create(N_col, N_bd, boundary, domain)
+    dataf1 = data_func_create(N_col, N_bd, boundary, domain, sampler=sampler, device=device)
     Fs = R * 0 + 1
     key_adam = keys[1]
     key_lbfgs = keys[2].split(1)
     Rg, Tg = dataf1.R, dataf1.T
     Fg = Rg * 0 + 1
     data1 = dataf1(key_adam, Fg, Rg, Tg)
-    save_colpoints(Fs, data1["x_col"], base_dir / "collocation_point_1.npz")
+    save_colpoints(Fs, as_np(data1["x_col"]), base_dir / "collocation_point_1.npz")
 
     model1.set_data(data1)
     model1.set_ref(1.0)
@@ -368,12 +395,12 @@ def run_pinn_training(
                        feature_map=feature_map, d_in=2)
     model2 = Model(net2, eq, n_bc, lw_eqn=lw2, device=device, base=model1)
     model2.engine.set_params(init_params(net2, seed + 3))
-    dataf2 = data_func_create(N_col * 2, N_bd * 2, boundary, domain)
+    dataf2 = data_func_create(N_col * 2, N_bd * 2, boundary, domain, sampler=sampler, device=device)
     key_adam = keys[4]
     key_lbfgs = keys[5].split(1)
     Fg = Rg * 0 + 1
     data2 = dataf2(key_adam, Fg, Rg, Tg)
-    save_colpoints(Fs, data2["x_col"], base_dir / "collocation_point_2.npz")
+    save_colpoints(Fs, as_np(data2["x_col"]), base_dir / "collocation_point_2.npz")
     model2.set_data(data2)
     model2.set_ref(1.0)
     model2.set_ref(model2.loss_info()[0])

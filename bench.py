@@ -88,14 +88,29 @@ def cpu_reference_run(wl, n_cpu: int, steps: int, warmup: int):
 
 # ----------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
+    """SM clock / throttle-reason sampling DURING the timed region: NVML in a thread (2 ms period),
+    falling back to `nvidia-smi -lms 100` when pynvml is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.gpu, self.proc, self.lines, self.samples, self.stop_flag = gpu_index, None, [], [], False
+        self.nvml = None
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -105,11 +120,38 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.th.join(timeout=1)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": float(self.sm_max), "reasons": ["no samples"]}
+            n = self.nvml
+            bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            reasons = sorted(k for k, b in bits.items() if any(r & b for _, _, r in self.samples))
+            sm = [s for s, _, _ in self.samples]
+            return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.sm_max), "power_w_max": float(max(p for _, p, _ in self.samples)),
+                    "samples": len(sm), "source": "nvml", "reasons": reasons}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -134,7 +176,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         hi = [s for s in sm if s >= 0.5 * max(sm)]
         return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "source": "nvidia-smi", "reasons": sorted(reasons)}
 
 
 # ----------------------------------------------------------------------------- main

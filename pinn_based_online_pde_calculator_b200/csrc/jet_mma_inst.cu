@@ -8,7 +8,7 @@
 #endif
 
 #ifndef J_NT
-#define J_NT (J_WP <= 64 ? 128 : 256)
+#define J_NT (J_WP <= 128 ? 128 : 256)
 #endif
 using Cfg = MmaCfg<J_WP, J_N1, J_N2, J_MIX, J_NT>;
 

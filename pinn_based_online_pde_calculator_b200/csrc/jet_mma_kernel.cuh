@@ -28,13 +28,13 @@ struct MmaCfg {
   static constexpr int ROWS = TP / 2;           // thread rows (mw, g)
   static constexpr int SP = K * WP + 8;         // smem point stride == 8 (mod 32)
   static constexpr int WPS = WP + 8;            // weight row stride (smem chunk and pack)
-  static constexpr int KC = (NT <= 64) ? 16 : (K >= 6) ? (WP <= 64 ? 16 : 8) : (WP <= 64 ? 32 : (WP <= 128 ? 16 : 8));
+  static constexpr int KC = (NT <= 64) ? 16 : (K >= 6) ? (WP <= 64 ? 16 : 8) : (WP <= 64 ? (K <= 4 ? 64 : 32) : (WP <= 128 ? 16 : 8));
   static constexpr int NCH = WP / KC;
   static constexpr uint32_t CHUNK_BYTES = KC * WPS * 4;
   static constexpr int SCR_HALF = ((5 * ROWS * WP + ROWS + 1) / 2 + 3) / 4 * 4;  // final-fold scratch / 2
   static constexpr int HS_FLOATS = (TP * SP > SCR_HALF) ? TP * SP : SCR_HALF;
-  // weight-gradient work items: (16 k-rows) x (8 n-tiles = 64 units)
-  static constexpr int WITEMS = (WP / 16) * (WP / 64);
+  // weight-gradient work items: (32 k-rows) x (32 units)
+  static constexpr int WITEMS = (WP / 32) * (WP / 32);
   static constexpr int WPASS = (WITEMS + NWARP - 1) / NWARP;
   static constexpr bool OK = (WP >= 64) && (NWARP % NW == 0) && (MW >= 1) && (WITEMS % NWARP == 0 || WITEMS < NWARP) &&
                              (5 * ROWS * WP + ROWS <= 2 * HS_FLOATS);
@@ -326,13 +326,17 @@ __device__ __forceinline__ void mma_wgrad_layer(const float* __restrict__ Hs, co
   }
   (void)bsc;
   const int warp = tid >> 5;
+  // work item = (32 k-rows = 2 m-tiles) x (32 units = 4 n-tiles): 8 accumulator tiles per warp,
+  // 8 A + 8 B fragment elements per reduction step
 #pragma unroll 1
   for (int item = warp; item < C::WITEMS; item += C::NWARP) {
-    const int mt = item / (C::WP / 64), ng = item % (C::WP / 64);
-    const int k0 = 16 * mt, u0 = 64 * ng;
-    float w[8][4];
+    const int mt = item / (C::WP / 32), ng = item % (C::WP / 32);
+    const int k0 = 32 * mt, u0 = 32 * ng;
+    float w[2][4][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) w[nt][0] = w[nt][1] = w[nt][2] = w[nt][3] = 0.f;
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) w[m][nt][0] = w[m][nt][1] = w[m][nt][2] = w[m][nt][3] = 0.f;
 #pragma unroll 1
     for (int ps = 0; ps < C::TP / 8; ++ps) {
       const int pa = 8 * ps + G.t, pb = pa + 4;  // swizzle 0 for pa, 4 for pb
@@ -340,37 +344,49 @@ __device__ __forceinline__ void mma_wgrad_layer(const float* __restrict__ Hs, co
       for (int c = 0; c < C::K; ++c) {
         const float* ha = Hs + pa * C::SP + c * C::WP;
         const float* hb = Hs + pb * C::SP + c * C::WP;
-        uint32_t ah[4], al[4];
-        split_tf32(ha[k0 + G.g], ah[0], al[0]);
-        split_tf32(ha[k0 + G.g + 8], ah[1], al[1]);
-        split_tf32(hb[(k0 + G.g) ^ 4], ah[2], al[2]);
-        split_tf32(hb[(k0 + G.g + 8) ^ 4], ah[3], al[3]);
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const int kr = k0 + 16 * m + G.g;
+          split_tf32(ha[kr], ah[m][0], al[m][0]);
+          split_tf32(ha[kr + 8], ah[m][1], al[m][1]);
+          split_tf32(hb[kr ^ 4], ah[m][2], al[m][2]);
+          split_tf32(hb[(kr + 8) ^ 4], ah[m][3], al[m][3]);
+        }
         const float* ga = Gs + pa * C::SP + c * C::WP + u0 + G.g;
         const float* gb = Gs + pb * C::SP + c * C::WP + ((u0 + G.g) ^ 4);
-        uint32_t bh[8][2], bl[8][2];
+        uint32_t bh[4][2], bl[4][2];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 0; nt < 4; ++nt) {
           split_tf32(ga[8 * nt], bh[nt][0], bl[nt][0]);
           split_tf32(gb[8 * nt], bh[nt][1], bl[nt][1]);
         }
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) mma_tf32(w[nt][0], w[nt][1], w[nt][2], w[nt][3], al, bh[nt][0], bh[nt][1]);
+        for (int m = 0; m < 2; ++m)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) mma_tf32(w[nt][0], w[nt][1], w[nt][2], w[nt][3], ah, bl[nt][0], bl[nt][1]);
+          for (int nt = 0; nt < 4; ++nt) mma_tf32(w[m][nt][0], w[m][nt][1], w[m][nt][2], w[m][nt][3], al[m], bh[nt][0], bh[nt][1]);
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) mma_tf32(w[nt][0], w[nt][1], w[nt][2], w[nt][3], ah, bh[nt][0], bh[nt][1]);
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_tf32(w[m][nt][0], w[m][nt][1], w[m][nt][2], w[m][nt][3], ah[m], bl[nt][0], bl[nt][1]);
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_tf32(w[m][nt][0], w[m][nt][1], w[m][nt][2], w[m][nt][3], ah[m], bh[nt][0], bh[nt][1]);
       }
     }
-    // read-modify-write the CTA-private accumulator (rows k0+g, k0+g+8; cols u0+8nt+2t, +1)
+    // read-modify-write the CTA-private accumulator (rows k0+16m+g, +8; cols u0+8nt+2t, +1)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      float2* d0 = reinterpret_cast<float2*>(gW + (size_t)(k0 + G.g) * C::WPS + u0 + 8 * nt + 2 * G.t);
-      float2* d1 = reinterpret_cast<float2*>(gW + (size_t)(k0 + G.g + 8) * C::WPS + u0 + 8 * nt + 2 * G.t);
-      float2 v0 = *d0, v1 = *d1;
-      v0.x += w[nt][0]; v0.y += w[nt][1];
-      v1.x += w[nt][2]; v1.y += w[nt][3];
-      *d0 = v0; *d1 = v1;
-    }
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float2* d0 = reinterpret_cast<float2*>(gW + (size_t)(k0 + 16 * m + G.g) * C::WPS + u0 + 8 * nt + 2 * G.t);
+        float2* d1 = reinterpret_cast<float2*>(gW + (size_t)(k0 + 16 * m + G.g + 8) * C::WPS + u0 + 8 * nt + 2 * G.t);
+        float2 v0 = *d0, v1 = *d1;
+        v0.x += w[m][nt][0]; v0.y += w[m][nt][1];
+        v1.x += w[m][nt][2]; v1.y += w[m][nt][3];
+        *d0 = v0; *d1 = v1;
+      }
   }
 }
 

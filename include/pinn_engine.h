@@ -81,7 +81,7 @@ int32_t pinn_engine_tile_points(pinn_engine_t* h);
 int32_t pinn_engine_launches_per_eval(pinn_engine_t* h);
 /* kernel family chosen at create: 0 = fp32 SIMT (packed FFMA2), 1 = 3xTF32 mma.sync tensor-core kernel.
  * Selection: environment PINN_B200_KERNEL = simt | mma | auto (auto: tensor-core kernel for padded
- * widths 64 and 128, fp32 kernel otherwise). */
+ * widths 64, 128 and 256, fp32 kernel for 32). */
 int32_t pinn_engine_kernel_kind(pinn_engine_t* h);
 
 /* params pytree <-> flat fp32 vector (sw:142-154 layout, sw:466 order) */

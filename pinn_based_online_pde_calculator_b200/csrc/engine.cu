@@ -237,7 +237,7 @@ extern "C" int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engi
     const JetKernelInfo *c0 = pinn_find_kernel(wp, spec->n1, spec->n2, spec->mix, 0), *b0 = pinn_find_kernel(wp, 0, 0, 0, 0);
     if (want == "mma") { h->kcol = c1; h->kbc = b1; }
     else if (want == "simt") { h->kcol = c0; h->kbc = b0; }
-    else if (c1 && b1 && wp <= 128) { h->kcol = c1; h->kbc = b1; }  // W=256: fp32 kernel (accumulation depth)
+    else if (c1 && b1) { h->kcol = c1; h->kbc = b1; }
     else { h->kcol = c0; h->kbc = b0; }
     if (!h->kcol || !h->kbc) {
       delete h;

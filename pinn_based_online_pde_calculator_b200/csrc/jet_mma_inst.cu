@@ -29,6 +29,7 @@ static cudaError_t prepare_impl(int* ctas_per_sm) {
   if (e != cudaSuccess) return e;
   int n = 1;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, jet_mma_kernel<Cfg, true>, Cfg::NT, Cfg::smem_bytes(true));
+  if (Cfg::USE_TMEM && n > 2) n = 2;  // two CTAs x 256 TMEM columns per SM
   if (ctas_per_sm) *ctas_per_sm = n < 1 ? 1 : n;
   return e;
 }

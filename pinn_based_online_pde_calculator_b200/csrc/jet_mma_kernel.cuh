@@ -14,6 +14,10 @@
 #pragma once
 #include "jet_kernel.cuh"
 
+#ifndef PINN_TMEM_COLS
+#define PINN_TMEM_COLS 256   // TMEM columns per CTA of the (optional) Tensor-Memory stash
+#endif
+
 template <int WP_, int N1_, int N2_, int MIX_, int NT_>
 struct MmaCfg {
   static constexpr int WP = WP_, N1 = N1_, N2 = N2_, MIX = MIX_;
@@ -41,9 +45,20 @@ struct MmaCfg {
   static constexpr size_t smem_bytes(bool train) {
     return (size_t)(HS_FLOATS * (train ? 2 : 1) + 2 * KC * WPS + WP + PINN_MAX_OPS + PINN_MAX_CONSTS) * 4 + 64;
   }
+  // TMEM stash: 4-warp CTAs only (one warp per 32-lane quadrant); 16*K columns per layer, 256 per CTA
+  // Measured on B200 (round 1): merely executing tcgen05.alloc in this kernel -- even 32 columns that
+  // are never touched -- slows the mma.sync (HMMA) GEMM phases by 1.4x (C2: 7.06 -> 10.0 ms/step), so
+  // legacy warp-level MMA and explicit Tensor-Memory allocations do not mix; the TMEM stash is therefore
+  // compiled out by default (-DPINN_TMEM_STASH=1 re-enables it for experiments).
+#ifndef PINN_TMEM_STASH
+#define PINN_TMEM_STASH 0
+#endif
+  static constexpr bool USE_TMEM = (PINN_TMEM_STASH != 0) && (NT == 128);
+  static constexpr int TMEM_LAYERS = PINN_TMEM_COLS / (16 * K);
   static constexpr int MINB_S = (int)(232448 / (smem_bytes(true) + 1024));            // smem-limited CTAs per SM
   static constexpr int MINB_R = 65536 / (NT * 256);                                     // at 255 registers per thread
-  static constexpr int MINB = MINB_S < 1 ? 1 : (MINB_S < MINB_R ? MINB_S : MINB_R);   // resident CTAs per SM
+  static constexpr int MINB_U = MINB_S < 1 ? 1 : (MINB_S < MINB_R ? MINB_S : MINB_R);
+  static constexpr int MINB = (USE_TMEM && MINB_U > 2) ? 2 : MINB_U;   // resident CTAs per SM (2 x 256 TMEM columns)
 };
 
 // ---------------------------------------------------------------- tensor-core helpers
@@ -71,12 +86,44 @@ __device__ __forceinline__ void mma3(float& d0, float& d1, float& d2, float& d3,
   mma_tf32(d0, d1, d2, d3, ah, bh0, bh1);
 }
 
+// ---------------------------------------------------------------- TMEM scratchpad (tcgen05.st / tcgen05.ld)
+// The backward stash of the first layers lives in Tensor Memory instead of the L2-resident global
+// scratch: 256 columns per CTA (two CTAs per SM share the 512), lane = the thread's lane inside
+// its warp's 32-lane quadrant, column = (layer, channel, point, unit slot).  SASS: STTM / LDTM.
+__device__ __forceinline__ void tmem_alloc256(uint32_t* smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"((uint32_t)PINN_TMEM_COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc256(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"((uint32_t)PINN_TMEM_COLS) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // thread geometry of the fragment layout
 struct MmaGeo {
   int lane, g, t, mw, nw, row;  // row = 8*mw + g (thread row over points)
   int pt0;                      // first owned point (second = pt0 + 8)
   int n0;                       // first unit of the warp (32*nw)
   int swz;                      // column swizzle of the owned points
+  uint32_t tmem;                // TMEM address of this warp's lane quadrant, column 0 (0 = TMEM stash off)
 };
 
 // unit index of register slot j8 (0..7): n-tile j8/2, column 2t + j8%2
@@ -188,7 +235,7 @@ __device__ __forceinline__ float4* mma_stash_ptr(float* stash_l, int c, int p, i
 template <class C, bool TRAIN>
 __device__ __forceinline__ void mma_act_forward(float (&acc)[C::K][2][8], const float* __restrict__ bias, int act,
                                                 float* __restrict__ stash_l, const MmaGeo& G, int tid,
-                                                const float (&beta)[2][3]) {
+                                                const float (&beta)[2][3], int tm_col) {
   float b[8];
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
@@ -205,10 +252,15 @@ __device__ __forceinline__ void mma_act_forward(float (&acc)[C::K][2][8], const 
       acc[0][p][j] = s0;
     }
     if (TRAIN) {
+      if (tm_col >= 0) {  // layer stash in Tensor Memory
 #pragma unroll
-      for (int c = 0; c < C::K; ++c) {
-        *mma_stash_ptr<C>(stash_l, c, p, 0, tid) = make_float4(acc[c][p][0], acc[c][p][1], acc[c][p][2], acc[c][p][3]);
-        *mma_stash_ptr<C>(stash_l, c, p, 1, tid) = make_float4(acc[c][p][4], acc[c][p][5], acc[c][p][6], acc[c][p][7]);
+        for (int c = 0; c < C::K; ++c) tmem_st8(G.tmem + tm_col + (c * 2 + p) * 8, acc[c][p]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < C::K; ++c) {
+          *mma_stash_ptr<C>(stash_l, c, p, 0, tid) = make_float4(acc[c][p][0], acc[c][p][1], acc[c][p][2], acc[c][p][3]);
+          *mma_stash_ptr<C>(stash_l, c, p, 1, tid) = make_float4(acc[c][p][4], acc[c][p][5], acc[c][p][6], acc[c][p][7]);
+        }
       }
     }
 #pragma unroll
@@ -231,10 +283,18 @@ __device__ __forceinline__ void mma_act_forward(float (&acc)[C::K][2][8], const 
       acc[0][p][j] = y[j];
     }
   }
+  if (TRAIN && tm_col >= 0) tmem_wait_st();
 }
 
 template <class C>
-__device__ __forceinline__ void mma_load_stash(float (&st)[C::K][8], const float* __restrict__ stash_l, int p, int tid) {
+__device__ __forceinline__ void mma_load_stash(float (&st)[C::K][8], const float* __restrict__ stash_l, int p, int tid,
+                                               uint32_t tmem, int tm_col) {
+  if (tm_col >= 0) {
+#pragma unroll
+    for (int c = 0; c < C::K; ++c) tmem_ld8(tmem + tm_col + (c * 2 + p) * 8, st[c]);
+    tmem_wait_ld();
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < C::K; ++c) {
     const float4 v0 = *mma_stash_ptr<C>(const_cast<float*>(stash_l), c, p, 0, tid);
@@ -247,11 +307,11 @@ __device__ __forceinline__ void mma_load_stash(float (&st)[C::K][8], const float
 // adjoint of the activation jets (same math as act_backward)
 template <class C>
 __device__ __forceinline__ void mma_act_backward(float (&acc)[C::K][2][8], int act, const float* __restrict__ stash_l,
-                                                 int tid, const float (&beta)[2][3]) {
+                                                 int tid, const float (&beta)[2][3], uint32_t tmem, int tm_col) {
 #pragma unroll
   for (int p = 0; p < 2; ++p) {
     float st[C::K][8];
-    mma_load_stash<C>(st, stash_l, p, tid);
+    mma_load_stash<C>(st, stash_l, p, tid, tmem, tm_col);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float y, d1, d2, d3;
@@ -302,11 +362,11 @@ __device__ __forceinline__ void mma_act_backward(float (&acc)[C::K][2][8], int a
 // recompute a layer's output jets from its stash into the smem tile S
 template <class C>
 __device__ __forceinline__ void mma_recompute_outputs(float* __restrict__ S, int act, const float* __restrict__ stash_l,
-                                                      const MmaGeo& G, int tid, const float (&beta)[2][3]) {
+                                                      const MmaGeo& G, int tid, const float (&beta)[2][3], int tm_col) {
 #pragma unroll
   for (int p = 0; p < 2; ++p) {
     float st[C::K][8];
-    mma_load_stash<C>(st, stash_l, p, tid);
+    mma_load_stash<C>(st, stash_l, p, tid, G.tmem, tm_col);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float y, d1, d2, d3;
@@ -455,6 +515,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
   G.pt0 = 16 * G.mw + G.g;
   G.n0 = 32 * G.nw;
   G.swz = ((G.g >> 2) & 1) << 2;
+  G.tmem = 0;
   const int Lh = net.n_hidden;
   const int nF = (Lh - 1) * NCH;
   const int S = TRAIN ? 2 * nF : nF;
@@ -485,7 +546,17 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
     mbar_init(&mbar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  constexpr bool TM = TRAIN && C::USE_TMEM;
+  __shared__ uint32_t s_tmem_base;
+  if (TM && warp == 0) tmem_alloc256(&s_tmem_base);
+  if (TM) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (TM) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    G.tmem = s_tmem_base + ((uint32_t)(warp & 3) << 21);  // lane field = 32 * (warp % 4), bits [31:16]
+  }
+  // stash column of layer l in TMEM, or -1 when the layer's stash stays in the global scratch
+  auto tm_col = [&](int l) -> int { return (TM && l < C::TMEM_LAYERS) ? l * (16 * K) : -1; };
   if (tid == 0 && total > 0) issue(0);
 
   constexpr size_t STL = (size_t)C::TP * K * WP;  // stash floats per layer (= K*16*NT)
@@ -602,7 +673,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
       }
       lap(0);
       mma_act_forward<C, TRAIN>(acc, L.wpack + net.off_b[l], l == 0 ? net.act_first : net.act_hidden,
-                                stash + l * STL, G, tid, beta);
+                                stash + l * STL, G, tid, beta, tm_col(l));
       lap(1);
     }
 
@@ -696,12 +767,12 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
       }
 #pragma unroll 1
       for (int l = Lh - 1; l >= 0; --l) {
-        mma_act_backward<C>(acc, l == 0 ? net.act_first : net.act_hidden, stash + l * STL, tid, beta);
+        mma_act_backward<C>(acc, l == 0 ? net.act_first : net.act_hidden, stash + l * STL, tid, beta, G.tmem, tm_col(l));
         lap(3);
         if (l == 0) break;
         __syncthreads();
         mma_store_tile<C>(Gs, acc, G);
-        mma_recompute_outputs<C>(Hs, (l - 1 == 0) ? net.act_first : net.act_hidden, stash + (l - 1) * STL, G, tid, beta);
+        mma_recompute_outputs<C>(Hs, (l - 1 == 0) ? net.act_first : net.act_hidden, stash + (l - 1) * STL, G, tid, beta, tm_col(l - 1));
         __syncthreads();
         lap(4);
         mma_wgrad_layer<C>(Hs, Gs, bsc, gacc + net.off_w[l], gacc + net.off_b[l], tid, G);
@@ -772,5 +843,10 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
       for (int r = 0; r < C::ROWS; ++r) s += sc2[r];
       gacc[net.off_bl] += s;
     }
+  }
+  if (TM) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc256(s_tmem_base);
   }
 }

@@ -220,3 +220,40 @@ def test_errors_are_python_exceptions():
     with pytest.raises(RuntimeError):
         PinnEngine(NetworkSpec(2, 300, [0, 0], [1, 1], feature_map="affine"), compile_equation("u_xx", 2), n_bc=0)
     eng.close()
+
+
+@pytest.mark.parametrize("kernel", ["simt", "auto"])
+def test_stage2_frozen_base_matches_oracle(kernel, monkeypatch):
+    """mNN_pred_create (software.py:221-234): u = u1_frozen(z) + epsil2 * NN2(z), sin first layer.
+    The engine receives the frozen stage-1 jets as `base` columns; loss and gradient w.r.t. the
+    stage-2 parameters must match the oracle's nested-autograd evaluation of the combined network."""
+    monkeypatch.setenv("PINN_B200_KERNEL", kernel)
+    from pinn_based_online_pde_calculator_b200.equation import REFERENCE_POLAR_LAPLACE
+
+    lb, ub = [0.1, 0.0], [1.0, 1.0]
+    pb1 = make_problem(n_hidden=3, width=40, d_in=2, expr=REFERENCE_POLAR_LAPLACE, n_col=400, n_bd=50, n_bc=2, lb=lb, ub=ub,
+                       feature_map="polar", lw=0.05, coord_names=("r", "t"), seed=1)
+    pb2 = make_problem(n_hidden=6, width=50, d_in=2, expr=REFERENCE_POLAR_LAPLACE, n_col=400, n_bd=50, n_bc=2, lb=lb, ub=ub,
+                       feature_map="polar", act_first=1, scl=3.0, epsil=0.02, lw=0.7, coord_names=("r", "t"), seed=1)
+    limit = pb1["limit"]
+    f_u1 = O.sol_pred_create(limit, 1.0, 1.0, act_s=0)
+    f_u1_frozen = lambda z: f_u1(pb1["params"], z)
+    pred_u2 = O.mNN_pred_create(f_u1_frozen, limit, 3.0, 0.02, act_s=1)
+    lossf = O.loss_create(pred_u2, torch.tensor([0.7, 0.0], dtype=torch.float64), 1.3)
+    data = dict(x_col=pb2["x_col"], cond_bd=[pb2["x_bd"], pb2["u_bd"]])
+    g_ref, info_ref = O.loss_and_grad(lossf, pb2["params"], data)
+    g_ref = O.ravel_params(g_ref).numpy()
+    # engine: stage-1 engine evaluates the frozen jets, stage-2 engine consumes them as base columns
+    eng1 = engine_for(pb1)
+    x_col = pb2["x_col"].numpy().astype(np.float32)
+    base_col = eng1.eval(x_col, want_u=False, want_f=False, want_jets=True)[2]
+    base_bd = [eng1.eval(a.numpy().astype(np.float32), want_f=False)[0] for a in pb2["x_bd"]]
+    eng2 = PinnEngine(pb2["net"], pb2["eq"], n_bc=2)
+    eng2.set_params(O.ravel_params(pb2["params"]).numpy().astype(np.float32))
+    eng2.set_points(x_col, [a.numpy() for a in pb2["x_bd"]], [a.numpy() for a in pb2["u_bd"]], base_col=base_col, base_bd=base_bd)
+    eng2.set_loss(0.7, 1.3)
+    g, info = eng2.loss_grad()
+    assert np.allclose(info, info_ref.numpy(), rtol=TOL)
+    assert rel_err(g.cpu().numpy(), g_ref) < TOL
+    eng1.close()
+    eng2.close()

@@ -2,7 +2,7 @@
 oracle (oracle/reference_oracle.py): weights, points, loss_info, flat gradient of
 loss/lref, and per-point u / residual.  The GPU tests compare the CUDA engine with
 these files, so nothing under oracle/ or /root/reference is needed on the GPU box.
-Re-run:  python tools/gen_golden.py
+Re-run:  python tests/golden/gen_golden.py
 """
 import os
 import sys
@@ -10,7 +10,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import reference_oracle as O  # noqa: E402
 from tests.helpers import make_problem, oracle_loss_grad  # noqa: E402

@@ -16,7 +16,7 @@ import string
 import sys
 
 REF = "/root/reference/pinn_app/callbacks/input_validation.py"
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "validator_golden.json")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "validator_golden.json")
 
 src = open(REF).read()
 tree = ast.parse(src)

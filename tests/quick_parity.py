@@ -1,5 +1,5 @@
 import sys, traceback
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 import numpy as np
 from tests.helpers import *
 from tests.test_gpu_parity import CASES

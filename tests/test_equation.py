@@ -1,5 +1,5 @@
 """Equation front end: validator parity with the reference (golden verdicts produced by
-the reference's own on_equation_change, tools/gen_validator_golden.py), parser, compiler."""
+the reference's own on_equation_change, tests/golden/gen_validator_golden.py), parser, compiler."""
 import json
 import math
 import os

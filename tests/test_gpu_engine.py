@@ -21,7 +21,7 @@ TOL = 1e-5
 @pytest.mark.parametrize("kernel", ["simt", "auto"])
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "case_*.npz"))))
 def test_engine_matches_golden_fixture(path, kernel, monkeypatch):
-    from tools.gen_golden import CASES
+    from tests.golden.gen_golden import CASES
 
     monkeypatch.setenv("PINN_B200_KERNEL", kernel)
     name = os.path.basename(path)[len("case_"):-len(".npz")]

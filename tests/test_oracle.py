@@ -137,11 +137,11 @@ def test_lhs_is_stratified_and_colloc_respects_distribution():
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "case_*.npz"))))
 def test_oracle_reproduces_committed_golden_vectors(path):
-    from tools.gen_golden import CASES, LREF
+    from tests.golden.gen_golden import CASES, LREF
 
     name = os.path.basename(path)[len("case_"):-len(".npz")]
     if CASES[name]["width"] > 64:
-        pytest.skip("wide golden cases are re-derived only by tools/gen_golden.py (CPU suite time)")
+        pytest.skip("wide golden cases are re-derived only by tests/golden/gen_golden.py (CPU suite time)")
     z = np.load(path)
     pb = make_problem(**CASES[name])
     g, info, _, _ = oracle_loss_grad(pb, lref=LREF)

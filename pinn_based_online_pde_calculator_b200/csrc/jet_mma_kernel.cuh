@@ -62,15 +62,13 @@ struct MmaCfg {
 };
 
 // ---------------------------------------------------------------- tensor-core helpers
-// Veltkamp split with round-to-nearest: hi keeps 11 significant bits (exactly a TF32 value),
-// lo = x - hi is exact.  Rounding (not truncating) keeps the split unbiased, so the residual
-// errors of the 3xTF32 product accumulate like a random walk instead of coherently.
-// __fmul_rn/__fadd_rn are never contracted into FMAs (which would break the split).
+// Round-to-nearest split: hi = x rounded to the 11 significant bits of TF32 (add half an ulp to the
+// bit pattern, clear the 13 low mantissa bits: two integer-pipe ops), lo = x - hi (exact, one fp32
+// add).  Rounding (not truncating) keeps the split unbiased, so the residual errors of the 3xTF32
+// product accumulate like a random walk instead of coherently.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  const float t = __fmul_rn(x, 8193.0f);
-  const float h = __fadd_rn(t, -__fadd_rn(t, -x));
-  hi = __float_as_uint(h);
-  lo = __float_as_uint(__fadd_rn(x, -h));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(__fadd_rn(x, -__uint_as_float(hi)));
 }
 __device__ __forceinline__ void mma_tf32(float& d0, float& d1, float& d2, float& d3, const uint32_t (&a)[4],
                                          uint32_t b0, uint32_t b1) {
@@ -430,43 +428,49 @@ __device__ __forceinline__ void mma_wgrad_layer(const float* __restrict__ Hs, co
     for (int ps = 0; ps < C::TP / 8; ++ps) {
       const int pa = 8 * ps + G.t, pb = pa + 4;  // swizzle 0 for pa, 4 for pb
 #pragma unroll
-      for (int c = 0; c < C::K; ++c) {
-        const float* ha = Hs + pa * C::SP + c * C::WP;
-        const float* hb = Hs + pb * C::SP + c * C::WP;
-        uint32_t ah[2][4], al[2][4];
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          const int kr = k0 + 16 * m + G.g;
-          split_tf32(ha[kr], ah[m][0], al[m][0]);
-          split_tf32(ha[kr + 8], ah[m][1], al[m][1]);
-          split_tf32(hb[kr ^ 4], ah[m][2], al[m][2]);
-          split_tf32(hb[(kr + 8) ^ 4], ah[m][3], al[m][3]);
-        }
-        const float* ga = Gs + pa * C::SP + c * C::WP + u0 + G.g;
-        const float* gb = Gs + pb * C::SP + c * C::WP + ((u0 + G.g) ^ 4);
-        uint32_t bh[4][2], bl[4][2];
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          split_tf32(ga[8 * nt], bh[nt][0], bl[nt][0]);
-          split_tf32(gb[8 * nt], bh[nt][1], bl[nt][1]);
-        }
-        float tq[2][4][4];  // two-level accumulation (see mma_gemm_chunk)
+      for (int c0 = 0; c0 < C::K; c0 += 2) {
+        float tq[2][4][4];  // two-level accumulation (see mma_gemm_chunk): flushed every two reduction steps
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) tq[m][nt][0] = tq[m][nt][1] = tq[m][nt][2] = tq[m][nt][3] = 0.f;
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+        for (int cc = 0; cc < 2; ++cc) {
+          if (c0 + cc < C::K) {
+            const int c = c0 + cc;
+            const float* ha = Hs + pa * C::SP + c * C::WP;
+            const float* hb = Hs + pb * C::SP + c * C::WP;
+            uint32_t ah[2][4], al[2][4];
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) mma_tf32(tq[m][nt][0], tq[m][nt][1], tq[m][nt][2], tq[m][nt][3], al[m], bh[nt][0], bh[nt][1]);
+            for (int m = 0; m < 2; ++m) {
+              const int kr = k0 + 16 * m + G.g;
+              split_tf32(ha[kr], ah[m][0], al[m][0]);
+              split_tf32(ha[kr + 8], ah[m][1], al[m][1]);
+              split_tf32(hb[kr ^ 4], ah[m][2], al[m][2]);
+              split_tf32(hb[(kr + 8) ^ 4], ah[m][3], al[m][3]);
+            }
+            const float* ga = Gs + pa * C::SP + c * C::WP + u0 + G.g;
+            const float* gb = Gs + pb * C::SP + c * C::WP + ((u0 + G.g) ^ 4);
+            uint32_t bh[4][2], bl[4][2];
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+            for (int nt = 0; nt < 4; ++nt) {
+              split_tf32(ga[8 * nt], bh[nt][0], bl[nt][0]);
+              split_tf32(gb[8 * nt], bh[nt][1], bl[nt][1]);
+            }
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) mma_tf32(tq[m][nt][0], tq[m][nt][1], tq[m][nt][2], tq[m][nt][3], ah[m], bl[nt][0], bl[nt][1]);
+            for (int m = 0; m < 2; ++m)
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+              for (int nt = 0; nt < 4; ++nt) mma_tf32(tq[m][nt][0], tq[m][nt][1], tq[m][nt][2], tq[m][nt][3], al[m], bh[nt][0], bh[nt][1]);
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) mma_tf32(tq[m][nt][0], tq[m][nt][1], tq[m][nt][2], tq[m][nt][3], ah[m], bh[nt][0], bh[nt][1]);
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt) mma_tf32(tq[m][nt][0], tq[m][nt][1], tq[m][nt][2], tq[m][nt][3], ah[m], bl[nt][0], bl[nt][1]);
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt) mma_tf32(tq[m][nt][0], tq[m][nt][1], tq[m][nt][2], tq[m][nt][3], ah[m], bh[nt][0], bh[nt][1]);
+          }
+        }
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll

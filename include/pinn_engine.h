@@ -71,6 +71,9 @@ int pinn_device_count(void);
 int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engine_t** out);
 void pinn_engine_destroy(pinn_engine_t* h);
 int pinn_engine_set_stream(pinn_engine_t* h, void* cuda_stream);
+/* wait for everything enqueued on the engine stream (needed by callers that consume device outputs on
+ * another stream; no entry point synchronises implicitly unless it returns host data) */
+int pinn_engine_sync(pinn_engine_t* h);
 
 /* P = number of parameters in jax.flatten_util.ravel_pytree order (sw:466,502) */
 int64_t pinn_engine_num_params(pinn_engine_t* h);

@@ -366,6 +366,12 @@ extern "C" int pinn_engine_set_stream(pinn_engine_t* h, void* s) {
   return 0;
 }
 
+extern "C" int pinn_engine_sync(pinn_engine_t* h) {
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 extern "C" int64_t pinn_engine_num_params(pinn_engine_t* h) { return h->fmap.n_params; }
 extern "C" int32_t pinn_engine_num_loss_info(pinn_engine_t* h) { return h->n_info; }
 extern "C" int32_t pinn_engine_tile_points(pinn_engine_t* h) { return h->kcol->tile_points; }

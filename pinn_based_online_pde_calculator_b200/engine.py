@@ -32,7 +32,7 @@ EXPORTS = [
     "pinn_engine_get_params", "pinn_engine_set_points", "pinn_engine_set_global_counts",
     "pinn_engine_set_loss", "pinn_engine_loss_grad", "pinn_engine_adam_init", "pinn_engine_adam_steps",
     "pinn_engine_eval", "pinn_engine_lbfgs", "pinn_nccl_unique_id", "pinn_engine_init_nccl",
-    "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels", "pinn_engine_kernel_kind", "pinn_engine_phase_profile", "pinn_sample_lhs", "pinn_sample_cdf2d",
+    "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels", "pinn_engine_kernel_kind", "pinn_engine_phase_profile", "pinn_sample_lhs", "pinn_sample_cdf2d", "pinn_engine_sync",
 ]
 
 
@@ -73,6 +73,7 @@ def load_library(path: Optional[str] = None):
     lib.pinn_engine_destroy.argtypes = [C.c_void_p]
     lib.pinn_engine_destroy.restype = None
     lib.pinn_engine_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pinn_engine_sync.argtypes = [C.c_void_p]
     lib.pinn_engine_num_params.argtypes = [C.c_void_p]
     lib.pinn_engine_num_params.restype = C.c_int64
     lib.pinn_engine_num_loss_info.argtypes = [C.c_void_p]
@@ -225,10 +226,24 @@ class PinnEngine:
 
     def set_stream(self, cuda_stream_ptr: int):
         _check(self.lib, self.lib.pinn_engine_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+        self._shared_stream = True
+
+    def sync(self):
+        _check(self.lib, self.lib.pinn_engine_sync(self.h))
+
+    def _torch_inputs_ready(self):
+        """Device tensors handed to the engine were produced on torch's current stream; unless the engine
+        shares that stream (set_stream), wait for it so the engine's own stream sees complete data."""
+        if not getattr(self, "_shared_stream", False):
+            import torch
+
+            torch.cuda.current_stream(self.device).synchronize()
 
     # ---- parameters (ravel_pytree order, software.py:466)
     def set_params(self, flat):
         a = _as_f32(flat)
+        if _is_device(a):
+            self._torch_inputs_ready()
         n = a.size if isinstance(a, np.ndarray) else a.numel()
         if n != self.n_params:
             raise ValueError(f"expected {self.n_params} parameters, got {n}")
@@ -254,6 +269,8 @@ class PinnEngine:
                     raise ValueError("mixing host and device buffers in set_points")
         n_col = x_col.shape[0]
         n = len(xb)
+        if dev:
+            self._torch_inputs_ready()
         PX = (C.c_void_p * max(1, n))(*[_ptr(a) for a in xb])
         PU = (C.c_void_p * max(1, n))(*[_ptr(a) for a in ub])
         PB = (C.c_void_p * max(1, n))(*[_ptr(a) for a in bb])
@@ -283,6 +300,7 @@ class PinnEngine:
         p = None
         if params is not None:
             p = params if _is_device(params) else torch.as_tensor(np.asarray(params, dtype=np.float32)).to(f"cuda:{self.device}")
+            self._torch_inputs_ready()
         _check(self.lib, self.lib.pinn_engine_loss_grad(self.h, _ptr(p), _ptr(g), _ptr(info)))
         return g, info
 
@@ -330,8 +348,12 @@ class PinnEngine:
         u = mk(n) if want_u else None
         f = mk(n) if want_f else None
         j = mk(n, self.K) if want_jets else None
+        if dev:
+            self._torch_inputs_ready()
         _check(self.lib, self.lib.pinn_engine_eval(self.h, _ptr(z), n, _ptr(_as_f32(aux)), _ptr(_as_f32(base)),
                                                    _ptr(u), _ptr(f), _ptr(j), int(dev)))
+        if dev and not getattr(self, "_shared_stream", False):
+            self.sync()  # outputs are consumed on torch's stream
         return u, f, j
 
     # ---- lbfgs_optimizer (software.py:499-514)

@@ -149,6 +149,12 @@ int pinn_sample_cdf2d(int device, void* stream, uint32_t seed, int64_t n, const 
 /* fp32 FMA-pipe microbenchmark (roofline denominator of the SIMT path):
  * returns achieved TFLOP/s; variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2 */
 int pinn_fma_peak(int device, int variant, double* tflops_out);
+/* tcgen05 probe (measurement helper): D = A * B^T on one CTA, tf32 inputs / fp32 TMEM accumulator.  A, B0, B1
+ * are RAW shared-memory images (the host lays the operands out), cfg = {M, N, k-steps, A MN-major, B MN-major,
+ * products (2 = second one with B1 into lanes +16, M = 64), repetitions, words of A, words of B,
+ * A: LBO, SBO, k-step advance in bytes, B: the same}; dumps TMEM as out[128 lanes][512 columns]. */
+int pinn_umma_probe(int device, const float* A, const float* B0, const float* B1, const int* cfg, float* out,
+                    double* cycles, int* status);
 
 /* roofline helper: average device time (ms) of the collocation kernel and of the
  * boundary kernel launched alone, CUDA events on the engine stream, an L2 flush of

@@ -9,16 +9,20 @@ namespace umma {
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// ---- shared-memory matrix descriptor, no swizzle, 4-byte elements (tf32)
-// K-major operand  (rows r = M or N index, k = reduction index), core matrix = 8 rows x 16 B:
-//   byte(r, k) = (k / 4) * LBO + (r / 8) * SBO + (r % 8) * 16 + (k % 4) * 4
-// MN-major operand (mn = M or N index, k = reduction index), core matrix = 8 k x 16 B:
-//   byte(mn, k) = (mn / 4) * SBO + (k / 8) * LBO + (k % 8) * 16 + (mn % 4) * 4
-// A tile written K-major with SBO = 128 and LBO = P is therefore ALSO a valid MN-major operand of the
-// transposed product with SBO' = P and LBO' = 128 (used by the weight-gradient GEMM).
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// ---- shared-memory matrix descriptor, 4-byte elements (tf32).  Layouts MEASURED on B200 with
+// tools/umma_probe.py (profiles/r01_umma_probe.txt):
+// K-major operand, no swizzle (rows r = M or N index, k = reduction index; core matrix = 8 rows x 16 B):
+//   byte(r, k) = (k / 4) * LBO + (r / 8) * SBO + (r % 8) * 16 + (k % 4) * 4          k-step advance 2 * LBO
+// K-major operand, 128B swizzle (layout type 2; 32 k per 128 B row, LBO unused):
+//   byte(r, k) = (r / 8) * SBO + (r % 8) * 128 + (((k / 4) ^ (r % 8)) * 16) + (k % 4) * 4
+// MN-major operand: un-swizzled and layout types 2/4/6 return ZERO products for tf32; layout type 1
+// (128B swizzle with 32B atomicity) works (mn = M or N index, 32 mn per 128 B row, 4 k rows per atom):
+//   byte(mn, k) = (mn / 32) * LBO + (k / 4) * SBO + (k % 4) * 128 + ((((mn % 32) / 4) ^ (2 * (k % 4))) * 16) + (mn % 4) * 4
+// A operand from TMEM (TS form): row = lane, the 8 k of one MMA = 8 consecutive 32-bit columns.
+// layout_type: 0 none, 1 128B (32B atomicity), 2 128B, 4 64B, 6 32B swizzle
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 0) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);  // version 1 (sm_100), layout type 0 = no swizzle
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) /* version 1 (sm_100) */ | ((uint64_t)(layout_type & 7u) << 61);
 }
 
 // ---- instruction descriptor, kind::tf32, fp32 accumulate
@@ -33,6 +37,15 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// D[tmem] (+)= A[tmem: M lanes x 8 columns] * B[smem]
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -95,6 +108,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+               "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 }  // namespace umma

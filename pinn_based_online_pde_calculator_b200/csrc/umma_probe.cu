@@ -15,7 +15,7 @@ struct ProbeArgs {
   const float* B0;  // raw image of operand B
   const float* B1;  // second B image (second product, lanes +16; M = 64 only)
   int a_words, b_words;
-  int M, N, ksteps, a_mn, b_mn, nsets, reps, nd;
+  int M, N, ksteps, a_mn, b_mn, nsets, reps, nd, a_lt, b_lt, a_tmem;
   uint32_t a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step;
   float* out;  // [128][512]
   long long* cycles;
@@ -45,21 +45,38 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(ProbeArgs p) {
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tb = tbase;
+  if (p.a_tmem) {
+    // A given row-major [128][8*ksteps]: lane = row, columns 256.. of TMEM
+    for (int col = 0; col < 8 * p.ksteps; col += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = p.A[(size_t)tid * 8 * p.ksteps + col + i];
+      umma::tmem_st8(tb + ((uint32_t)(warp * 32) << 16) + 256 + col, v);
+    }
+    umma::tmem_st_wait();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+  }
   if (tid == 0) {
     const uint32_t idesc = umma::idesc_tf32(p.M, p.N, p.a_mn, p.b_mn);
     // descriptors precomputed; the issue loop only bumps the 14-bit start-address field
-    const uint64_t a0 = umma::smem_desc(umma::smem_addr(As), p.a_lbo, p.a_sbo);
-    const uint64_t b0[2] = {umma::smem_desc(umma::smem_addr(Bs0), p.b_lbo, p.b_sbo), umma::smem_desc(umma::smem_addr(Bs1), p.b_lbo, p.b_sbo)};
+    const uint64_t a0 = umma::smem_desc(umma::smem_addr(As), p.a_lbo, p.a_sbo, p.a_lt);
+    const uint64_t b0[2] = {umma::smem_desc(umma::smem_addr(Bs0), p.b_lbo, p.b_sbo, p.b_lt),
+                            umma::smem_desc(umma::smem_addr(Bs1), p.b_lbo, p.b_sbo, p.b_lt)};
     const uint32_t da = p.a_step >> 4, db = p.b_step >> 4;
     const int nd = p.nd < 1 ? 1 : p.nd;  // round-robin over nd accumulator regions (timing only)
     const long long t0 = clock64();
     for (int rep = 0; rep < p.reps; ++rep)
       for (int s = 0; s < p.nsets; ++s) {
         const uint32_t d = tb + ((uint32_t)(16 * s) << 16) + (uint32_t)((rep % nd) * p.N);
-        if (p.ksteps == 8) {
+        if (p.ksteps == 8 && !p.a_tmem) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             umma::mma_tf32_ss(d, a0 + (uint64_t)(j * da), b0[s] + (uint64_t)(j * db), idesc, (rep >= nd || j) ? 1u : 0u);
+        } else if (p.a_tmem) {
+          for (int j = 0; j < p.ksteps; ++j)
+            umma::mma_tf32_ts(d, tb + 256 + 8 * j, b0[s] + (uint64_t)(j * db), idesc, (rep >= nd || j) ? 1u : 0u);
         } else {
           for (int j = 0; j < p.ksteps; ++j)
             umma::mma_tf32_ss(d, a0 + (uint64_t)(j * da), b0[s] + (uint64_t)(j * db), idesc, (rep >= nd || j) ? 1u : 0u);
@@ -98,7 +115,8 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(ProbeArgs p) {
 }  // namespace
 
 // cfg: [0] M, [1] N, [2] ksteps, [3] a_mn_major, [4] b_mn_major, [5] nsets, [6] reps, [7] a_words, [8] b_words,
-//      [9..11] A: lbo, sbo, k-step advance (bytes), [12..14] B: lbo, sbo, k-step advance, [15] accumulator regions (timing)
+//      [9..11] A: lbo, sbo, k-step advance (bytes), [12..14] B: lbo, sbo, k-step advance, [15] accumulator regions (timing),
+//      [16], [17] swizzle layout type of A, B, [18] A operand from TMEM (A = row-major [128][8*ksteps])
 extern "C" int pinn_umma_probe(int device, const float* A, const float* B0, const float* B1, const int* cfg, float* out,
                                double* cycles, int* status) {
   CKP(cudaSetDevice(device));
@@ -124,7 +142,7 @@ extern "C" int pinn_umma_probe(int device, const float* A, const float* B0, cons
   p.A = dA; p.B0 = dB0; p.B1 = B1 ? dB1 : dB0;
   p.a_words = aw; p.b_words = bw;
   p.M = M; p.N = N; p.ksteps = cfg[2]; p.a_mn = cfg[3]; p.b_mn = cfg[4]; p.nsets = nsets; p.reps = cfg[6] < 1 ? 1 : cfg[6];
-  p.nd = cfg[15]; p.a_lbo = cfg[9]; p.a_sbo = cfg[10]; p.a_step = cfg[11]; p.b_lbo = cfg[12]; p.b_sbo = cfg[13]; p.b_step = cfg[14];
+  p.nd = cfg[15]; p.a_lt = cfg[16]; p.b_lt = cfg[17]; p.a_tmem = cfg[18]; p.a_lbo = cfg[9]; p.a_sbo = cfg[10]; p.a_step = cfg[11]; p.b_lbo = cfg[12]; p.b_sbo = cfg[13]; p.b_step = cfg[14];
   p.out = dout; p.cycles = dcyc; p.status = dst;
   CKP(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_probe_kernel<<<1, 128, smem>>>(p);

@@ -19,12 +19,12 @@ def _lib():
     return lib
 
 
-def raw(lib, A_img, B_img, B1_img, M, N, ksteps, a_mn, b_mn, a_desc, b_desc, nsets=1, reps=1, nd=1):
+def raw(lib, A_img, B_img, B1_img, M, N, ksteps, a_mn, b_mn, a_desc, b_desc, nsets=1, reps=1, nd=1, a_lt=0, b_lt=0, a_tmem=0):
     """a_desc/b_desc = (lbo, sbo, step) in bytes"""
     A_img = np.ascontiguousarray(A_img, np.float32)
     B_img = np.ascontiguousarray(B_img, np.float32)
     B1c = np.ascontiguousarray(B1_img, np.float32) if B1_img is not None else None
-    cfg = np.array([M, N, ksteps, a_mn, b_mn, nsets, reps, A_img.size, B_img.size, *a_desc, *b_desc, nd], np.int32)
+    cfg = np.array([M, N, ksteps, a_mn, b_mn, nsets, reps, A_img.size, B_img.size, *a_desc, *b_desc, nd, a_lt, b_lt, a_tmem], np.int32)
     out = np.empty((128, 512), np.float32)
     cyc = C.c_double()
     st = np.zeros(2, np.int32)
@@ -205,7 +205,58 @@ def group_rate():
     print(f"two interleaved M=64 N=256 products: {(t[64] - t[16]) / n:.1f} cycles per tcgen05.mma")
 
 
-GROUPS = dict(kmajor=group_kmajor, mn_discover=group_mn_discover, mn_check=group_mn_check, rounding=group_rounding, rate=group_rate)
+def group_ts():
+    """A operand from TMEM (lane = row, 8 columns per k-step), B K-major in shared memory"""
+    lib = _lib()
+    rng = np.random.RandomState(2)
+    ints = lambda *s: rng.randint(-4, 5, size=s).astype(np.float32)
+    for (N, K) in [(64, 64), (256, 32), (8, 8)]:
+        A, B = ints(128, K), ints(N, K)
+        bi, bd = img_k_major(B)
+        rc, out, cyc, st = raw(lib, A, bi, None, 128, N, K // 8, 0, 0, (0, 0, 0), bd, a_tmem=1)
+        print(f"TS mode M=128 N={N} K={K}: rc={rc} done={st[0]} match={np.array_equal(out[:128, :N], A @ B.T)}")
+    for N in (64, 128, 256):
+        A, B = ints(128, 64), ints(N, 64)
+        bi, bd = img_k_major(B)
+        t = {}
+        for reps in (16, 64):
+            rc, out, cyc, st = raw(lib, A, bi, None, 128, N, 8, 0, 0, (0, 0, 0), bd, reps=reps, a_tmem=1)
+            t[reps] = cyc
+        print(f"TS mode M=128 N={N}: {(t[64] - t[16]) / (48 * 8):.1f} cycles per tcgen05.mma")
+
+
+def group_mn_swizzle():
+    """MN-major A with the swizzled layout types: which byte does the hardware read for A(m, k)?"""
+    lib = _lib()
+    words = 45056
+    w = np.arange(words)
+    eye, bd = img_k_major(np.eye(8, dtype=np.float32))
+    for lt in (2, 4, 6, 1):
+        for (lbo, sbo) in [(4096, 1024), (1024, 4096)]:
+            res = []
+            for part in (w % 2048, w // 2048):
+                rc, out, cyc, st = raw(lib, part.astype(np.float32), eye, None, 128, 8, 1, 1, 0, (lbo, sbo, 0), bd, a_lt=lt)
+                res.append(out[:, :8].copy())
+            W = 4 * (res[0] + 2048 * res[1]).astype(np.int64)
+            print(f"A MN-major layout_type={lt} LBO={lbo} SBO={sbo}: rc={rc} done={st[0]}")
+            print("  bytes (m=0..7, k=0):", W[:8, 0].tolist())
+            print("  bytes (m=0,4,..,60, k=0):", W[0:64:4, 0].tolist())
+            print("  bytes (m=64,96,  k=0):", W[[64, 96], 0].tolist())
+            for k in range(8):
+                print(f"  bytes (m=0,4,..,28, k={k}):", W[0:32:4, k].tolist())
+    # K-major with 128B swizzle (the layout TMA would write): row r, 32 k-elements per 128 B row
+    for lt in (2,):
+        res = []
+        for part in (w % 2048, w // 2048):
+            rc, out, cyc, st = raw(lib, part.astype(np.float32), eye, None, 128, 8, 1, 0, 0, (16, 1024, 0), bd, a_lt=lt)
+            res.append(out[:, :8].copy())
+        W = 4 * (res[0] + 2048 * res[1]).astype(np.int64)
+        print(f"A K-major layout_type={lt} LBO=16 SBO=1024:")
+        for r in (0, 1, 2, 7, 8, 9, 127):
+            print(f"  bytes (m={r}, k=0..7):", W[r, :8].tolist())
+
+
+GROUPS = dict(ts=group_ts, mn_swizzle=group_mn_swizzle, kmajor=group_kmajor, mn_discover=group_mn_discover, mn_check=group_mn_check, rounding=group_rounding, rate=group_rate)
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:

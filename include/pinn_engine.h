@@ -101,6 +101,14 @@ int pinn_engine_set_points(pinn_engine_t* h, const float* x_col, int64_t n_col, 
                            const float* base_col, int32_t n_bc, const float* const* x_bd,
                            const float* const* u_bd, const float* const* base_bd, const int64_t* n_bd,
                            int on_device);
+/* Pipelined refresh of the point set with HOST buffers of the SAME shapes as the current set (no user
+ * aux/base columns): prefetch copies them to staging memory on a separate copy stream, overlapping the
+ * step in flight; commit swaps them in on the engine stream.  Neither blocks the host.  The data-side
+ * analogue of re-sampling inside the training loop (software.py:708-716) without stalling the step. */
+int pinn_engine_prefetch_points(pinn_engine_t* h, const float* x_col, int64_t n_col, int32_t n_bc, const float* const* x_bd,
+                                const float* const* u_bd, const int64_t* n_bd);
+int pinn_engine_commit_points(pinn_engine_t* h);
+
 /* multi-GPU: the GLOBAL point counts the means are taken over (default: local counts) */
 int pinn_engine_set_global_counts(pinn_engine_t* h, int64_t n_col_global, const int64_t* n_bd_global);
 /* loss_fun.lw[0] and loss_fun.ref (sw:381-382, 739) */

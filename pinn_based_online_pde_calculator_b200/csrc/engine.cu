@@ -80,6 +80,12 @@ struct pinn_engine {
   int device = 0, num_sms = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // staged (prefetched) copy of the next point set: filled on copy_stream while the engine stream computes
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_staged = nullptr, ev_consumed = nullptr;
+  float *stg_col = nullptr, *stg_bc = nullptr, *stg_ubc = nullptr;
+  size_t stg_col_cap = 0, stg_bc_cap = 0;
+  bool staged = false;
   pinn_spec_t spec{};
   std::vector<int32_t> ops, aux_ops;
   std::vector<float> consts;
@@ -326,6 +332,12 @@ extern "C" void pinn_engine_destroy(pinn_engine_t* h) {
     if (b) cudaFree(b);
   free_set(h->col);
   free_set(h->bc);
+  if (h->stg_col) cudaFree(h->stg_col);
+  if (h->stg_bc) cudaFree(h->stg_bc);
+  if (h->stg_ubc) cudaFree(h->stg_ubc);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->ev_staged) cudaEventDestroy(h->ev_staged);
+  if (h->ev_consumed) cudaEventDestroy(h->ev_consumed);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -550,6 +562,73 @@ extern "C" int pinn_engine_set_points(pinn_engine_t* h, const float* x_col, int6
   h->n_col_global = 0;
   h->n_bd_global.clear();
   return upload_meta(h);
+}
+
+// Pipelined refresh of the point set (same shapes as the current one): prefetch copies the NEXT
+// step's host buffers into staging memory on a separate copy stream -- it overlaps the step the
+// engine stream is computing -- and commit swaps them in (device-to-device, then the hoisted aux
+// program) on the engine stream.  Neither call blocks the host.
+extern "C" int pinn_engine_prefetch_points(pinn_engine_t* h, const float* x_col, int64_t n_col, int32_t n_bc,
+                                           const float* const* x_bd, const float* const* u_bd, const int64_t* n_bd) {
+  CK(cudaSetDevice(h->device));
+  if (!h->points_set) return fail("prefetch_points: call set_points once first (it fixes the shapes)");
+  if (n_col != h->n_col || n_bc != h->spec.n_bc) return fail("prefetch_points: shapes differ from the current point set");
+  for (int i = 0; i < n_bc; ++i)
+    if (n_bd[i] != h->n_bd[i]) return fail("prefetch_points: boundary group %d has %lld points, current set has %lld", i,
+                                           (long long)n_bd[i], (long long)h->n_bd[i]);
+  if (h->spec.n_aux_user > 0 || h->col.base || h->bc.base || !h->col.own_coords)
+    return fail("prefetch_points: only for engine-owned point sets without user aux/base columns (use set_points)");
+  const int d = h->spec.d_in;
+  if (!h->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_staged, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_consumed, cudaEventDisableTiming));
+  }
+  if (h->stg_col_cap < (size_t)n_col * d) {
+    if (h->stg_col) cudaFree(h->stg_col);
+    CK(cudaMalloc(&h->stg_col, sizeof(float) * n_col * d));
+    h->stg_col_cap = (size_t)n_col * d;
+  }
+  if (h->n_bd_total > 0 && h->stg_bc_cap < (size_t)h->n_bd_total) {
+    if (h->stg_bc) cudaFree(h->stg_bc);
+    if (h->stg_ubc) cudaFree(h->stg_ubc);
+    CK(cudaMalloc(&h->stg_bc, sizeof(float) * h->n_bd_total * d));
+    CK(cudaMalloc(&h->stg_ubc, sizeof(float) * h->n_bd_total));
+    h->stg_bc_cap = (size_t)h->n_bd_total;
+  }
+  if (h->staged) return fail("prefetch_points: the previous prefetch has not been committed");
+  CK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed, 0));  // staging free again (no-op before the first commit)
+  CK(cudaMemcpyAsync(h->stg_col, x_col, sizeof(float) * n_col * d, cudaMemcpyHostToDevice, h->copy_stream));
+  int64_t o = 0;
+  for (int i = 0; i < n_bc; ++i) {
+    if (n_bd[i] == 0) continue;
+    CK(cudaMemcpyAsync(h->stg_bc + o * d, x_bd[i], sizeof(float) * n_bd[i] * d, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaMemcpyAsync(h->stg_ubc + o, u_bd[i], sizeof(float) * n_bd[i], cudaMemcpyHostToDevice, h->copy_stream));
+    o += n_bd[i];
+  }
+  CK(cudaEventRecord(h->ev_staged, h->copy_stream));
+  h->staged = true;
+  return 0;
+}
+
+extern "C" int pinn_engine_commit_points(pinn_engine_t* h) {
+  CK(cudaSetDevice(h->device));
+  if (!h->staged) return fail("commit_points: nothing was prefetched");
+  const int d = h->spec.d_in;
+  CK(cudaStreamWaitEvent(h->stream, h->ev_staged, 0));
+  CK(cudaMemcpyAsync(h->col.coords, h->stg_col, sizeof(float) * h->n_col * d, cudaMemcpyDeviceToDevice, h->stream));
+  if (h->n_bd_total > 0) {
+    CK(cudaMemcpyAsync(h->bc.coords, h->stg_bc, sizeof(float) * h->n_bd_total * d, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->bc.aux, h->stg_ubc, sizeof(float) * h->n_bd_total, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  CK(cudaEventRecord(h->ev_consumed, h->stream));
+  if (h->spec.n_aux_ops > 0) {
+    k_eval_aux<<<(unsigned)((h->n_col + 255) / 256), 256, 0, h->stream>>>(h->prog_aux, h->col.coords, d, nullptr, 0, h->col.aux,
+                                                                          h->spec.n_aux_col, h->n_col);
+    CK(cudaGetLastError());
+  }
+  h->staged = false;
+  return 0;
 }
 
 extern "C" int pinn_engine_set_global_counts(pinn_engine_t* h, int64_t n_col_global, const int64_t* n_bd_global) {

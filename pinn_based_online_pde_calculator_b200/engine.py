@@ -32,7 +32,7 @@ EXPORTS = [
     "pinn_engine_get_params", "pinn_engine_set_points", "pinn_engine_set_global_counts",
     "pinn_engine_set_loss", "pinn_engine_loss_grad", "pinn_engine_adam_init", "pinn_engine_adam_steps",
     "pinn_engine_eval", "pinn_engine_lbfgs", "pinn_nccl_unique_id", "pinn_engine_init_nccl",
-    "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels", "pinn_engine_kernel_kind", "pinn_engine_phase_profile", "pinn_sample_lhs", "pinn_sample_cdf2d", "pinn_engine_sync", "pinn_umma_probe",
+    "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels", "pinn_engine_kernel_kind", "pinn_engine_phase_profile", "pinn_sample_lhs", "pinn_sample_cdf2d", "pinn_engine_sync", "pinn_umma_probe", "pinn_engine_prefetch_points", "pinn_engine_commit_points",
 ]
 
 
@@ -74,6 +74,8 @@ def load_library(path: Optional[str] = None):
     lib.pinn_engine_destroy.restype = None
     lib.pinn_engine_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.pinn_engine_sync.argtypes = [C.c_void_p]
+    lib.pinn_engine_prefetch_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pinn_engine_commit_points.argtypes = [C.c_void_p]
     lib.pinn_engine_num_params.argtypes = [C.c_void_p]
     lib.pinn_engine_num_params.restype = C.c_int64
     lib.pinn_engine_num_loss_info.argtypes = [C.c_void_p]
@@ -227,6 +229,24 @@ class PinnEngine:
     def set_stream(self, cuda_stream_ptr: int):
         _check(self.lib, self.lib.pinn_engine_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
         self._shared_stream = True
+
+    def prefetch_points(self, x_col, x_bd: Sequence = (), u_bd: Sequence = ()):
+        """Start copying the NEXT point set (host arrays, same shapes as the current one; pinned memory
+        makes the copy asynchronous) while the step in flight computes; see commit_points."""
+        x_col = _as_f32(x_col)
+        xb = [_as_f32(a) for a in x_bd]
+        ub = [_as_f32(a).reshape(-1) for a in u_bd]
+        n = len(xb)
+        PX = (C.c_void_p * max(1, n))(*[_ptr(a) for a in xb])
+        PU = (C.c_void_p * max(1, n))(*[_ptr(a) for a in ub])
+        NB = (C.c_int64 * max(1, n))(*[int(a.shape[0]) for a in xb])
+        # keep the host buffers alive while their asynchronous copy may be in flight (two generations)
+        self._prefetched = (getattr(self, "_prefetched", (None,))[-1], (x_col, xb, ub))
+        _check(self.lib, self.lib.pinn_engine_prefetch_points(self.h, _ptr(x_col), int(x_col.shape[0]), n, PX, PU, NB))
+
+    def commit_points(self):
+        """Swap the prefetched point set in (engine stream; does not block)."""
+        _check(self.lib, self.lib.pinn_engine_commit_points(self.h))
 
     def sync(self):
         _check(self.lib, self.lib.pinn_engine_sync(self.h))

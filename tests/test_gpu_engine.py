@@ -210,6 +210,35 @@ def test_device_resident_points_and_params_roundtrip():
     eng.close()
 
 
+def test_prefetch_commit_equals_set_points():
+    """pinn_engine_prefetch_points / commit_points (pipelined refresh of the point set) must give the
+    same bits as set_points on the same host arrays, and reject mismatching shapes."""
+    pb = make_problem(n_hidden=2, width=64, d_in=2, expr="u_xx + u_yy + sin(x)*y", n_col=777, n_bd=33, n_bc=2, lb=[0, 0], ub=[1, 1])
+    pb2 = make_problem(n_hidden=2, width=64, d_in=2, expr="u_xx + u_yy + sin(x)*y", n_col=777, n_bd=33, n_bc=2, lb=[0, 0], ub=[1, 1],
+                       seed=5)
+    eng = engine_for(pb)
+    g1, i1 = eng.loss_grad()
+    f32 = lambda a: np.ascontiguousarray(a.numpy(), dtype=np.float32)
+    eng.set_points(f32(pb2["x_col"]), [f32(a) for a in pb2["x_bd"]], [f32(a) for a in pb2["u_bd"]])
+    g2, i2 = eng.loss_grad()
+    assert not torch.equal(g1, g2)
+    eng.prefetch_points(f32(pb["x_col"]), [f32(a) for a in pb["x_bd"]], [f32(a) for a in pb["u_bd"]])
+    eng.commit_points()
+    g3, i3 = eng.loss_grad()
+    assert torch.equal(g3, g1) and np.array_equal(i3, i1)
+    eng.prefetch_points(f32(pb2["x_col"]), [f32(a) for a in pb2["x_bd"]], [f32(a) for a in pb2["u_bd"]])
+    with pytest.raises(RuntimeError, match="not been committed"):
+        eng.prefetch_points(f32(pb["x_col"]), [f32(a) for a in pb["x_bd"]], [f32(a) for a in pb["u_bd"]])
+    eng.commit_points()
+    g4, i4 = eng.loss_grad()
+    assert torch.equal(g4, g2) and np.array_equal(i4, i2)
+    with pytest.raises(RuntimeError, match="shapes differ"):
+        eng.prefetch_points(f32(pb["x_col"])[:100], [f32(a) for a in pb["x_bd"]], [f32(a) for a in pb["u_bd"]])
+    with pytest.raises(RuntimeError, match="nothing was prefetched"):
+        eng.commit_points()
+    eng.close()
+
+
 def test_errors_are_python_exceptions():
     wl = make_workload("C1")
     eng = PinnEngine(wl.net, wl.eq, n_bc=2)
@@ -217,6 +246,8 @@ def test_errors_are_python_exceptions():
         eng.loss_grad()
     with pytest.raises(ValueError):
         eng.set_params(np.zeros(3, np.float32))
+    with pytest.raises(RuntimeError, match="n_col"):
+        eng.set_points(np.zeros((0, 1), np.float32), [np.zeros((1, 1), np.float32)] * 2, [np.zeros(1, np.float32)] * 2)
     with pytest.raises(RuntimeError):
         PinnEngine(NetworkSpec(2, 300, [0, 0], [1, 1], feature_map="affine"), compile_equation("u_xx", 2), n_bc=0)
     eng.close()

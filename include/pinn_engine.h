@@ -157,6 +157,8 @@ int pinn_sample_cdf2d(int device, void* stream, uint32_t seed, int64_t n, const 
 /* fp32 FMA-pipe microbenchmark (roofline denominator of the SIMT path):
  * returns achieved TFLOP/s; variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2 */
 int pinn_fma_peak(int device, int variant, double* tflops_out);
+/* phase clocks (CTA 0) of the last launch of the experimental tcgen05 kernel family (PINN_B200_KERNEL=umma) */
+int pinn_engine_umma_clocks(pinn_engine_t* h, long long* out8);
 /* tcgen05 probe (measurement helper): D = A * B^T on one CTA, tf32 inputs / fp32 TMEM accumulator.  A, B0, B1
  * are RAW shared-memory images (the host lays the operands out), cfg = {M, N, k-steps, A MN-major, B MN-major,
  * products (2 = second one with B1 into lanes +16, M = 64), repetitions, words of A, words of B,

@@ -16,6 +16,7 @@
 #include "aux_kernels.cuh"
 #include "sampler_kernels.cuh"
 #include "jet_launch.h"
+#include "jet_umma.h"
 #include "pinn_common.h"
 
 static thread_local std::string g_err;
@@ -86,6 +87,10 @@ struct pinn_engine {
   float *stg_col = nullptr, *stg_bc = nullptr, *stg_ubc = nullptr;
   size_t stg_col_cap = 0, stg_bc_cap = 0;
   bool staged = false;
+  long long umma_clk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool use_umma = false;         // PINN_B200_KERNEL=umma and the configuration is supported: collocation term on tcgen05
+  float* d_uimg = nullptr;       // pre-split operand images of the tcgen05 family
+  long long* d_uclk = nullptr;  // phase clocks of the last tcgen05 launch (experimental family)
   pinn_spec_t spec{};
   std::vector<int32_t> ops, aux_ops;
   std::vector<float> consts;
@@ -261,6 +266,16 @@ extern "C" int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engi
   h->grid_max_col = h->num_sms * occ_col;
   h->grid_max_bc = h->num_sms * occ_bc;
   h->grid_max = std::max(h->grid_max_col, h->grid_max_bc);
+  {
+    const char* kenv = getenv("PINN_B200_KERNEL");
+    if (kenv && !strcmp(kenv, "umma")) {
+      if (!jet_umma_supported(h->net, h->kcol->k, spec->n1, spec->n2, spec->mix)) {
+        delete h;
+        return fail("PINN_B200_KERNEL=umma: the tcgen05 family supports padded width 64 with jets (value, 2 first, combined second order), 2..4 hidden layers");
+      }
+      h->use_umma = true;
+    }
+  }
   h->n_slots = spec->n_bc + 1;
   h->n_info = 3 + h->n_slots;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -307,6 +322,11 @@ extern "C" int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engi
   CK(cudaMalloc(&h->d_meta, sizeof(LossMeta)));
   CK(cudaMemset(h->d_ring_pos, 0, sizeof(int)));
   CK(cudaMemset(h->d_adam_count, 0, sizeof(int)));
+  if (h->use_umma) {
+    CK(cudaMalloc(&h->d_uimg, sizeof(float) * jet_umma_image_floats(h->net)));
+    CK(cudaMalloc(&h->d_uclk, sizeof(long long) * 8));
+    CK(cudaMemset(h->d_uclk, 0, sizeof(long long) * 8));
+  }
   if (!getenv("PINN_B200_NO_L2_WINDOW")) apply_l2_policy(h);
   *out = h;
   return 0;
@@ -327,7 +347,7 @@ extern "C" void pinn_engine_destroy(pinn_engine_t* h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void* bufs[] = {h->d_params, h->d_fused, h->d_m, h->d_v, h->d_wpack, h->d_stash, h->d_seg_scale,
                   h->d_lr, h->d_adam_c, h->d_loss_part, h->d_ring, h->d_ring_pos, h->d_adam_count, h->d_meta,
-                  h->d_x, h->d_g, h->d_d, h->d_xt, h->d_S, h->d_Y, h->d_rho, h->d_alpha, h->d_scal};
+                  h->d_x, h->d_g, h->d_d, h->d_xt, h->d_S, h->d_Y, h->d_rho, h->d_alpha, h->d_scal, h->d_uimg, h->d_uclk};
   for (void* b : bufs)
     if (b) cudaFree(b);
   free_set(h->col);
@@ -388,7 +408,7 @@ extern "C" int64_t pinn_engine_num_params(pinn_engine_t* h) { return h->fmap.n_p
 extern "C" int32_t pinn_engine_num_loss_info(pinn_engine_t* h) { return h->n_info; }
 extern "C" int32_t pinn_engine_tile_points(pinn_engine_t* h) { return h->kcol->tile_points; }
 extern "C" int32_t pinn_engine_launches_per_eval(pinn_engine_t* h) { return 6; }
-extern "C" int32_t pinn_engine_kernel_kind(pinn_engine_t* h) { return h->kcol->kind; }
+extern "C" int32_t pinn_engine_kernel_kind(pinn_engine_t* h) { return h->use_umma ? 2 : h->kcol->kind; }
 
 extern "C" int pinn_engine_set_params(pinn_engine_t* h, const float* flat, int on_device) {
   CK(cudaSetDevice(h->device));
@@ -537,6 +557,11 @@ extern "C" int pinn_engine_set_points(pinn_engine_t* h, const float* x_col, int6
     L.n_tiles = (int)((n_col + tp - 1) / tp);
     L.seg_tile_end[0] = L.n_tiles; L.seg_pt_begin[0] = 0; L.seg_pt_end[0] = n_col; L.seg_slot[0] = h->n_slots - 1;
     h->grid_col = std::min(L.n_tiles, h->grid_max_col);
+    if (h->use_umma) {  // tiles of 32 points, one CTA per SM
+      L.n_tiles = (int)((n_col + 31) / 32);
+      L.seg_tile_end[0] = L.n_tiles;
+      h->grid_col = std::min(L.n_tiles, h->num_sms);
+    }
   }
   fill_launch(h, h->Lbc, h->kbc, h->prog_bc);
   {
@@ -657,7 +682,12 @@ static int enqueue_eval(pinn_engine* h, const float* params_dev, int tick) {
   CK(cudaMemsetAsync(h->d_gacc, 0, sizeof(float) * (size_t)nb * h->net.pg, st));
   CK(cudaMemsetAsync(h->d_loss_part, 0, sizeof(double) * (size_t)nb * h->n_slots, st));
   if (h->Lbc.n_tiles > 0) CK(h->kbc->launch(h->Lbc, true, h->grid_bc, st));
-  CK(h->kcol->launch(h->Lcol, true, h->grid_col, st));
+  if (h->use_umma) {
+    CK(jet_umma_build_images(h->d_wpack, h->net, h->kcol->ldw, h->d_uimg, st));
+    CK(jet_umma_train_launch(h->Lcol, h->d_uimg, h->kcol->ldw, h->grid_col, st, h->d_uclk));
+  } else {
+    CK(h->kcol->launch(h->Lcol, true, h->grid_col, st));
+  }
   k_grad_reduce<<<(P + 127) / 128, 128, 0, st>>>(h->fmap, h->d_gacc, nb, h->net.pg, h->d_fused);
   CK(cudaGetLastError());
   k_loss_reduce<<<1, 32, 0, st>>>(h->d_loss_part, nb, h->n_slots, h->d_fused + P);
@@ -797,7 +827,24 @@ extern "C" int pinn_engine_eval(pinn_engine_t* h, const float* z, int64_t n, con
   const int tp = h->kcol->tile_points;
   L.n_tiles = (int)((n + tp - 1) / tp);
   L.seg_tile_end[0] = L.n_tiles; L.seg_pt_begin[0] = 0; L.seg_pt_end[0] = n; L.seg_slot[0] = 0;
-  cudaError_t e = h->kcol->launch(L, false, std::min(L.n_tiles, h->grid_max_col), st);
+  cudaError_t e;
+  const char* kenv = getenv("PINN_B200_KERNEL");
+  if (kenv && !strcmp(kenv, "umma")) {
+    // experimental tcgen05 family (evaluation only so far)
+    if (!jet_umma_supported(h->net, K, h->spec.n1, h->spec.n2, h->spec.mix)) { cleanup(); return fail("PINN_B200_KERNEL=umma: configuration not supported by the tcgen05 family"); }
+    float* images = (float*)dalloc(sizeof(float) * jet_umma_image_floats(h->net));
+    long long* clk = (long long*)dalloc(sizeof(long long) * 8);
+    if (!images || !clk) { cleanup(); return fail("cudaMalloc failed"); }
+    cudaMemsetAsync(clk, 0, sizeof(long long) * 8, st);
+    L.n_tiles = (int)((n + 31) / 32);
+    L.seg_tile_end[0] = L.n_tiles;
+    e = jet_umma_build_images(h->d_wpack, h->net, h->kcol->ldw, images, st);
+    if (e == cudaSuccess) e = jet_umma_eval_launch(L, images, 2 * h->num_sms, st, clk);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->umma_clk, clk, sizeof(long long) * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  } else {
+    e = h->kcol->launch(L, false, std::min(L.n_tiles, h->grid_max_col), st);
+  }
   if (e != cudaSuccess) { cleanup(); return fail("eval launch: %s", cudaGetErrorString(e)); }
   if (!on_device) {
     if (u_out) cudaMemcpyAsync(u_out, du, sizeof(float) * n, cudaMemcpyDeviceToHost, st);
@@ -811,6 +858,17 @@ extern "C" int pinn_engine_eval(pinn_engine_t* h, const float* z, int64_t n, con
     cleanup();
     if (e != cudaSuccess) return fail("eval: %s", cudaGetErrorString(e));
   }
+  return 0;
+}
+
+extern "C" int pinn_engine_umma_clocks(pinn_engine_t* h, long long* out8) {
+  if (h->use_umma) {  // clocks of the last training launch
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out8, h->d_uclk, sizeof(long long) * 8, cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  for (int i = 0; i < 8; ++i) out8[i] = h->umma_clk[i];
   return 0;
 }
 

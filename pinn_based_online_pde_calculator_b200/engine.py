@@ -32,7 +32,7 @@ EXPORTS = [
     "pinn_engine_get_params", "pinn_engine_set_points", "pinn_engine_set_global_counts",
     "pinn_engine_set_loss", "pinn_engine_loss_grad", "pinn_engine_adam_init", "pinn_engine_adam_steps",
     "pinn_engine_eval", "pinn_engine_lbfgs", "pinn_nccl_unique_id", "pinn_engine_init_nccl",
-    "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels", "pinn_engine_kernel_kind", "pinn_engine_phase_profile", "pinn_sample_lhs", "pinn_sample_cdf2d", "pinn_engine_sync", "pinn_umma_probe", "pinn_engine_prefetch_points", "pinn_engine_commit_points",
+    "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels", "pinn_engine_kernel_kind", "pinn_engine_phase_profile", "pinn_sample_lhs", "pinn_sample_cdf2d", "pinn_engine_sync", "pinn_umma_probe", "pinn_engine_prefetch_points", "pinn_engine_commit_points", "pinn_engine_umma_clocks",
 ]
 
 
@@ -209,7 +209,7 @@ class PinnEngine:
         self.n_params = int(self.lib.pinn_engine_num_params(h))
         self.n_info = int(self.lib.pinn_engine_num_loss_info(h))
         self.K = eq.K
-        self.kernel = ("simt_fp32", "mma_3xtf32")[int(self.lib.pinn_engine_kernel_kind(h))]
+        self.kernel = ("simt_fp32", "mma_3xtf32", "umma_3xtf32")[int(self.lib.pinn_engine_kernel_kind(h))]
         self._keep = []  # device tensors borrowed by the engine
         self.lref = 1.0
         self.lw = 1.0

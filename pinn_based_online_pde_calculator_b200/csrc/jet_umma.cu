@@ -285,8 +285,8 @@ constexpr int SM_WIMG = 0;                    // current weight images (hi, lo):
 constexpr int SM_STH = 32768;                 // wgrad A operand: layer-input jets H (hi plane, lo plane), 2 x 32 KB
 constexpr int SM_STA = SM_STH + 65536;        // wgrad B operand: pre-activation adjoints (hi plane | lo plane), 2 x 32 KB
 constexpr int SM_EXCH = SM_STA + 65536;       // 8 exchange arrays [UCH][32]
-constexpr int SM_MISC = SM_EXCH + 8 * UCH * 32 * 4;
-constexpr int SM_TRAIN_BYTES = SM_MISC + (8 * 32 + PINN_MAX_OPS + PINN_MAX_CONSTS) * 4 + 64;
+constexpr int SM_MISC = SM_EXCH + 2 * 8 * UCH * 32 * 4;  // exchange arrays per unit half
+constexpr int SM_TRAIN_BYTES = SM_MISC + (12 * 32 + PINN_MAX_OPS + PINN_MAX_CONSTS) * 4 + 64;
 constexpr uint32_t TC_DW = 256, TC_TRAIN_COLS = 512;
 constexpr int PLANE = 32768;  // bytes of one staging plane: 2 groups of 32 units x 128 rows x 128 B
 
@@ -328,14 +328,15 @@ __device__ __forceinline__ void bulk_load_w(uint8_t* smem, const float* src, uin
   bulk_g2s(smem + SM_WIMG + UIMG * 4, src + UIMG, UIMG * 4, bar);
 }
 
-__global__ void __launch_bounds__(128, 1) jet_umma_train_kernel(PinnLaunch L, const float* __restrict__ img, int ldw,
+__global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, const float* __restrict__ img, int ldw,
                                                                 long long* __restrict__ clk) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const PinnNet& net = L.net;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = tid;  // MMA row = 32 * channel + point
+  // 8 warps: warp = jet channel (= TMEM lane quadrant, wid % 4), hsel = which half of the units the warp handles
+  const int tid = threadIdx.x, wid = tid >> 5, warp = wid & 3, hsel = wid >> 2, lane = tid & 31;
+  const int row = 32 * warp + lane;  // MMA row = 32 * channel + point
   const int Lh = net.n_hidden;
-  float* x1 = reinterpret_cast<float*>(smem + SM_EXCH);
+  float* x1 = reinterpret_cast<float*>(smem + SM_EXCH) + hsel * 8 * UCH * 32;
   float* x2 = x1 + UCH * 32;
   float* qx = x2 + UCH * 32;
   float* qy = qx + UCH * 32;
@@ -343,8 +344,8 @@ __global__ void __launch_bounds__(128, 1) jet_umma_train_kernel(PinnLaunch L, co
   float* py = px + UCH * 32;
   float* pl = py + UCH * 32;
   float* yl = pl + UCH * 32;
-  float* us = reinterpret_cast<float*>(smem + SM_MISC);  // [4][32]
-  float* ub = us + 4 * 32;                               // [4][32]
+  float* us = reinterpret_cast<float*>(smem + SM_MISC);  // [2][4][32] partial dot products of the two unit halves
+  float* ub = us + 8 * 32;                               // [4][32]
   int* s_ops = reinterpret_cast<int*>(ub + 4 * 32);
   float* s_consts = reinterpret_cast<float*>(s_ops + PINN_MAX_OPS);
   uint8_t* const Hh = smem + SM_STH;
@@ -354,9 +355,9 @@ __global__ void __launch_bounds__(128, 1) jet_umma_train_kernel(PinnLaunch L, co
   __shared__ uint64_t barD, barW, barL;
   __shared__ uint32_t tbase;
 
-  for (int i = tid; i < L.prog.n_ops; i += 128) s_ops[i] = L.prog.ops[i];
-  for (int i = tid; i < PINN_MAX_CONSTS; i += 128) s_consts[i] = L.prog.consts[i];
-  if (warp == 0) umma::tmem_alloc(&tbase, TC_TRAIN_COLS);
+  for (int i = tid; i < L.prog.n_ops; i += 256) s_ops[i] = L.prog.ops[i];
+  for (int i = tid; i < PINN_MAX_CONSTS; i += 256) s_consts[i] = L.prog.consts[i];
+  if (wid == 0) umma::tmem_alloc(&tbase, TC_TRAIN_COLS);
   if (tid == 0) {
     umma::mbar_init(&barD, 1);
     umma::mbar_init(&barW, 1);
@@ -391,13 +392,13 @@ __global__ void __launch_bounds__(128, 1) jet_umma_train_kernel(PinnLaunch L, co
       umma::tmem_ld8(tl + TC_DW, a);
       umma::tmem_ld8(tl + TC_DW + 64, b);
       umma::tmem_ld_wait();
-      if (lane < 16) gacc[net.off_wl + i] += a[0] + b[0];
+      if (lane < 16 && hsel == 0) gacc[net.off_wl + i] += a[0] + b[0];
       return;
     }
     float* d = (g == 0) ? gacc + net.off_w0 + (i < 3 ? i : 0) * UW : gacc + net.off_w[g] + i * ldw;
     const bool act_lane = lane < 16 && (g != 0 || i < 3);
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
+    {
+      const int half = hsel;
       float a[32], b[32];
       float4 acc4[8];
       umma::tmem_ld16(tl + TC_DW + 32 * half, reinterpret_cast<float(&)[16]>(a[0]));
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(128, 1) jet_umma_train_kernel(PinnLaunch L, co
       const bool last = (l == Lh - 1);
       float* st_l = stash + ((size_t)(l * UK + warp) * UW) * UTP + lane;
 #pragma unroll 1
-      for (int ch = 0; ch < UW / UCH; ++ch) {
+      for (int ch = 2 * hsel; ch < 2 * hsel + 2; ++ch) {
         const int u0 = ch * UCH;
         float a[UCH], y[UCH];
         if (l == 0) {
@@ -534,16 +535,16 @@ __global__ void __launch_bounds__(128, 1) jet_umma_train_kernel(PinnLaunch L, co
 
     // ------------------------------------------------------------ output layer, residual, seeds
     {
-      float uc = net.epsil * (uacc + (warp == 0 ? __ldg(L.wpack + net.off_bl) : 0.f));
-      if (L.base) uc += __ldg(L.base + gp * UK + warp);
-      us[warp * 32 + lane] = uc;
+      float uc = net.epsil * (uacc + ((warp == 0 && hsel == 0) ? __ldg(L.wpack + net.off_bl) : 0.f));
+      if (L.base && hsel == 0) uc += __ldg(L.base + gp * UK + warp);
+      us[(hsel * 4 + warp) * 32 + lane] = uc;
     }
     __syncthreads();
-    if (warp == 0) {
+    if (wid == 0) {
       float u[UK][1], f[1], df[UK][1];
       const float* auxp[1] = {L.aux ? (L.aux + gp * L.n_aux) : nullptr};
 #pragma unroll
-      for (int c = 0; c < UK; ++c) u[c][0] = us[c * 32 + lane];
+      for (int c = 0; c < UK; ++c) u[c][0] = us[c * 32 + lane] + us[(4 + c) * 32 + lane];
       vm_run<UK, 1>(s_ops, L.prog.n_ops, s_consts, z, auxp, u, f, df);
       const float sc = valid ? __ldg(L.seg_scale + slot) : 0.f;
 #pragma unroll
@@ -562,7 +563,7 @@ __global__ void __launch_bounds__(128, 1) jet_umma_train_kernel(PinnLaunch L, co
 #pragma unroll
       for (int i = 0; i < UCH; ++i) v[i] = 0.f;
 #pragma unroll 1
-      for (int ch = 0; ch < UW / UCH; ++ch) {
+      for (int ch = 2 * hsel; ch < 2 * hsel + 2; ++ch) {
         v[0] = (ch == 0) ? e : 0.f;
         stage16(Ah, Al, row, ch * UCH, v);
       }
@@ -574,7 +575,7 @@ __global__ void __launch_bounds__(128, 1) jet_umma_train_kernel(PinnLaunch L, co
         const int act = (l == 0) ? net.act_first : net.act_hidden;
         const float* st_l = stash + ((size_t)(l * UK + warp) * UW) * UTP + lane;
 #pragma unroll 1
-        for (int ch = 0; ch < UW / UCH; ++ch) {
+        for (int ch = 2 * hsel; ch < 2 * hsel + 2; ++ch) {
           const int u0 = ch * UCH;
           float s[UCH], y[UCH];
 #pragma unroll
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(128, 1) jet_umma_train_kernel(PinnLaunch L, co
 #pragma unroll
         for (int i = 0; i < UCH; ++i) v[i] = 0.f;
 #pragma unroll 1
-        for (int ch = 0; ch < UW / UCH; ++ch) {
+        for (int ch = 2 * hsel; ch < 2 * hsel + 2; ++ch) {
           if (ch == 0) { v[0] = net.scl * h0; v[1] = net.scl * h1; v[2] = net.scl * h2; }
           else { v[0] = v[1] = v[2] = 0.f; }
           stage16(Hh, Hl, row, ch * UCH, v);
@@ -652,7 +653,7 @@ __global__ void __launch_bounds__(128, 1) jet_umma_train_kernel(PinnLaunch L, co
         const int act = (l == 0) ? net.act_first : net.act_hidden;
         const float* st_l = stash + ((size_t)(l * UK + warp) * UW) * UTP + lane;
 #pragma unroll 1
-        for (int ch = 0; ch < UW / UCH; ++ch) {
+        for (int ch = 2 * hsel; ch < 2 * hsel + 2; ++ch) {
           const int u0 = ch * UCH;
           float s[UCH], yb[UCH], ab[UCH], d3v[UCH];
 #pragma unroll
@@ -735,7 +736,7 @@ __global__ void __launch_bounds__(128, 1) jet_umma_train_kernel(PinnLaunch L, co
   }
 
   // ------------------------------------------------------------ per-CTA scalars
-  if (warp == 0) {
+  if (wid == 0) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
@@ -752,7 +753,7 @@ __global__ void __launch_bounds__(128, 1) jet_umma_train_kernel(PinnLaunch L, co
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_free(tb, TC_TRAIN_COLS);
+  if (wid == 0) umma::tmem_free(tb, TC_TRAIN_COLS);
 }
 
 size_t eval_smem_bytes(const PinnNet& net) {
@@ -775,7 +776,7 @@ cudaError_t jet_umma_build_images(const float* wpack, const PinnNet& net, int ld
 cudaError_t jet_umma_train_launch(const PinnLaunch& L, const float* images, int ldw, int grid, cudaStream_t st, long long* clk) {
   cudaError_t e = cudaFuncSetAttribute(jet_umma_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TRAIN_BYTES);
   if (e != cudaSuccess) return e;
-  jet_umma_train_kernel<<<grid, 128, SM_TRAIN_BYTES, st>>>(L, images, ldw, clk);
+  jet_umma_train_kernel<<<grid, 256, SM_TRAIN_BYTES, st>>>(L, images, ldw, clk);
   return cudaGetLastError();
 }
 

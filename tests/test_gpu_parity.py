@@ -59,3 +59,35 @@ def test_loss_and_grad_match_oracle(name, kernel, monkeypatch):
     # the 5x256 heat residual is a small difference of large terms: measured 1.1e-5 in fp32
     assert rel_err(f, f_ref) < (2e-5 if name.startswith("C5") else TOL)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_tcgen05_family_matches_oracle_and_production_kernel(monkeypatch):
+    """Experimental tcgen05 family (PINN_B200_KERNEL=umma): TS-form layer GEMMs with the
+    activation operand in Tensor Memory, swizzled MN-major weight-gradient GEMMs.  Loss, gradient and
+    evaluation must agree with the oracle within the parity bar and with the production kernel."""
+    from tests.helpers import engine_for, make_problem, oracle_loss_grad, rel_err
+
+    pb = make_problem(n_hidden=4, width=64, d_in=2, expr="u_xx + u_yy + 2*y*(1-y) + 2*x*(1-x)", n_col=1500, n_bd=40, n_bc=4,
+                      lb=[0, 0], ub=[1, 1])
+    g_ref, info_ref, _, _ = oracle_loss_grad(pb)
+    monkeypatch.delenv("PINN_B200_KERNEL", raising=False)
+    eng0 = engine_for(pb)
+    g0, i0 = eng0.loss_grad()
+    z = pb["x_col"].numpy().astype(np.float32)
+    u0, f0, j0 = eng0.eval(z, want_jets=True)
+    eng0.close()
+    monkeypatch.setenv("PINN_B200_KERNEL", "umma")
+    eng1 = engine_for(pb)
+    assert eng1.kernel == "umma_3xtf32"
+    g1, i1 = eng1.loss_grad()
+    u1, f1, j1 = eng1.eval(z, want_jets=True)
+    assert np.allclose(i1, info_ref, rtol=1e-5)
+    assert rel_err(g1.cpu().numpy(), g_ref) < 1e-5
+    assert rel_err(g1.cpu().numpy(), g0.cpu().numpy()) < 1e-5
+    assert rel_err(u1, u0) < 1e-5 and rel_err(f1, f0) < 1e-5 and rel_err(j1, j0) < 1e-5
+    # unsupported configurations fail loudly instead of silently using another family
+    pb2 = make_problem(n_hidden=2, width=32, d_in=2, expr="u_xx + u_yy", n_col=10, n_bd=4, n_bc=1, lb=[0, 0], ub=[1, 1])
+    with pytest.raises(RuntimeError, match="tcgen05"):
+        engine_for(pb2)
+    eng1.close()

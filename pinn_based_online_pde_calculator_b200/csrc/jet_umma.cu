@@ -370,6 +370,9 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
   const uint32_t tb = tbase;
   const uint32_t tl = tb + ((uint32_t)(warp * 32) << 16);
   uint32_t parD = 0, parW = 0, parL = 0;
+  // the cross-channel exchange only couples the four warps of a unit half: a named barrier per half lets
+  // the two halves drift apart and overlap each other's latencies
+  auto half_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + hsel) : "memory"); };
   const uint32_t idesc = umma::idesc_tf32(128, UW, 0, 0);
   const float* W0 = L.wpack + net.off_w0;
   const float* wl = L.wpack + net.off_wl;
@@ -489,7 +492,7 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
             for (int i = 0; i < UCH; ++i) q[i * 32 + lane] = bq * a[i] * a[i];
           }
         }
-        __syncthreads();
+        half_sync();
         if (warp == 1 || warp == 2) {
 #pragma unroll
           for (int i = 0; i < UCH; ++i) y[i] = x1[i * 32 + lane] * a[i];
@@ -507,7 +510,7 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
           tmem_st16(tl + TC_AHI + u0, hi);
           tmem_st16(tl + TC_ALO + u0, lo);
         }
-        __syncthreads();
+        half_sync();
       }
       lap(0);
       if (!last) {
@@ -593,7 +596,7 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
 #pragma unroll
             for (int i = 0; i < UCH; ++i) q[i * 32 + lane] = bq * s[i] * s[i];
           }
-          __syncthreads();
+          half_sync();
           if (warp == 1 || warp == 2) {
 #pragma unroll
             for (int i = 0; i < UCH; ++i) y[i] = x1[i * 32 + lane] * s[i];
@@ -602,7 +605,7 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
             for (int i = 0; i < UCH; ++i) y[i] = fmaf(x2[i * 32 + lane], qx[i * 32 + lane] + qy[i * 32 + lane], x1[i * 32 + lane] * s[i]);
           }
           stage16(Hh, Hl, row, u0, y);
-          __syncthreads();
+          half_sync();
         }
       } else {
         float v[UCH];
@@ -688,7 +691,7 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
               pl[i * 32 + lane] = s[i] * yb[i];
             }
           }
-          __syncthreads();
+          half_sync();
           if (warp == 0) {
 #pragma unroll
             for (int i = 0; i < UCH; ++i) {
@@ -715,7 +718,7 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
             tmem_st16(tl + TC_ALO + u0, lo);
           }
           stage16(Ah, Al, row, u0, ab);
-          __syncthreads();
+          half_sync();
         }
       }
       lap(6);

@@ -573,92 +573,21 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
     }
 #pragma unroll 1
     for (int l = Lh - 1; l >= -1; --l) {
-      // ---- R(l): recompute the output jets of hidden layer l (l = -1: the feature jets) -> wgrad A operand
       if (l >= 0) {
+        // ---- FB(l): ONE pass over the stash of hidden layer l gives (a) its output jets again -> wgrad A
+        // operand of layer l+1 and (b) the adjoint of its pre-activations -> TMEM (dgrad operand of layer l)
         const int act = (l == 0) ? net.act_first : net.act_hidden;
         const float* st_l = stash + ((size_t)(l * UK + warp) * UW) * UTP + lane;
+        if (l < Lh - 1) {
+          umma::mbar_wait(&barD, parD);  // data gradient of layer l+1 (issued in the previous iteration)
+          parD ^= 1;
+          umma::fence_after_sync();
+          if (tid == 0 && l >= 1) bulk_load_w(smem, img + (size_t)(l - 1) * 4 * UIMG + 2 * UIMG, &barL);  // dgrad image of layer l
+        }
 #pragma unroll 1
         for (int ch = 2 * hsel; ch < 2 * hsel + 2; ++ch) {
           const int u0 = ch * UCH;
-          float s[UCH], y[UCH];
-#pragma unroll
-          for (int i = 0; i < UCH; ++i) s[i] = st_l[(u0 + i) * UTP];
-          if (warp == 0) {
-            float d1[UCH], d2[UCH], d3[UCH];
-            act_bwd16(act, s, y, d1, d2, d3);
-#pragma unroll
-            for (int i = 0; i < UCH; ++i) {
-              x1[i * 32 + lane] = d1[i];
-              x2[i * 32 + lane] = d2[i];
-            }
-          } else if (warp < 3) {
-            float* q = (warp == 1) ? qx : qy;
-#pragma unroll
-            for (int i = 0; i < UCH; ++i) q[i * 32 + lane] = bq * s[i] * s[i];
-          }
-          half_sync();
-          if (warp == 1 || warp == 2) {
-#pragma unroll
-            for (int i = 0; i < UCH; ++i) y[i] = x1[i * 32 + lane] * s[i];
-          } else if (warp == 3) {
-#pragma unroll
-            for (int i = 0; i < UCH; ++i) y[i] = fmaf(x2[i * 32 + lane], qx[i * 32 + lane] + qy[i * 32 + lane], x1[i * 32 + lane] * s[i]);
-          }
-          stage16(Hh, Hl, row, u0, y);
-          half_sync();
-        }
-      } else {
-        float v[UCH];
-#pragma unroll
-        for (int i = 0; i < UCH; ++i) v[i] = 0.f;
-#pragma unroll 1
-        for (int ch = 2 * hsel; ch < 2 * hsel + 2; ++ch) {
-          if (ch == 0) { v[0] = net.scl * h0; v[1] = net.scl * h1; v[2] = net.scl * h2; }
-          else { v[0] = v[1] = v[2] = 0.f; }
-          stage16(Hh, Hl, row, ch * UCH, v);
-        }
-      }
-      lap(3);
-      // ---- weight gradient of GEMM layer l+1
-      umma::fence_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        umma::fence_after_sync();
-        issue_wgrad(tb, smem);
-        umma::commit(&barW);
-      }
-      // bias gradient of layer l+1 (value-channel rows 0..31 of the adjoint operand), except for the output layer
-      if (l + 1 < Lh && tid < UW) {
-        float sb = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < UTP; ++r) {
-          const uint32_t o = st_off(r, tid);
-          sb += *reinterpret_cast<const float*>(Ah + o) + *reinterpret_cast<const float*>(Al + o);
-        }
-        gacc[net.off_b[l + 1] + tid] += sb;
-      }
-      umma::mbar_wait(&barW, parW);
-      parW ^= 1;
-      umma::fence_after_sync();
-      lap(4);
-      flush_dw(l + 1);
-      lap(5);
-      if (l < 0) break;
-
-      // ---- B(l): adjoint of the activation jets of hidden layer l
-      if (l < Lh - 1) {
-        umma::mbar_wait(&barD, parD);  // data gradient of layer l+1 (issued at the end of B(l+1))
-        parD ^= 1;
-        umma::fence_after_sync();
-        if (tid == 0 && l >= 1) bulk_load_w(smem, img + (size_t)(l - 1) * 4 * UIMG + 2 * UIMG, &barL);  // dgrad image of layer l
-      }
-      {
-        const int act = (l == 0) ? net.act_first : net.act_hidden;
-        const float* st_l = stash + ((size_t)(l * UK + warp) * UW) * UTP + lane;
-#pragma unroll 1
-        for (int ch = 2 * hsel; ch < 2 * hsel + 2; ++ch) {
-          const int u0 = ch * UCH;
-          float s[UCH], yb[UCH], ab[UCH], d3v[UCH];
+          float s[UCH], yb[UCH], y[UCH], ab[UCH], d3v[UCH];
 #pragma unroll
           for (int i = 0; i < UCH; ++i) s[i] = st_l[(u0 + i) * UTP];
           if (l == Lh - 1) {
@@ -669,7 +598,7 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
             umma::tmem_ld_wait();
           }
           if (warp == 0) {
-            float y[UCH], d1[UCH], d2[UCH];
+            float d1[UCH], d2[UCH];
             act_bwd16(act, s, y, d1, d2, d3v);
 #pragma unroll
             for (int i = 0; i < UCH; ++i) {
@@ -704,36 +633,90 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
 #pragma unroll
             for (int i = 0; i < UCH; ++i) {
               const int o = i * 32 + lane;
+              y[i] = x1[o] * s[i];
               ab[i] = fmaf(2.0f * x2[o] * bq * s[i], yl[o], x1[o] * yb[i]);
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < UCH; ++i) ab[i] = x1[i * 32 + lane] * yb[i];
+            for (int i = 0; i < UCH; ++i) {
+              const int o = i * 32 + lane;
+              y[i] = fmaf(x2[o], qx[o] + qy[o], x1[o] * s[i]);
+              ab[i] = x1[o] * yb[i];
+            }
           }
-          if (l >= 1) {
+          stage16(Hh, Hl, row, u0, y);
+          {
             float hi[UCH], lo[UCH];
 #pragma unroll
             for (int i = 0; i < UCH; ++i) split_rn(ab[i], hi[i], lo[i]);
             tmem_st16(tl + TC_AHI + u0, hi);
             tmem_st16(tl + TC_ALO + u0, lo);
           }
-          stage16(Ah, Al, row, u0, ab);
           half_sync();
         }
-      }
-      lap(6);
-      if (l >= 1) {
         umma::tmem_st_wait();
-        umma::fence_before_sync();
-        __syncthreads();
-        umma::fence_after_sync();
-        if (tid == 0) {
+      } else {
+        // l = -1: the input of GEMM layer 0 are the feature jets (units 0..2)
+        float v[UCH];
+#pragma unroll
+        for (int i = 0; i < UCH; ++i) v[i] = 0.f;
+#pragma unroll 1
+        for (int ch = 2 * hsel; ch < 2 * hsel + 2; ++ch) {
+          if (ch == 0) { v[0] = net.scl * h0; v[1] = net.scl * h1; v[2] = net.scl * h2; }
+          else { v[0] = v[1] = v[2] = 0.f; }
+          stage16(Hh, Hl, row, ch * UCH, v);
+        }
+      }
+      lap(3);
+      // ---- weight gradient of GEMM layer l+1 (staged H x staged adjoints) and data gradient of layer l (TMEM adjoints)
+      umma::fence_async_smem();
+      umma::fence_before_sync();
+      __syncthreads();
+      umma::fence_after_sync();
+      if (tid == 0) {
+        issue_wgrad(tb, smem);
+        umma::commit(&barW);
+        if (l >= 1) {
           umma::mbar_wait(&barL, parL);
           issue_layer_gemm(tb, reinterpret_cast<const float*>(smem + SM_WIMG), reinterpret_cast<const float*>(smem + SM_WIMG) + UIMG, idesc);
           umma::commit(&barD);
         }
-        parL ^= 1;
       }
+      if (l >= 1) parL ^= 1;
+      // bias gradient of layer l+1 (value-channel rows 0..31 of the staged adjoints), except for the output layer
+      if (l + 1 < Lh && tid < UW) {
+        float sb = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < UTP; ++r) {
+          const uint32_t o = st_off(r, tid);
+          sb += *reinterpret_cast<const float*>(Ah + o) + *reinterpret_cast<const float*>(Al + o);
+        }
+        gacc[net.off_b[l + 1] + tid] += sb;
+      }
+      umma::mbar_wait(&barW, parW);
+      parW ^= 1;
+      umma::fence_after_sync();
+      lap(4);
+      flush_dw(l + 1);
+      lap(5);
+      if (l < 0) break;
+      // ---- C(l): the adjoints of layer l (already split, in TMEM) become the staged operand of wgrad(l)
+      __syncthreads();  // the bias-gradient readers of the old operand are done
+#pragma unroll 1
+      for (int ch = 2 * hsel; ch < 2 * hsel + 2; ++ch) {
+        const int u0 = ch * UCH;
+        float hi[UCH], lo[UCH];
+        umma::tmem_ld16(tl + TC_AHI + u0, hi);
+        umma::tmem_ld16(tl + TC_ALO + u0, lo);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < UCH / 4; ++j) {
+          const uint32_t o = st_off(row, u0 + 4 * j);
+          *reinterpret_cast<float4*>(Ah + o) = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          *reinterpret_cast<float4*>(Al + o) = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+      }
+      lap(6);
     }
     lap(7);
   }

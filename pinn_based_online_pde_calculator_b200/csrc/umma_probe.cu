@@ -1,8 +1,9 @@
 // tcgen05 probe: runs D = A * B^T (tf32 inputs, fp32 accumulate in TMEM) on ONE CTA for operands given
-// as plain row-major host matrices, and dumps the whole TMEM tile.  Used by tools/umma_probe.py to pin
-// down, on the real chip, (1) the un-swizzled K-major / MN-major descriptor conventions, (2) the TMEM
-// lane layout of M=128 and of two interleaved M=64 tiles, (3) how the accumulator rounds, (4) the
-// issue rate.  Measurement helper, not on the product path.
+// as RAW shared-memory images (the host lays them out) or, for A, as a row-major matrix loaded into
+// TMEM (TS form), with explicit descriptor fields, and dumps the whole TMEM tile.  Used by
+// tools/umma_probe.py to pin down, on the real chip, (1) the K-major / MN-major descriptor conventions
+// and swizzle modes, (2) the TMEM lane layout of M=128 and of two interleaved M=64 tiles, (3) how inputs
+// and the accumulator round, (4) the issue rate.  Measurement helper, not on the product path.
 #include <stdio.h>
 
 #include "../../include/pinn_engine.h"

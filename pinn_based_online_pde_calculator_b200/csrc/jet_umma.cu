@@ -24,15 +24,18 @@ constexpr int UCH = 16;   // units per epilogue chunk
 constexpr int UIMG = UW * UW;
 constexpr int UMAXL = 3;  // hidden GEMM layers whose operand images stay resident in shared memory
 // TMEM columns of a tile
-constexpr uint32_t TC_D = 0, TC_AHI = 64, TC_ALO = 128, TC_COLS = 256;
+// D holds two column blocks: [0,64) = (hi + lo) * W_hi, [64,128) = (hi + lo) * W_lo (summed by the epilogue)
+constexpr uint32_t TC_D = 0, TC_AHI = 128, TC_ALO = 192, TC_COLS = 256;
 
 __device__ __forceinline__ void split_rn(float x, float& hi, float& lo) {
   hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
   lo = __fadd_rn(x, -hi);
 }
 
-// images per hidden GEMM layer l = 1..L-1: [0] forward hi, [1] forward lo (N = out, K = in),
-// [2] data-gradient hi, [3] lo (N = in, K = out); un-swizzled K-major: word (k/4)*4N + 4n + k%4
+// images per hidden GEMM layer l = 1..L-1 (2*UIMG floats each): [0] forward operand, rows n = out unit
+// (hi plane rows 0..63, lo plane rows 64..127), K = in unit; [1] data-gradient operand, rows n = in unit
+// (hi | lo), K = out unit.  Un-swizzled K-major with 128 rows: word (k/4)*512 + 4*row + k%4.
+// One N = 128 MMA chain then yields A*[W_hi | W_lo] (two of the three split products) in one pass.
 __global__ void k_umma_images(const float* __restrict__ wpack, PinnNet net, int ldw, float* __restrict__ img) {
   const int l = blockIdx.y + 1;
   float* base = img + (size_t)(l - 1) * 4 * UIMG;
@@ -40,15 +43,14 @@ __global__ void k_umma_images(const float* __restrict__ wpack, PinnNet net, int 
     const int in = idx / UW, out = idx % UW;
     float hi, lo;
     split_rn(wpack[net.off_w[l] + in * ldw + out], hi, lo);
-    const int f = (in >> 2) * (UW * 4) + out * 4 + (in & 3);
-    const int g = (out >> 2) * (UW * 4) + in * 4 + (out & 3);
+    const int f = (in >> 2) * (2 * UW * 4) + out * 4 + (in & 3);
+    const int g = (out >> 2) * (2 * UW * 4) + in * 4 + (out & 3);
     base[f] = hi;
-    base[UIMG + f] = lo;
+    base[f + UW * 4] = lo;
     base[2 * UIMG + g] = hi;
-    base[3 * UIMG + g] = lo;
+    base[2 * UIMG + g + UW * 4] = lo;
   }
 }
-
 
 // activation jets of a chunk with the activation branch OUTSIDE the unrolled loops (straight-line code,
 // the 16 units of a chunk overlap their MUFU / FMA latencies)
@@ -98,18 +100,27 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
   umma::tmem_st8(taddr + 8, b);
 }
 
-// D[128 x 64] = A * W with A (hi at TC_AHI, lo at TC_ALO) in TMEM, W images (hi, lo) in smem: 24 MMAs,
-// small terms first; ONE thread
-__device__ __forceinline__ void issue_layer_gemm(uint32_t tb, const float* img_hi, const float* img_lo, uint32_t idesc) {
-  const uint64_t dh = umma::smem_desc(umma::smem_addr(img_hi), UW * 16, 128);
-  const uint64_t dl = umma::smem_desc(umma::smem_addr(img_lo), UW * 16, 128);
-  constexpr uint64_t STEP = (2 * UW * 16) >> 4;  // k-step advance of the K-major image in 16-byte units
+// D[128 x 128] = A_lo * [W_hi | W_lo] + A_hi * [W_hi | W_lo]: all four split products in 16 MMAs (N = 128 costs
+// the same as N = 64), the small lo terms first so that the truncating accumulator adds them exactly;
+// A (hi at TC_AHI, lo at TC_ALO) in TMEM, the N-concatenated weight image in smem; ONE thread
+__device__ __forceinline__ void issue_layer_gemm(uint32_t tb, const float* img128) {
+  const uint64_t dB = umma::smem_desc(umma::smem_addr(img128), 2 * UW * 16, 128);
+  constexpr uint64_t STEP = (2 * 2 * UW * 16) >> 4;  // k-step advance (two 16-byte k groups of 128 rows) in 16-byte units
+  const uint32_t i128 = umma::idesc_tf32(128, 2 * UW, 0, 0);
 #pragma unroll
-  for (int j = 0; j < UW / 8; ++j) umma::mma_tf32_ts(tb + TC_D, tb + TC_ALO + 8 * j, dh + j * STEP, idesc, j > 0 ? 1u : 0u);
+  for (int j = 0; j < UW / 8; ++j) umma::mma_tf32_ts(tb + TC_D, tb + TC_ALO + 8 * j, dB + j * STEP, i128, j > 0 ? 1u : 0u);
 #pragma unroll
-  for (int j = 0; j < UW / 8; ++j) umma::mma_tf32_ts(tb + TC_D, tb + TC_AHI + 8 * j, dl + j * STEP, idesc, 1u);
+  for (int j = 0; j < UW / 8; ++j) umma::mma_tf32_ts(tb + TC_D, tb + TC_AHI + 8 * j, dB + j * STEP, i128, 1u);
+}
+
+// a[i] = D[u0 + i] + D[64 + u0 + i]
+__device__ __forceinline__ void load_d16(uint32_t tl, int u0, float (&a)[UCH]) {
+  float b[UCH];
+  umma::tmem_ld16(tl + TC_D + u0, a);
+  umma::tmem_ld16(tl + TC_D + UW + u0, b);
+  umma::tmem_ld_wait();
 #pragma unroll
-  for (int j = 0; j < UW / 8; ++j) umma::mma_tf32_ts(tb + TC_D, tb + TC_AHI + 8 * j, dh + j * STEP, idesc, 1u);
+  for (int i = 0; i < UCH; ++i) a[i] += b[i];
 }
 
 __global__ void __launch_bounds__(128, 2) jet_umma_eval_kernel(PinnLaunch L, const float* __restrict__ img, long long* __restrict__ clk) {
@@ -195,8 +206,7 @@ __global__ void __launch_bounds__(128, 2) jet_umma_eval_kernel(PinnLaunch L, con
           for (int i = 0; i < UCH; ++i)
             a[i] = net.scl * fmaf(h0, __ldg(W0 + u0 + i), fmaf(h1, __ldg(W0 + UW + u0 + i), h2 * __ldg(W0 + 2 * UW + u0 + i)));
         } else {
-          umma::tmem_ld16(tl + TC_D + u0, a);
-          umma::tmem_ld_wait();
+          load_d16(tl, u0, a);
         }
         if (warp == 0) {
           float d1[UCH], d2[UCH], s0[UCH];
@@ -240,7 +250,7 @@ __global__ void __launch_bounds__(128, 2) jet_umma_eval_kernel(PinnLaunch L, con
         __syncthreads();
         umma::fence_after_sync();
         if (tid == 0) {
-          issue_layer_gemm(tb, bimg + (size_t)(l * 2 + 0) * UIMG, bimg + (size_t)(l * 2 + 1) * UIMG, idesc);
+          issue_layer_gemm(tb, bimg + (size_t)(l * 2) * UIMG);
           umma::commit(&bar);
         }
         umma::mbar_wait(&bar, parity);
@@ -309,17 +319,16 @@ __device__ __forceinline__ void stage16(uint8_t* plane_hi, uint8_t* plane_lo, in
   }
 }
 
-// DW[64 x 128] = H^T * [A_hi | A_lo]  (hi*hi | hi*lo)  then  DW[:, 0:64] += H_lo^T * A_hi ; K = 128 rows
+// DW[128 x 128] = [H_hi | H_lo]^T * [A_hi | A_lo] over the K = 128 rows: ONE chain of 16 MMAs gives all split
+// products (rows 0..63 = H_hi units, 64..127 = H_lo units; columns 0..63 = A_hi, 64..127 = A_lo);
+// W-bar[i][j] = DW[i][j] + DW[i][64+j] + DW[64+i][j] (the lo*lo block is not used)
 __device__ __forceinline__ void issue_wgrad(uint32_t tb, const uint8_t* smem) {
-  const uint64_t dHh = umma::smem_desc(umma::smem_addr(smem + SM_STH), 16384, 512, 1);
-  const uint64_t dHl = umma::smem_desc(umma::smem_addr(smem + SM_STH + PLANE), 16384, 512, 1);
+  const uint64_t dH = umma::smem_desc(umma::smem_addr(smem + SM_STH), 16384, 512, 1);
   const uint64_t dA = umma::smem_desc(umma::smem_addr(smem + SM_STA), 16384, 512, 1);
-  const uint32_t i128 = umma::idesc_tf32(64, 128, 1, 1), i64 = umma::idesc_tf32(64, 64, 1, 1);
+  const uint32_t idw = umma::idesc_tf32(128, 128, 1, 1);
   constexpr uint64_t STEP = 1024 >> 4;  // 8 rows = two 512 B atoms
 #pragma unroll
-  for (int j = 0; j < 16; ++j) umma::mma_tf32_ss(tb + TC_DW, dHh + j * STEP, dA + j * STEP, i128, j > 0 ? 1u : 0u);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) umma::mma_tf32_ss(tb + TC_DW, dHl + j * STEP, dA + j * STEP, i64, 1u);
+  for (int j = 0; j < 16; ++j) umma::mma_tf32_ss(tb + TC_DW, dH + j * STEP, dA + j * STEP, idw, j > 0 ? 1u : 0u);
 }
 
 __device__ __forceinline__ void bulk_load_w(uint8_t* smem, const float* src, uint64_t* bar) {
@@ -387,43 +396,51 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
   auto lap = [&](int k) {
     if (prof) { const long long now = clock64(); pc[k] += now - t_mark; t_mark = now; }
   };
-  // flush the weight-gradient tile of GEMM layer g from TMEM into the CTA's accumulators (RN adds)
+  // flush the weight-gradient tile of GEMM layer g from TMEM into the CTA's accumulators (RN adds):
+  // W-bar[i][j] = DW[i][j] + DW[i][64+j] + DW[64+i][j].  Row r of DW sits in TMEM lane r: quadrants 0/1
+  // hold the H_hi rows i, quadrants 2/3 the H_lo rows 64+i, which travel through shared memory
+  // (xs[j][i], the exchange buffer is idle here); the two warps of a quadrant split the columns.
+  float* const xs = reinterpret_cast<float*>(smem + SM_EXCH);  // [64 columns][64 rows]
   auto flush_dw = [&](int g) {
-    const int i = 16 * warp + lane;  // in-unit held by this lane (lanes 0..15 of each quadrant)
-    if (g == Lh) {
-      float a[8], b[8];
-      umma::tmem_ld8(tl + TC_DW, a);
-      umma::tmem_ld8(tl + TC_DW + 64, b);
-      umma::tmem_ld_wait();
-      if (lane < 16 && hsel == 0) gacc[net.off_wl + i] += a[0] + b[0];
-      return;
-    }
-    float* d = (g == 0) ? gacc + net.off_w0 + (i < 3 ? i : 0) * UW : gacc + net.off_w[g] + i * ldw;
-    const bool act_lane = lane < 16 && (g != 0 || i < 3);
-    {
-      const int half = hsel;
-      float a[32], b[32];
-      float4 acc4[8];
-      umma::tmem_ld16(tl + TC_DW + 32 * half, reinterpret_cast<float(&)[16]>(a[0]));
-      umma::tmem_ld16(tl + TC_DW + 32 * half + 16, reinterpret_cast<float(&)[16]>(a[16]));
-      umma::tmem_ld16(tl + TC_DW + 64 + 32 * half, reinterpret_cast<float(&)[16]>(b[0]));
-      umma::tmem_ld16(tl + TC_DW + 64 + 32 * half + 16, reinterpret_cast<float(&)[16]>(b[16]));
-      if (act_lane) {
+    const int r = 32 * warp + lane;  // DW row of this lane
+    const int c0 = 32 * hsel;        // first column handled by this warp
+    const bool rmw = warp < 2 && g != Lh && (g != 0 || r < 3);
+    float* const d = ((g == 0) ? gacc + net.off_w0 + (r < 3 ? r : 0) * UW : gacc + net.off_w[g == Lh ? 1 : g] + (r & 63) * ldw) + c0;
+    float4 acc4[8];
+    if (rmw) {  // issued first: the L2 round trip overlaps the TMEM reads and the exchange
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc4[j] = *reinterpret_cast<const float4*>(d + 32 * half + 4 * j);
-      }
+      for (int j = 0; j < 8; ++j) acc4[j] = *reinterpret_cast<const float4*>(d + 4 * j);
+    }
+    if (warp >= 2) {
+      float a[32];
+      umma::tmem_ld16(tl + TC_DW + c0, reinterpret_cast<float(&)[16]>(a[0]));
+      umma::tmem_ld16(tl + TC_DW + c0 + 16, reinterpret_cast<float(&)[16]>(a[16]));
       umma::tmem_ld_wait();
-      if (act_lane) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) xs[(c0 + j) * 64 + (r - 64)] = a[j];
+    }
+    __syncthreads();
+    if (warp < 2) {
+      float a[32], b[32];
+      umma::tmem_ld16(tl + TC_DW + c0, reinterpret_cast<float(&)[16]>(a[0]));
+      umma::tmem_ld16(tl + TC_DW + c0 + 16, reinterpret_cast<float(&)[16]>(a[16]));
+      umma::tmem_ld16(tl + TC_DW + 64 + c0, reinterpret_cast<float(&)[16]>(b[0]));
+      umma::tmem_ld16(tl + TC_DW + 64 + c0 + 16, reinterpret_cast<float(&)[16]>(b[16]));
+      umma::tmem_ld_wait();
+      if (g == Lh) {
+        if (hsel == 0) gacc[net.off_wl + r] += a[0] + b[0] + xs[r];
+      } else if (rmw) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          acc4[j].x += a[4 * j] + b[4 * j];
-          acc4[j].y += a[4 * j + 1] + b[4 * j + 1];
-          acc4[j].z += a[4 * j + 2] + b[4 * j + 2];
-          acc4[j].w += a[4 * j + 3] + b[4 * j + 3];
-          *reinterpret_cast<float4*>(d + 32 * half + 4 * j) = acc4[j];
+          acc4[j].x += a[4 * j] + b[4 * j] + xs[(c0 + 4 * j) * 64 + r];
+          acc4[j].y += a[4 * j + 1] + b[4 * j + 1] + xs[(c0 + 4 * j + 1) * 64 + r];
+          acc4[j].z += a[4 * j + 2] + b[4 * j + 2] + xs[(c0 + 4 * j + 2) * 64 + r];
+          acc4[j].w += a[4 * j + 3] + b[4 * j + 3] + xs[(c0 + 4 * j + 3) * 64 + r];
+          *reinterpret_cast<float4*>(d + 4 * j) = acc4[j];
         }
       }
     }
+    __syncthreads();  // xs (= the exchange buffer) is reused by the next pass
   };
 
 #pragma unroll 1
@@ -469,8 +486,7 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
           for (int i = 0; i < UCH; ++i)
             a[i] = net.scl * fmaf(h0, __ldg(W0 + u0 + i), fmaf(h1, __ldg(W0 + UW + u0 + i), h2 * __ldg(W0 + 2 * UW + u0 + i)));
         } else {
-          umma::tmem_ld16(tl + TC_D + u0, a);
-          umma::tmem_ld_wait();
+          load_d16(tl, u0, a);
         }
         if (warp == 0) {
           float d1[UCH], d2[UCH], s0[UCH];
@@ -520,7 +536,7 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
         umma::fence_after_sync();
         if (tid == 0) {
           umma::mbar_wait(&barL, parL);
-          issue_layer_gemm(tb, reinterpret_cast<const float*>(smem + SM_WIMG), reinterpret_cast<const float*>(smem + SM_WIMG) + UIMG, idesc);
+          issue_layer_gemm(tb, reinterpret_cast<const float*>(smem + SM_WIMG));
           umma::commit(&barD);
         }
         parL ^= 1;
@@ -578,6 +594,11 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
         // operand of layer l+1 and (b) the adjoint of its pre-activations -> TMEM (dgrad operand of layer l)
         const int act = (l == 0) ? net.act_first : net.act_hidden;
         const float* st_l = stash + ((size_t)(l * UK + warp) * UW) * UTP + lane;
+        float s2[2][UCH];  // this warp's stash of both chunks: the L2 round trip overlaps the data-gradient wait
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+          for (int i = 0; i < UCH; ++i) s2[c2][i] = st_l[((2 * hsel + c2) * UCH + i) * UTP];
         if (l < Lh - 1) {
           umma::mbar_wait(&barD, parD);  // data gradient of layer l+1 (issued in the previous iteration)
           parD ^= 1;
@@ -589,13 +610,12 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
           const int u0 = ch * UCH;
           float s[UCH], yb[UCH], y[UCH], ab[UCH], d3v[UCH];
 #pragma unroll
-          for (int i = 0; i < UCH; ++i) s[i] = st_l[(u0 + i) * UTP];
+          for (int i = 0; i < UCH; ++i) s[i] = (ch == 2 * hsel) ? s2[0][i] : s2[1][i];
           if (l == Lh - 1) {
 #pragma unroll
             for (int i = 0; i < UCH; ++i) yb[i] = e * __ldg(wl + u0 + i);
           } else {
-            umma::tmem_ld16(tl + TC_D + u0, yb);
-            umma::tmem_ld_wait();
+            load_d16(tl, u0, yb);
           }
           if (warp == 0) {
             float d1[UCH], d2[UCH];
@@ -678,7 +698,7 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
         umma::commit(&barW);
         if (l >= 1) {
           umma::mbar_wait(&barL, parL);
-          issue_layer_gemm(tb, reinterpret_cast<const float*>(smem + SM_WIMG), reinterpret_cast<const float*>(smem + SM_WIMG) + UIMG, idesc);
+          issue_layer_gemm(tb, reinterpret_cast<const float*>(smem + SM_WIMG));
           umma::commit(&barD);
         }
       }

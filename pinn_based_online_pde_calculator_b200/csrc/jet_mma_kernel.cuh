@@ -76,6 +76,23 @@ __device__ __forceinline__ void mma_tf32(float& d0, float& d1, float& d2, float&
       : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// bf16 MMA for the two small split terms (lo*hi, hi*lo): one m16n8k16 covers the 16 k of TWO tf32 k-steps at
+// the cost of one tf32 MMA.  The k <-> register-slot assignment inside an MMA is arbitrary as long as A and B
+// agree, so the fragments already loaded for the tf32 steps are reused: register 0/1 (rows g, g+8) pack
+// (k = t, t+4) of the first step, register 2/3 the second step; B register 0/1 likewise.
+__device__ __forceinline__ uint32_t pack_bf16(uint32_t x_lowk, uint32_t x_highk) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(x_highk)), "f"(__uint_as_float(x_lowk)));
+  return r;
+}
+__device__ __forceinline__ void mma_bf16(float& d0, float& d1, float& d2, float& d3, const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+#ifndef PINN_BF16_SMALL
+#define PINN_BF16_SMALL 1
+#endif
 // d += a*b with 3xTF32 compensation
 __device__ __forceinline__ void mma3(float& d0, float& d1, float& d2, float& d3, const uint32_t (&ah)[4],
                                      const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
@@ -129,7 +146,7 @@ struct MmaGeo {
 
 // acc[c][p][2nt+e] += sum_k S[pt(p)][c][kbase+k] * wc[k][n0 + 8nt + 2t'...]  (fragment layout)
 // acc[c][p][2nt+e] += sum_k S[pt(p)][c][kbase+k] * wc[k][n0 + 8nt + 2t + e]  (fragment layout)
-template <class C>
+template <class C, bool BF16_SMALL>
 __device__ __forceinline__ void mma_gemm_chunk(float (&acc)[C::K][2][8], const float* __restrict__ S,
                                                const float* __restrict__ wc, int kbase, const MmaGeo& G) {
   // Two-level accumulation: the TF32 MMAs of KS k-steps accumulate into a partial sum that starts
@@ -140,6 +157,90 @@ __device__ __forceinline__ void mma_gemm_chunk(float (&acc)[C::K][2][8], const f
   constexpr int KS = (C::KC >= 16) ? 2 : 1;
   constexpr int K_ = C::K;
   const int tA = G.t ^ G.swz, tB = tA ^ 4;
+#if PINN_BF16_SMALL
+  if (BF16_SMALL && KS == 2) {
+    // two k-steps per pass: hi*hi on TF32 MMAs (one per k-step), lo*hi and hi*lo on ONE bf16 MMA each
+#pragma unroll 1
+    for (int kk = 0; kk < C::KC; kk += 16) {
+      uint32_t bh[2][4][2], pbh[4][2], pbl[4][2];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const float* bp = wc + (kk + 8 * ks + G.t) * C::WPS + G.n0 + 8 * nt + G.g;
+          uint32_t l0, l1;
+          split_tf32(bp[0], bh[ks][nt][0], l0);
+          split_tf32(bp[4 * C::WPS], bh[ks][nt][1], l1);
+          pbh[nt][ks] = pack_bf16(bh[ks][nt][0], bh[ks][nt][1]);
+          pbl[nt][ks] = pack_bf16(l0, l1);
+        }
+#pragma unroll
+      for (int c0 = 0; c0 < K_; c0 += 2) {
+        float tq[2][4][4];
+        uint32_t pah[2][4], pal[2][4];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) tq[cc][nt][0] = tq[cc][nt][1] = tq[cc][nt][2] = tq[cc][nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t ah[2][4];
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            if (c0 + cc < K_) {
+              const float* sp = S + G.pt0 * C::SP + (c0 + cc) * C::WP + kbase + kk + 8 * ks;
+              uint32_t al[4];
+              split_tf32(sp[tA], ah[cc][0], al[0]);
+              split_tf32(sp[8 * C::SP + tA], ah[cc][1], al[1]);
+              split_tf32(sp[tB], ah[cc][2], al[2]);
+              split_tf32(sp[8 * C::SP + tB], ah[cc][3], al[3]);
+              pah[cc][2 * ks] = pack_bf16(ah[cc][0], ah[cc][2]);      // row g:   (k = t, t+4)
+              pah[cc][2 * ks + 1] = pack_bf16(ah[cc][1], ah[cc][3]);  // row g+8
+              pal[cc][2 * ks] = pack_bf16(al[0], al[2]);
+              pal[cc][2 * ks + 1] = pack_bf16(al[1], al[3]);
+            }
+          }
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            if (c0 + cc < K_) {
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt)
+                mma_tf32(tq[cc][nt][0], tq[cc][nt][1], tq[cc][nt][2], tq[cc][nt][3], ah[cc], bh[ks][nt][0], bh[ks][nt][1]);
+            }
+          }
+        }
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass)
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            if (c0 + cc < K_) {
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt) {
+                if (pass == 0)
+                  mma_bf16(tq[cc][nt][0], tq[cc][nt][1], tq[cc][nt][2], tq[cc][nt][3], pal[cc], pbh[nt][0], pbh[nt][1]);
+                else
+                  mma_bf16(tq[cc][nt][0], tq[cc][nt][1], tq[cc][nt][2], tq[cc][nt][3], pah[cc], pbl[nt][0], pbl[nt][1]);
+              }
+            }
+          }
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          if (c0 + cc < K_) {
+            const int c = c0 + cc;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              acc[c][0][2 * nt] += tq[cc][nt][0];
+              acc[c][0][2 * nt + 1] += tq[cc][nt][1];
+              acc[c][1][2 * nt] += tq[cc][nt][2];
+              acc[c][1][2 * nt + 1] += tq[cc][nt][3];
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
+#endif
 #pragma unroll 1
   for (int kk = 0; kk < C::KC; kk += 8 * KS) {
     uint32_t bh[KS][4][2], bl[KS][4][2];
@@ -434,6 +535,11 @@ __device__ __forceinline__ void mma_wgrad_layer(const float* __restrict__ Hs, co
         for (int m = 0; m < 2; ++m)
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) tq[m][nt][0] = tq[m][nt][1] = tq[m][nt][2] = tq[m][nt][3] = 0.f;
+#if PINN_BF16_SMALL
+        // the two channels of the pair are the two k-steps of ONE bf16 MMA for each small split term
+        uint32_t pah[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}}, pal[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
+        uint32_t pbh[4][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}, {0u, 0u}}, pbl[4][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}, {0u, 0u}};
+#endif
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           if (c0 + cc < C::K) {
@@ -457,6 +563,20 @@ __device__ __forceinline__ void mma_wgrad_layer(const float* __restrict__ Hs, co
               split_tf32(ga[8 * nt], bh[nt][0], bl[nt][0]);
               split_tf32(gb[8 * nt], bh[nt][1], bl[nt][1]);
             }
+#if PINN_BF16_SMALL
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              pah[m][2 * cc] = pack_bf16(ah[m][0], ah[m][2]);
+              pah[m][2 * cc + 1] = pack_bf16(ah[m][1], ah[m][3]);
+              pal[m][2 * cc] = pack_bf16(al[m][0], al[m][2]);
+              pal[m][2 * cc + 1] = pack_bf16(al[m][1], al[m][3]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              pbh[nt][cc] = pack_bf16(bh[nt][0], bh[nt][1]);
+              pbl[nt][cc] = pack_bf16(bl[nt][0], bl[nt][1]);
+            }
+#else
 #pragma unroll
             for (int m = 0; m < 2; ++m)
 #pragma unroll
@@ -465,12 +585,23 @@ __device__ __forceinline__ void mma_wgrad_layer(const float* __restrict__ Hs, co
             for (int m = 0; m < 2; ++m)
 #pragma unroll
               for (int nt = 0; nt < 4; ++nt) mma_tf32(tq[m][nt][0], tq[m][nt][1], tq[m][nt][2], tq[m][nt][3], ah[m], bl[nt][0], bl[nt][1]);
+#endif
 #pragma unroll
             for (int m = 0; m < 2; ++m)
 #pragma unroll
               for (int nt = 0; nt < 4; ++nt) mma_tf32(tq[m][nt][0], tq[m][nt][1], tq[m][nt][2], tq[m][nt][3], ah[m], bh[nt][0], bh[nt][1]);
           }
         }
+#if PINN_BF16_SMALL
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_bf16(tq[m][nt][0], tq[m][nt][1], tq[m][nt][2], tq[m][nt][3], pal[m], pbh[nt][0], pbh[nt][1]);
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_bf16(tq[m][nt][0], tq[m][nt][1], tq[m][nt][2], tq[m][nt][3], pah[m], pbl[nt][0], pbl[nt][1]);
+#endif
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll
@@ -670,7 +801,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
 #pragma unroll 1
         for (int ch = 0; ch < NCH; ++ch) {
           const float* wc = chunk_begin();
-          mma_gemm_chunk<C>(acc, Hs, wc, ch * KC, G);
+          mma_gemm_chunk<C, false>(acc, Hs, wc, ch * KC, G);  // forward: full 3xTF32 (loss / residual precision)
           __syncthreads();
           ++gpos;
         }
@@ -790,7 +921,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) jet_mma_kernel(const __grid_co
 #pragma unroll 1
         for (int ch = 0; ch < NCH; ++ch) {
           const float* wc = chunk_begin();
-          mma_gemm_chunk<C>(acc, Gs, wc, ch * KC, G);
+          mma_gemm_chunk<C, true>(acc, Gs, wc, ch * KC, G);  // data gradient: small split terms on bf16 MMAs
           __syncthreads();
           ++gpos;
         }

@@ -90,6 +90,13 @@ __device__ __forceinline__ void mma_bf16(float& d0, float& d1, float& d2, float&
       : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// packed fp32x2 add (Blackwell FADD2): (a0, a1) += (b0, b1) in one instruction
+__device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) {
+  f32x2_t A = pack2(a0, a1);
+  const f32x2_t B = pack2(b0, b1);
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(A) : "l"(B));
+  unpack2(A, a0, a1);
+}
 #ifndef PINN_BF16_SMALL
 #define PINN_BF16_SMALL 1
 #endif
@@ -229,10 +236,8 @@ __device__ __forceinline__ void mma_gemm_chunk(float (&acc)[C::K][2][8], const f
             const int c = c0 + cc;
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
-              acc[c][0][2 * nt] += tq[cc][nt][0];
-              acc[c][0][2 * nt + 1] += tq[cc][nt][1];
-              acc[c][1][2 * nt] += tq[cc][nt][2];
-              acc[c][1][2 * nt + 1] += tq[cc][nt][3];
+              fadd2(acc[c][0][2 * nt], acc[c][0][2 * nt + 1], tq[cc][nt][0], tq[cc][nt][1]);
+              fadd2(acc[c][1][2 * nt], acc[c][1][2 * nt + 1], tq[cc][nt][2], tq[cc][nt][3]);
             }
           }
         }
@@ -297,10 +302,8 @@ __device__ __forceinline__ void mma_gemm_chunk(float (&acc)[C::K][2][8], const f
           const int c = c0 + cc;
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) {
-            acc[c][0][2 * nt] += tq[cc][nt][0];
-            acc[c][0][2 * nt + 1] += tq[cc][nt][1];
-            acc[c][1][2 * nt] += tq[cc][nt][2];
-            acc[c][1][2 * nt + 1] += tq[cc][nt][3];
+            fadd2(acc[c][0][2 * nt], acc[c][0][2 * nt + 1], tq[cc][nt][0], tq[cc][nt][1]);
+            fadd2(acc[c][1][2 * nt], acc[c][1][2 * nt + 1], tq[cc][nt][2], tq[cc][nt][3]);
           }
         }
       }
@@ -606,8 +609,8 @@ __device__ __forceinline__ void mma_wgrad_layer(const float* __restrict__ Hs, co
         for (int m = 0; m < 2; ++m)
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) {
-            w[m][nt][0] += tq[m][nt][0]; w[m][nt][1] += tq[m][nt][1];
-            w[m][nt][2] += tq[m][nt][2]; w[m][nt][3] += tq[m][nt][3];
+            fadd2(w[m][nt][0], w[m][nt][1], tq[m][nt][0], tq[m][nt][1]);
+            fadd2(w[m][nt][2], w[m][nt][3], tq[m][nt][2], tq[m][nt][3]);
           }
       }
     }

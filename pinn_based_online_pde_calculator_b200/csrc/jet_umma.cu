@@ -294,9 +294,13 @@ __global__ void __launch_bounds__(128, 2) jet_umma_eval_kernel(PinnLaunch L, con
 constexpr int SM_WIMG = 0;                    // current weight images (hi, lo): 2 x 16 KB
 constexpr int SM_STH = 32768;                 // wgrad A operand: layer-input jets H (hi plane, lo plane), 2 x 32 KB
 constexpr int SM_STA = SM_STH + 65536;        // wgrad B operand: pre-activation adjoints (hi plane | lo plane), 2 x 32 KB
-constexpr int SM_EXCH = SM_STA + 65536;       // 8 exchange arrays [UCH][32]
-constexpr int SM_MISC = SM_EXCH + 2 * 8 * UCH * 32 * 4;  // exchange arrays per unit half
-constexpr int SM_TRAIN_BYTES = SM_MISC + (12 * 32 + PINN_MAX_OPS + PINN_MAX_CONSTS) * 4 + 64;
+constexpr int SM_EXCH = SM_STA + 65536;       // exchange arrays [unit group][NEX][UCH][32]
+constexpr int NQ = 2;                         // warps per jet channel (each handles 64 / NQ units)
+constexpr int CPW = (UW / UCH) / NQ;          // 16-unit chunks per warp and pass
+constexpr int NEX = 7;                        // exchange arrays: sigma', sigma'', q_x, q_y, p_x, p_y, ybar_L
+constexpr int UNT = 128 * NQ;                 // threads per CTA
+constexpr int SM_MISC = SM_EXCH + NQ * NEX * UCH * 32 * 4;
+constexpr int SM_TRAIN_BYTES = SM_MISC + ((NQ + 1) * 4 * 32 + PINN_MAX_OPS + PINN_MAX_CONSTS) * 4 + 64;
 constexpr uint32_t TC_DW = 256, TC_TRAIN_COLS = 512;
 constexpr int PLANE = 32768;  // bytes of one staging plane: 2 groups of 32 units x 128 rows x 128 B
 
@@ -337,24 +341,23 @@ __device__ __forceinline__ void bulk_load_w(uint8_t* smem, const float* src, uin
   bulk_g2s(smem + SM_WIMG + UIMG * 4, src + UIMG, UIMG * 4, bar);
 }
 
-__global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, const float* __restrict__ img, int ldw,
+__global__ void __launch_bounds__(UNT, 1) jet_umma_train_kernel(PinnLaunch L, const float* __restrict__ img, int ldw,
                                                                 long long* __restrict__ clk) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const PinnNet& net = L.net;
-  // 8 warps: warp = jet channel (= TMEM lane quadrant, wid % 4), hsel = which half of the units the warp handles
+  // 4 * NQ warps: warp = jet channel (= TMEM lane quadrant, wid % 4), hsel = which group of 64 / NQ units the warp handles
   const int tid = threadIdx.x, wid = tid >> 5, warp = wid & 3, hsel = wid >> 2, lane = tid & 31;
   const int row = 32 * warp + lane;  // MMA row = 32 * channel + point
   const int Lh = net.n_hidden;
-  float* x1 = reinterpret_cast<float*>(smem + SM_EXCH) + hsel * 8 * UCH * 32;
+  float* x1 = reinterpret_cast<float*>(smem + SM_EXCH) + hsel * NEX * UCH * 32;
   float* x2 = x1 + UCH * 32;
   float* qx = x2 + UCH * 32;
   float* qy = qx + UCH * 32;
   float* px = qy + UCH * 32;
   float* py = px + UCH * 32;
-  float* pl = py + UCH * 32;
-  float* yl = pl + UCH * 32;
-  float* us = reinterpret_cast<float*>(smem + SM_MISC);  // [2][4][32] partial dot products of the two unit halves
-  float* ub = us + 8 * 32;                               // [4][32]
+  float* yl = py + UCH * 32;
+  float* us = reinterpret_cast<float*>(smem + SM_MISC);  // [NQ][4][32] partial dot products of the unit groups
+  float* ub = us + NQ * 4 * 32;                          // [4][32]
   int* s_ops = reinterpret_cast<int*>(ub + 4 * 32);
   float* s_consts = reinterpret_cast<float*>(s_ops + PINN_MAX_OPS);
   uint8_t* const Hh = smem + SM_STH;
@@ -364,8 +367,8 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
   __shared__ uint64_t barD, barW, barL;
   __shared__ uint32_t tbase;
 
-  for (int i = tid; i < L.prog.n_ops; i += 256) s_ops[i] = L.prog.ops[i];
-  for (int i = tid; i < PINN_MAX_CONSTS; i += 256) s_consts[i] = L.prog.consts[i];
+  for (int i = tid; i < L.prog.n_ops; i += UNT) s_ops[i] = L.prog.ops[i];
+  for (int i = tid; i < PINN_MAX_CONSTS; i += UNT) s_consts[i] = L.prog.consts[i];
   if (wid == 0) umma::tmem_alloc(&tbase, TC_TRAIN_COLS);
   if (tid == 0) {
     umma::mbar_init(&barD, 1);
@@ -402,36 +405,38 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
   // (xs[j][i], the exchange buffer is idle here); the two warps of a quadrant split the columns.
   float* const xs = reinterpret_cast<float*>(smem + SM_EXCH);  // [64 columns][64 rows]
   auto flush_dw = [&](int g) {
+    constexpr int NC = 64 / NQ;      // columns per warp
     const int r = 32 * warp + lane;  // DW row of this lane
-    const int c0 = 32 * hsel;        // first column handled by this warp
+    const int c0 = NC * hsel;        // first column handled by this warp
     const bool rmw = warp < 2 && g != Lh && (g != 0 || r < 3);
     float* const d = ((g == 0) ? gacc + net.off_w0 + (r < 3 ? r : 0) * UW : gacc + net.off_w[g == Lh ? 1 : g] + (r & 63) * ldw) + c0;
-    float4 acc4[8];
+    float4 acc4[NC / 4];
     if (rmw) {  // issued first: the L2 round trip overlaps the TMEM reads and the exchange
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc4[j] = *reinterpret_cast<const float4*>(d + 4 * j);
+      for (int j = 0; j < NC / 4; ++j) acc4[j] = *reinterpret_cast<const float4*>(d + 4 * j);
     }
     if (warp >= 2) {
-      float a[32];
-      umma::tmem_ld16(tl + TC_DW + c0, reinterpret_cast<float(&)[16]>(a[0]));
-      umma::tmem_ld16(tl + TC_DW + c0 + 16, reinterpret_cast<float(&)[16]>(a[16]));
+      float a[NC];
+#pragma unroll
+      for (int q = 0; q < NC / 16; ++q) umma::tmem_ld16(tl + TC_DW + c0 + 16 * q, reinterpret_cast<float(&)[16]>(a[16 * q]));
       umma::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) xs[(c0 + j) * 64 + (r - 64)] = a[j];
+      for (int j = 0; j < NC; ++j) xs[(c0 + j) * 64 + (r - 64)] = a[j];
     }
     __syncthreads();
     if (warp < 2) {
-      float a[32], b[32];
-      umma::tmem_ld16(tl + TC_DW + c0, reinterpret_cast<float(&)[16]>(a[0]));
-      umma::tmem_ld16(tl + TC_DW + c0 + 16, reinterpret_cast<float(&)[16]>(a[16]));
-      umma::tmem_ld16(tl + TC_DW + 64 + c0, reinterpret_cast<float(&)[16]>(b[0]));
-      umma::tmem_ld16(tl + TC_DW + 64 + c0 + 16, reinterpret_cast<float(&)[16]>(b[16]));
+      float a[NC], b[NC];
+#pragma unroll
+      for (int q = 0; q < NC / 16; ++q) {
+        umma::tmem_ld16(tl + TC_DW + c0 + 16 * q, reinterpret_cast<float(&)[16]>(a[16 * q]));
+        umma::tmem_ld16(tl + TC_DW + 64 + c0 + 16 * q, reinterpret_cast<float(&)[16]>(b[16 * q]));
+      }
       umma::tmem_ld_wait();
       if (g == Lh) {
         if (hsel == 0) gacc[net.off_wl + r] += a[0] + b[0] + xs[r];
       } else if (rmw) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < NC / 4; ++j) {
           acc4[j].x += a[4 * j] + b[4 * j] + xs[(c0 + 4 * j) * 64 + r];
           acc4[j].y += a[4 * j + 1] + b[4 * j + 1] + xs[(c0 + 4 * j + 1) * 64 + r];
           acc4[j].z += a[4 * j + 2] + b[4 * j + 2] + xs[(c0 + 4 * j + 2) * 64 + r];
@@ -478,7 +483,7 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
       const bool last = (l == Lh - 1);
       float* st_l = stash + ((size_t)(l * UK + warp) * UW) * UTP + lane;
 #pragma unroll 1
-      for (int ch = 2 * hsel; ch < 2 * hsel + 2; ++ch) {
+      for (int ch = CPW * hsel; ch < CPW * (hsel + 1); ++ch) {
         const int u0 = ch * UCH;
         float a[UCH], y[UCH];
         if (l == 0) {
@@ -563,7 +568,12 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
       float u[UK][1], f[1], df[UK][1];
       const float* auxp[1] = {L.aux ? (L.aux + gp * L.n_aux) : nullptr};
 #pragma unroll
-      for (int c = 0; c < UK; ++c) u[c][0] = us[c * 32 + lane] + us[(4 + c) * 32 + lane];
+      for (int c = 0; c < UK; ++c) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) t += us[(q * 4 + c) * 32 + lane];
+        u[c][0] = t;
+      }
       vm_run<UK, 1>(s_ops, L.prog.n_ops, s_consts, z, auxp, u, f, df);
       const float sc = valid ? __ldg(L.seg_scale + slot) : 0.f;
 #pragma unroll
@@ -582,7 +592,7 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
 #pragma unroll
       for (int i = 0; i < UCH; ++i) v[i] = 0.f;
 #pragma unroll 1
-      for (int ch = 2 * hsel; ch < 2 * hsel + 2; ++ch) {
+      for (int ch = CPW * hsel; ch < CPW * (hsel + 1); ++ch) {
         v[0] = (ch == 0) ? e : 0.f;
         stage16(Ah, Al, row, ch * UCH, v);
       }
@@ -594,11 +604,11 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
         // operand of layer l+1 and (b) the adjoint of its pre-activations -> TMEM (dgrad operand of layer l)
         const int act = (l == 0) ? net.act_first : net.act_hidden;
         const float* st_l = stash + ((size_t)(l * UK + warp) * UW) * UTP + lane;
-        float s2[2][UCH];  // this warp's stash of both chunks: the L2 round trip overlaps the data-gradient wait
+        float s2[CPW][UCH];  // this warp's stash of its chunks: the L2 round trip overlaps the data-gradient wait
 #pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2)
+        for (int c2 = 0; c2 < CPW; ++c2)
 #pragma unroll
-          for (int i = 0; i < UCH; ++i) s2[c2][i] = st_l[((2 * hsel + c2) * UCH + i) * UTP];
+          for (int i = 0; i < UCH; ++i) s2[c2][i] = st_l[((CPW * hsel + c2) * UCH + i) * UTP];
         if (l < Lh - 1) {
           umma::mbar_wait(&barD, parD);  // data gradient of layer l+1 (issued in the previous iteration)
           parD ^= 1;
@@ -606,19 +616,23 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
           if (tid == 0 && l >= 1) bulk_load_w(smem, img + (size_t)(l - 1) * 4 * UIMG + 2 * UIMG, &barL);  // dgrad image of layer l
         }
 #pragma unroll 1
-        for (int ch = 2 * hsel; ch < 2 * hsel + 2; ++ch) {
+        for (int ch = CPW * hsel; ch < CPW * (hsel + 1); ++ch) {
           const int u0 = ch * UCH;
           float s[UCH], yb[UCH], y[UCH], ab[UCH], d3v[UCH];
 #pragma unroll
-          for (int i = 0; i < UCH; ++i) s[i] = (ch == 2 * hsel) ? s2[0][i] : s2[1][i];
+          for (int i = 0; i < UCH; ++i) s[i] = (CPW == 1 || ch == CPW * hsel) ? s2[0][i] : s2[CPW - 1][i];
           if (l == Lh - 1) {
 #pragma unroll
             for (int i = 0; i < UCH; ++i) yb[i] = e * __ldg(wl + u0 + i);
           } else {
             load_d16(tl, u0, yb);
           }
+          float aL[UCH];  // value channel only: the second-order channel's pre-activations (a_L * ybar_L term)
           if (warp == 0) {
             float d1[UCH], d2[UCH];
+            const float* st_3 = stash + ((size_t)(l * UK + 3) * UW) * UTP + lane;
+#pragma unroll
+            for (int i = 0; i < UCH; ++i) aL[i] = st_3[(u0 + i) * UTP];
             act_bwd16(act, s, y, d1, d2, d3v);
 #pragma unroll
             for (int i = 0; i < UCH; ++i) {
@@ -635,18 +649,16 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < UCH; ++i) {
-              yl[i * 32 + lane] = yb[i];
-              pl[i * 32 + lane] = s[i] * yb[i];
-            }
+            for (int i = 0; i < UCH; ++i) yl[i * 32 + lane] = yb[i];
           }
           half_sync();
           if (warp == 0) {
 #pragma unroll
             for (int i = 0; i < UCH; ++i) {
               const int o = i * 32 + lane;
-              const float P = px[o] + py[o] + pl[o];
-              const float R = (qx[o] + qy[o]) * yl[o];
+              const float yL = yl[o];
+              const float P = fmaf(aL[i], yL, px[o] + py[o]);
+              const float R = (qx[o] + qy[o]) * yL;
               ab[i] = fmaf(d3v[i], R, fmaf(x2[o], P, x1[o] * yb[i]));
             }
           } else if (warp < 3) {
@@ -681,7 +693,7 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
 #pragma unroll
         for (int i = 0; i < UCH; ++i) v[i] = 0.f;
 #pragma unroll 1
-        for (int ch = 2 * hsel; ch < 2 * hsel + 2; ++ch) {
+        for (int ch = CPW * hsel; ch < CPW * (hsel + 1); ++ch) {
           if (ch == 0) { v[0] = net.scl * h0; v[1] = net.scl * h1; v[2] = net.scl * h2; }
           else { v[0] = v[1] = v[2] = 0.f; }
           stage16(Hh, Hl, row, ch * UCH, v);
@@ -723,7 +735,7 @@ __global__ void __launch_bounds__(256, 1) jet_umma_train_kernel(PinnLaunch L, co
       // ---- C(l): the adjoints of layer l (already split, in TMEM) become the staged operand of wgrad(l)
       __syncthreads();  // the bias-gradient readers of the old operand are done
 #pragma unroll 1
-      for (int ch = 2 * hsel; ch < 2 * hsel + 2; ++ch) {
+      for (int ch = CPW * hsel; ch < CPW * (hsel + 1); ++ch) {
         const int u0 = ch * UCH;
         float hi[UCH], lo[UCH];
         umma::tmem_ld16(tl + TC_AHI + u0, hi);
@@ -782,7 +794,7 @@ cudaError_t jet_umma_build_images(const float* wpack, const PinnNet& net, int ld
 cudaError_t jet_umma_train_launch(const PinnLaunch& L, const float* images, int ldw, int grid, cudaStream_t st, long long* clk) {
   cudaError_t e = cudaFuncSetAttribute(jet_umma_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TRAIN_BYTES);
   if (e != cudaSuccess) return e;
-  jet_umma_train_kernel<<<grid, 256, SM_TRAIN_BYTES, st>>>(L, images, ldw, clk);
+  jet_umma_train_kernel<<<grid, UNT, SM_TRAIN_BYTES, st>>>(L, images, ldw, clk);
   return cudaGetLastError();
 }
 

@@ -32,7 +32,7 @@ struct MmaCfg {
   static constexpr int ROWS = TP / 2;           // thread rows (mw, g)
   static constexpr int SP = K * WP + 8;         // smem point stride == 8 (mod 32)
   static constexpr int WPS = WP + 8;            // weight row stride (smem chunk and pack)
-  static constexpr int KC = (NT <= 64) ? 16 : (K >= 6) ? (WP <= 64 ? 16 : 8) : (WP <= 64 ? (K <= 4 ? 64 : 32) : 16);  // W = 256, K <= 5: 16 fits (199 KB)
+  static constexpr int KC = (NT <= 64) ? 16 : (K >= 6) ? (WP <= 64 ? 16 : 8) : (WP <= 64 ? (K <= 4 ? 64 : 32) : (WP <= 128 && K <= 4) ? 32 : 16);  // W = 128, K <= 4: 32 keeps 2 CTAs/SM (101 KB); W = 256, K <= 5: 16 fits (199 KB)
   static constexpr int NCH = WP / KC;
   static constexpr uint32_t CHUNK_BYTES = KC * WPS * 4;
   static constexpr int SCR_HALF = ((5 * ROWS * WP + ROWS + 1) / 2 + 3) / 4 * 4;  // final-fold scratch / 2

@@ -23,7 +23,7 @@ for x in allc:
 L.append("\nRoofline of the tensor-core kernel = measured `mma.sync` TF32 rate (277 TFLOP/s) x 3/7 (forward GEMM: three TF32 MMAs per product; each backward GEMM: one TF32 + two half-cost bf16 MMAs); of the fp32 kernel = measured FFMA rate (71.7 TFLOP/s).")
 L.append("`algorithmic TFLOP/s` uses the SURVEY's count 2K(2M1+M2) with one channel per derivative; the kernels execute K_exec/K of it for Laplacian-type operators (C2, C4, R0: 4/5; C5: 5/6).")
 L.append("C1/R0 are launch-latency bound (1k / 5.2k points).  C3 pads W=50 to 64 (39 % extra MACs not counted as algorithmic work).\n")
-L.append("## Weak scaling (each GPU holds the full per-GPU workload; one fused NCCL allreduce per step)\n")
+L.append("## Weak scaling (each GPU holds the full per-GPU workload; one fused NCCL allreduce per step; measured on the v9 build, 6.22 ms/step on 1 GPU)\n")
 L.append("| config | GPUs | points/s | e2e points/s | ms/step | speed-up vs 1 GPU |")
 L.append("|---|---|---|---|---|---|")
 v1 = sc[0]["value"]

@@ -215,33 +215,26 @@ static int build_layout(pinn_engine* h, int ldw) {
   return 0;
 }
 
-extern "C" int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engine_t** out) {
-  if (!spec || !out) return fail("null argument");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    return fail("no CUDA device: the B200 engine has no CPU fallback");
-  if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
-  CK(cudaSetDevice(device));
-  if (spec->n_ops <= 0 || spec->n_ops > PINN_MAX_OPS) return fail("residual program length %d not in 1..%d", spec->n_ops, PINN_MAX_OPS);
-  if (spec->n_consts < 0 || spec->n_consts > PINN_MAX_CONSTS) return fail("too many constants");
-  if (spec->n_bc < 0 || spec->n_bc > PINN_MAX_SEG - 1) return fail("n_bc must be 0..%d", PINN_MAX_SEG - 1);
-  pinn_engine* h = new pinn_engine();
+extern "C" void pinn_engine_destroy(pinn_engine_t* h);
+
+// everything after the handle exists; on failure the caller destroys the partially built handle
+static int create_impl(pinn_engine* h, const pinn_spec_t* spec, int device) {
   h->device = device;
   h->spec = *spec;
   h->ops.assign(spec->ops, spec->ops + spec->n_ops);
   h->consts.assign(spec->consts, spec->consts + spec->n_consts);
   h->spec.ops = h->ops.data();
   h->spec.consts = h->consts.data();
-  if (spec->n_aux_ops < 0 || spec->n_aux_ops > PINN_MAX_OPS) { delete h; return fail("aux program too long"); }
-  if (spec->n_aux_user < 0 || spec->n_aux_user > spec->n_aux_col) { delete h; return fail("n_aux_user out of range"); }
-  if (spec->n_aux_ops == 0 && spec->n_aux_user != spec->n_aux_col) { delete h; return fail("hoisted columns need an aux program"); }
+  if (spec->n_aux_ops < 0 || spec->n_aux_ops > PINN_MAX_OPS) { return fail("aux program too long"); }
+  if (spec->n_aux_user < 0 || spec->n_aux_user > spec->n_aux_col) { return fail("n_aux_user out of range"); }
+  if (spec->n_aux_ops == 0 && spec->n_aux_user != spec->n_aux_col) { return fail("hoisted columns need an aux program"); }
   if (spec->n_aux_ops > 0) h->aux_ops.assign(spec->aux_ops, spec->aux_ops + spec->n_aux_ops);
   h->spec.aux_ops = h->aux_ops.data();
   {
     // kernel family: PINN_B200_KERNEL = simt | mma | auto (default: the 3xTF32 tensor-core kernel when
     // it is instantiated for this width and jet structure, else the fp32 SIMT kernel)
     const int wp = pad_width(spec->width);
-    if (wp < 0) { delete h; return fail("width %d > 256 not supported", spec->width); }
+    if (wp < 0) { return fail("width %d > 256 not supported", spec->width); }
     const char* env = getenv("PINN_B200_KERNEL");
     const std::string want = env ? env : "auto";
     const JetKernelInfo *c1 = pinn_find_kernel(wp, spec->n1, spec->n2, spec->mix, 1), *b1 = pinn_find_kernel(wp, 0, 0, 0, 1);
@@ -251,15 +244,14 @@ extern "C" int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engi
     else if (c1 && b1) { h->kcol = c1; h->kbc = b1; }
     else { h->kcol = c0; h->kbc = b0; }
     if (!h->kcol || !h->kbc) {
-      delete h;
       return fail("no %s kernel instantiation for WP=%d jets (n1=%d,n2=%d,mix=%d)", want.c_str(), wp, spec->n1, spec->n2, spec->mix);
     }
   }
-  if (build_layout(h, h->kcol->ldw)) { delete h; return 1; }
+  if (build_layout(h, h->kcol->ldw)) { return 1; }
   int occ_col = 1, occ_bc = 1;
   cudaError_t e = h->kcol->prepare(&occ_col);
   if (e == cudaSuccess) e = h->kbc->prepare(&occ_bc);
-  if (e != cudaSuccess) { delete h; return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;
@@ -270,7 +262,6 @@ extern "C" int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engi
     const char* kenv = getenv("PINN_B200_KERNEL");
     if (kenv && !strcmp(kenv, "umma")) {
       if (!jet_umma_supported(h->net, h->kcol->k, spec->n1, spec->n2, spec->mix)) {
-        delete h;
         return fail("PINN_B200_KERNEL=umma: the tcgen05 family supports padded width 64 with jets (value, 2 first, combined second order), 2..4 hidden layers");
       }
       h->use_umma = true;
@@ -328,6 +319,26 @@ extern "C" int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engi
     CK(cudaMemset(h->d_uclk, 0, sizeof(long long) * 8));
   }
   if (!getenv("PINN_B200_NO_L2_WINDOW")) apply_l2_policy(h);
+  return 0;
+}
+
+extern "C" int pinn_engine_create(const pinn_spec_t* spec, int device, pinn_engine_t** out) {
+  if (!spec || !out) return fail("null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: the B200 engine has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
+  CK(cudaSetDevice(device));
+  if (spec->n_ops <= 0 || spec->n_ops > PINN_MAX_OPS) return fail("residual program length %d not in 1..%d", spec->n_ops, PINN_MAX_OPS);
+  if (spec->n_consts < 0 || spec->n_consts > PINN_MAX_CONSTS) return fail("too many constants");
+  if (spec->n_bc < 0 || spec->n_bc > PINN_MAX_SEG - 1) return fail("n_bc must be 0..%d", PINN_MAX_SEG - 1);
+  pinn_engine* h = new pinn_engine();
+  if (create_impl(h, spec, device)) {
+    const std::string err = g_err;  // destroy may touch the error slot
+    pinn_engine_destroy(h);
+    g_err = err;
+    return 1;
+  }
   *out = h;
   return 0;
 }

@@ -87,6 +87,10 @@ struct pinn_engine {
   float *stg_col = nullptr, *stg_bc = nullptr, *stg_ubc = nullptr;
   size_t stg_col_cap = 0, stg_bc_cap = 0;
   bool staged = false;
+  // the boundary kernel runs on a forked stream next to the collocation kernel (own accumulator / stash rows)
+  cudaStream_t bc_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool fork_bc = false;  // decided in set_points: the collocation grid leaves CTA slots free
   long long umma_clk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool use_umma = false;         // PINN_B200_KERNEL=umma and the configuration is supported: collocation term on tcgen05
   float* d_uimg = nullptr;       // pre-split operand images of the tcgen05 family
@@ -304,6 +308,9 @@ static int create_impl(pinn_engine* h, const pinn_spec_t* spec, int device) {
   CK(cudaMalloc(&h->d_stash, sizeof(float) * (h->stash_floats + h->gacc_floats)));
   h->d_gacc = h->d_stash + h->stash_floats;
   CK(cudaMalloc(&h->d_loss_part, sizeof(double) * (size_t)h->grid_max * h->n_slots));
+  CK(cudaStreamCreateWithFlags(&h->bc_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CK(cudaMalloc(&h->d_seg_scale, sizeof(float) * PINN_MAX_SEG));
   CK(cudaMalloc(&h->d_lr, sizeof(float)));
   CK(cudaMalloc(&h->d_adam_c, sizeof(float) * 2));
@@ -363,6 +370,9 @@ extern "C" void pinn_engine_destroy(pinn_engine_t* h) {
     if (b) cudaFree(b);
   free_set(h->col);
   free_set(h->bc);
+  if (h->bc_stream) cudaStreamDestroy(h->bc_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->stg_col) cudaFree(h->stg_col);
   if (h->stg_bc) cudaFree(h->stg_bc);
   if (h->stg_ubc) cudaFree(h->stg_ubc);
@@ -591,6 +601,17 @@ extern "C" int pinn_engine_set_points(pinn_engine_t* h, const float* x_col, int6
     }
     L.n_seg = ns; L.n_tiles = tiles;
     h->grid_bc = std::min(tiles, h->grid_max_bc);
+    // When the collocation kernel does not fill the machine (small problems, e.g. the reference's 5,200
+    // points) the boundary kernel runs next to it on a forked stream and its CTAs own the rows after the
+    // collocation CTAs'.  Otherwise the two persistent grids would only fight for the same CTA slots: they
+    // run back to back and share rows (fewer rows to zero and reduce).
+    h->fork_bc = tiles > 0 && h->grid_col + h->grid_bc <= h->grid_max;  // both grids fit next to each other (rows and CTA slots)
+    if (h->fork_bc) {
+      const size_t stash_row = (size_t)h->spec.n_hidden * std::max(h->kcol->stash_floats_per_layer, h->kbc->stash_floats_per_layer);
+      L.stash = h->d_stash + (size_t)h->grid_col * stash_row;
+      L.gacc = h->d_gacc + (size_t)h->grid_col * h->net.pg;
+      L.loss_part = h->d_loss_part + (size_t)h->grid_col * h->n_slots;
+    }
   }
   if (!on_device) CK(cudaStreamSynchronize(h->stream));  // host buffers may be reused by the caller
   h->points_set = true;
@@ -687,18 +708,27 @@ static int enqueue_eval(pinn_engine* h, const float* params_dev, int tick) {
   if (!h->points_set) return fail("set_points has not been called");
   cudaStream_t st = h->stream;
   const int P = h->fmap.n_params;
-  const int nb = std::max(h->grid_col, h->grid_bc);
+  const bool has_bc = h->Lbc.n_tiles > 0, fork = has_bc && h->fork_bc;
+  const int nb = fork ? h->grid_col + h->grid_bc : std::max(h->grid_col, h->grid_bc);
   k_pack<<<(P + 255) / 256, 256, 0, st>>>(h->fmap, params_dev ? params_dev : h->d_params, h->d_wpack);
   CK(cudaGetLastError());
   CK(cudaMemsetAsync(h->d_gacc, 0, sizeof(float) * (size_t)nb * h->net.pg, st));
   CK(cudaMemsetAsync(h->d_loss_part, 0, sizeof(double) * (size_t)nb * h->n_slots, st));
-  if (h->Lbc.n_tiles > 0) CK(h->kbc->launch(h->Lbc, true, h->grid_bc, st));
+  if (fork) {
+    CK(cudaEventRecord(h->ev_fork, st));
+    CK(cudaStreamWaitEvent(h->bc_stream, h->ev_fork, 0));
+    CK(h->kbc->launch(h->Lbc, true, h->grid_bc, h->bc_stream));
+    CK(cudaEventRecord(h->ev_join, h->bc_stream));
+  } else if (has_bc) {
+    CK(h->kbc->launch(h->Lbc, true, h->grid_bc, st));
+  }
   if (h->use_umma) {
     CK(jet_umma_build_images(h->d_wpack, h->net, h->kcol->ldw, h->d_uimg, st));
     CK(jet_umma_train_launch(h->Lcol, h->d_uimg, h->kcol->ldw, h->grid_col, st, h->d_uclk));
   } else {
     CK(h->kcol->launch(h->Lcol, true, h->grid_col, st));
   }
+  if (fork) CK(cudaStreamWaitEvent(st, h->ev_join, 0));  // join
   k_grad_reduce<<<(P + 127) / 128, 128, 0, st>>>(h->fmap, h->d_gacc, nb, h->net.pg, h->d_fused);
   CK(cudaGetLastError());
   k_loss_reduce<<<1, 32, 0, st>>>(h->d_loss_part, nb, h->n_slots, h->d_fused + P);
@@ -891,7 +921,7 @@ extern "C" int pinn_engine_time_kernels(pinn_engine_t* h, int32_t reps, int64_t 
   if (!h->points_set) return fail("set_points has not been called");
   cudaStream_t st = h->stream;
   const int P = h->fmap.n_params;
-  const int nb = std::max(h->grid_col, h->grid_bc);
+  const int nb = h->fork_bc ? h->grid_col + h->grid_bc : std::max(h->grid_col, h->grid_bc);
   void* flush = nullptr;
   if (flush_bytes > 0) CK(cudaMalloc(&flush, (size_t)flush_bytes));
   k_pack<<<(P + 255) / 256, 256, 0, st>>>(h->fmap, h->d_params, h->d_wpack);

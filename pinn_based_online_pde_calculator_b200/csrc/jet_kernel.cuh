@@ -112,32 +112,6 @@ __device__ __forceinline__ float tanh_bf(float x) {
 // replicated 16x per call site (instruction-cache footprint)
 static __device__ __noinline__ void sincos_ni(float x, float* s, float* c) { sincosf(x, s, c); }
 
-// inline sin/cos for the common range: three-constant Cody-Waite reduction by pi/2 (exact products through
-// FMA) + the single-precision minimax polynomials on [-pi/4, pi/4] (about 1 ulp); 20 straight-line
-// instructions that interleave across the units of a thread.  Huge arguments take the library path.
-__device__ __forceinline__ void sincos_pinn(float x, float* s, float* c) {
-  if (fabsf(x) > 3.0e4f) {
-    sincos_ni(x, s, c);
-    return;
-  }
-  const float k = rintf(x * 0.636619772f);
-  float r = fmaf(k, -1.57079601e+00f, x);
-  r = fmaf(k, -3.13916473e-07f, r);
-  r = fmaf(k, -5.39030253e-15f, r);
-  const int q = __float2int_rn(k);
-  const float r2 = r * r;
-  float sp = fmaf(r2, -1.95152959e-4f, 8.33216087e-3f);
-  sp = fmaf(sp, r2, -1.66666546e-1f);
-  sp = fmaf(sp * r2, r, r);
-  float cp = fmaf(r2, 2.44331571e-5f, -1.38873163e-3f);
-  cp = fmaf(cp, r2, 4.16666457e-2f);
-  cp = fmaf(cp, r2, -0.5f);
-  cp = fmaf(cp, r2, 1.0f);
-  const float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
-  *s = (q & 2) ? -ss : ss;
-  *c = ((q + 1) & 2) ? -cc : cc;
-}
-
 // forward: y = act(a0), d1 = act'(a0), d2 = act''(a0); s0 = value stashed for backward
 __device__ __forceinline__ void act_fwd(int act, float a0, float& y, float& d1, float& d2, float& s0) {
   if (act == PINN_TANH) {
@@ -147,7 +121,7 @@ __device__ __forceinline__ void act_fwd(int act, float a0, float& y, float& d1, 
     s0 = y;
   } else {
     float s, c;
-    sincos_pinn(a0, &s, &c);
+    sincos_ni(a0, &s, &c);
     y = s; d1 = c; d2 = -s; s0 = a0;
   }
 }
@@ -160,7 +134,7 @@ __device__ __forceinline__ void act_bwd(int act, float s0, float& y, float& d1, 
     d3 = d1 * fmaf(6.0f * y, y, -2.0f);
   } else {
     float s, c;
-    sincos_pinn(s0, &s, &c);
+    sincos_ni(s0, &s, &c);
     y = s; d1 = c; d2 = -s; d3 = -c;
   }
 }

@@ -67,7 +67,7 @@ __device__ __forceinline__ void act_fwd16(int act, const float (&a)[UCH], float 
 #pragma unroll
     for (int i = 0; i < UCH; ++i) {
       float sn, cs;
-      sincos_pinn(a[i], &sn, &cs);
+      sincos_ni(a[i], &sn, &cs);
       y[i] = sn; d1[i] = cs; d2[i] = -sn; s0[i] = a[i];
     }
   }
@@ -86,7 +86,7 @@ __device__ __forceinline__ void act_bwd16(int act, const float (&s0)[UCH], float
 #pragma unroll
     for (int i = 0; i < UCH; ++i) {
       float sn, cs;
-      sincos_pinn(s0[i], &sn, &cs);
+      sincos_ni(s0[i], &sn, &cs);
       y[i] = sn; d1[i] = cs; d2[i] = -sn; d3[i] = -cs;
     }
   }

@@ -266,13 +266,14 @@ __global__ void k_lbfgs_push(int n, int slot, float* __restrict__ x, float* __re
                              float* __restrict__ Sh, float* __restrict__ Yh, double* __restrict__ rho,
                              double* __restrict__ out) {
   __shared__ double sh[32];
+  __shared__ int accept;
   float* s = Sh + (size_t)slot * n;
   float* y = Yh + (size_t)slot * n;
+  // pass 1: curvature s.y and |g_new|_inf WITHOUT touching the history (a rejected pair must not
+  // overwrite the oldest live pair when the ring is full)
   double sy = 0.0, mx = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const float si = xt[i] - x[i], yi = gt[i] - g[i];
-    s[i] = si; y[i] = yi;
-    x[i] = xt[i]; g[i] = gt[i];
     sy += (double)si * (double)yi;
     mx = fmax(mx, fabs((double)gt[i]));
   }
@@ -287,7 +288,15 @@ __global__ void k_lbfgs_push(int n, int slot, float* __restrict__ x, float* __re
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sh[w]);
     out[0] = sy;
     out[1] = m;
-    rho[slot] = 1.0 / sy;
+    accept = (sy > 0.0 && isfinite(sy)) ? 1 : 0;
+    if (accept) rho[slot] = 1.0 / sy;
+  }
+  __syncthreads();
+  // pass 2: store the pair if accepted; the iterate always moves
+  const bool acc = accept != 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (acc) { s[i] = xt[i] - x[i]; y[i] = gt[i] - g[i]; }
+    x[i] = xt[i]; g[i] = gt[i];
   }
 }
 

@@ -17,6 +17,7 @@
 #include "sampler_kernels.cuh"
 #include "jet_launch.h"
 #include "jet_umma.h"
+#include "jet_tc.h"
 #include "pinn_common.h"
 
 static thread_local std::string g_err;
@@ -93,7 +94,8 @@ struct pinn_engine {
   bool fork_bc = false;  // decided in set_points: the collocation grid leaves CTA slots free
   long long umma_clk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool use_umma = false;         // PINN_B200_KERNEL=umma and the configuration is supported: collocation term on tcgen05
-  float* d_uimg = nullptr;       // pre-split operand images of the tcgen05 family
+  void* d_wimg = nullptr;        // bf16x3 weight-image stream of the tcgen05 production family (kind 3)
+  float* d_uimg = nullptr;       // pre-split operand images of the experimental tcgen05 family C
   long long* d_uclk = nullptr;  // phase clocks of the last tcgen05 launch (experimental family)
   pinn_spec_t spec{};
   std::vector<int32_t> ops, aux_ops;
@@ -142,12 +144,17 @@ struct pinn_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
 
+  // reusable scratch of pinn_engine_eval (grown on demand, freed with the handle)
+  std::vector<std::pair<void*, size_t>> eval_bufs;
+  size_t l2_carve = 0;  // this engine's share of the device-wide persisting-L2 carve-out
+
   // lbfgs buffers
   float *d_x = nullptr, *d_g = nullptr, *d_d = nullptr, *d_xt = nullptr, *d_S = nullptr, *d_Y = nullptr;
   double *d_rho = nullptr, *d_alpha = nullptr, *d_scal = nullptr;
 };
 
 static void apply_l2_policy(pinn_engine* h);
+static void l2_release(pinn_engine* h);
 
 static int pad_width(int w) {
   if (w <= 32) return 32;
@@ -235,16 +242,21 @@ static int create_impl(pinn_engine* h, const pinn_spec_t* spec, int device) {
   if (spec->n_aux_ops > 0) h->aux_ops.assign(spec->aux_ops, spec->aux_ops + spec->n_aux_ops);
   h->spec.aux_ops = h->aux_ops.data();
   {
-    // kernel family: PINN_B200_KERNEL = simt | mma | auto (default: the 3xTF32 tensor-core kernel when
-    // it is instantiated for this width and jet structure, else the fp32 SIMT kernel)
+    // kernel family: PINN_B200_KERNEL = simt | mma | tc | auto.  auto: the tcgen05 bf16x3 kernel (kind 3) for the
+    // collocation term when it is instantiated for this width and jet structure (padded widths 128 / 256, at
+    // least two hidden layers), else the 3xTF32 mma.sync kernel, else the fp32 SIMT kernel.  The boundary
+    // term (value-only jets, ~1 % of the points) stays on the mma.sync / SIMT kernel.
     const int wp = pad_width(spec->width);
     if (wp < 0) { return fail("width %d > 256 not supported", spec->width); }
     const char* env = getenv("PINN_B200_KERNEL");
     const std::string want = env ? env : "auto";
     const JetKernelInfo *c1 = pinn_find_kernel(wp, spec->n1, spec->n2, spec->mix, 1), *b1 = pinn_find_kernel(wp, 0, 0, 0, 1);
     const JetKernelInfo *c0 = pinn_find_kernel(wp, spec->n1, spec->n2, spec->mix, 0), *b0 = pinn_find_kernel(wp, 0, 0, 0, 0);
-    if (want == "mma") { h->kcol = c1; h->kbc = b1; }
+    const JetKernelInfo* c3 = (spec->n_hidden >= 2) ? pinn_find_kernel(wp, spec->n1, spec->n2, spec->mix, 3) : nullptr;
+    if (want == "tc") { h->kcol = c3; h->kbc = b1; }
+    else if (want == "mma" || want == "umma") { h->kcol = c1; h->kbc = b1; }
     else if (want == "simt") { h->kcol = c0; h->kbc = b0; }
+    else if (c3 && b1) { h->kcol = c3; h->kbc = b1; }
     else if (c1 && b1) { h->kcol = c1; h->kbc = b1; }
     else { h->kcol = c0; h->kbc = b0; }
     if (!h->kcol || !h->kbc) {
@@ -320,6 +332,7 @@ static int create_impl(pinn_engine* h, const pinn_spec_t* spec, int device) {
   CK(cudaMalloc(&h->d_meta, sizeof(LossMeta)));
   CK(cudaMemset(h->d_ring_pos, 0, sizeof(int)));
   CK(cudaMemset(h->d_adam_count, 0, sizeof(int)));
+  if (h->kcol->kind == 3) CK(cudaMalloc(&h->d_wimg, jet_tc_image_bytes(h->net) * PINN_TC_IMAGE_COPIES));
   if (h->use_umma) {
     CK(cudaMalloc(&h->d_uimg, sizeof(float) * jet_umma_image_floats(h->net)));
     CK(cudaMalloc(&h->d_uclk, sizeof(long long) * 8));
@@ -365,9 +378,12 @@ extern "C" void pinn_engine_destroy(pinn_engine_t* h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void* bufs[] = {h->d_params, h->d_fused, h->d_m, h->d_v, h->d_wpack, h->d_stash, h->d_seg_scale,
                   h->d_lr, h->d_adam_c, h->d_loss_part, h->d_ring, h->d_ring_pos, h->d_adam_count, h->d_meta,
-                  h->d_x, h->d_g, h->d_d, h->d_xt, h->d_S, h->d_Y, h->d_rho, h->d_alpha, h->d_scal, h->d_uimg, h->d_uclk};
+                  h->d_x, h->d_g, h->d_d, h->d_xt, h->d_S, h->d_Y, h->d_rho, h->d_alpha, h->d_scal, h->d_uimg, h->d_uclk, h->d_wimg};
   for (void* b : bufs)
     if (b) cudaFree(b);
+  for (auto& b : h->eval_bufs)
+    if (b.first) cudaFree(b.first);
+  l2_release(h);
   free_set(h->col);
   free_set(h->bc);
   if (h->bc_stream) cudaStreamDestroy(h->bc_stream);
@@ -388,13 +404,39 @@ extern "C" void pinn_engine_destroy(pinn_engine_t* h) {
 // Keep the per-CTA stash (rewritten every tile, read back once) resident in L2: a persisting
 // access-policy window on the engine stream, so dirty stash lines are overwritten in place
 // instead of being evicted to HBM.
+// cudaLimitPersistingL2CacheSize is DEVICE-global: several live engines (stage-2 model next to stage 1,
+// concurrent sessions) must not shrink each other's carve-out, so the limit is the maximum over the
+// live engines of the device.
+#include <mutex>
+static std::mutex g_l2_mu;
+static std::vector<std::pair<int, pinn_engine*>> g_l2_live;  // (device, engine) with l2_carve > 0
+static void l2_set_limit_locked(int device) {
+  size_t want = 0;
+  for (auto& e : g_l2_live)
+    if (e.first == device) want = std::max(want, e.second->l2_carve);
+  if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();
+}
+static void l2_release(pinn_engine* h) {
+  std::lock_guard<std::mutex> lk(g_l2_mu);
+  bool had = false;
+  for (size_t i = 0; i < g_l2_live.size(); ++i)
+    if (g_l2_live[i].second == h) { g_l2_live.erase(g_l2_live.begin() + i); had = true; break; }
+  if (had) l2_set_limit_locked(h->device);
+}
 static void apply_l2_policy(pinn_engine* h) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return;
   if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
   const size_t bytes = (h->stash_floats + h->gacc_floats) * sizeof(float);
   const size_t carve = std::min<size_t>(bytes, (size_t)prop.persistingL2CacheMaxSize);
-  if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
+  {
+    std::lock_guard<std::mutex> lk(g_l2_mu);
+    h->l2_carve = carve;
+    bool present = false;
+    for (auto& e : g_l2_live) present |= (e.second == h);
+    if (!present) g_l2_live.emplace_back(h->device, h);
+    l2_set_limit_locked(h->device);
+  }
   cudaStreamAttrValue attr;
   memset(&attr, 0, sizeof attr);
   attr.accessPolicyWindow.base_ptr = h->d_stash;
@@ -488,7 +530,21 @@ static void fill_launch(pinn_engine* h, PinnLaunch& L, const JetKernelInfo* k, c
   L.loss_part = h->d_loss_part;
   L.n_slots = h->n_slots;
   L.prog = prog;
+  L.wimg = h->d_wimg;
+  L.wimg_copy_bytes = (long long)jet_tc_image_bytes(h->net);
+  L.wimg_copies = PINN_TC_IMAGE_COPIES;
+  L.ldw = h->kcol->ldw;
   (void)k;
+}
+
+// everything the fused kernels read besides the points: the padded fp32 pack and, for the tcgen05
+// family, the bf16x3 weight-image stream
+static int enqueue_pack(pinn_engine* h, const float* params_dev, cudaStream_t st) {
+  const int P = h->fmap.n_params;
+  k_pack<<<(P + 255) / 256, 256, 0, st>>>(h->fmap, params_dev ? params_dev : h->d_params, h->d_wpack);
+  CK(cudaGetLastError());
+  if (h->kcol->kind == 3) CK(jet_tc_build_images(h->d_wpack, h->net, h->kcol->ldw, h->d_wimg, PINN_TC_IMAGE_COPIES, st));
+  return 0;
 }
 
 extern "C" int pinn_engine_set_points(pinn_engine_t* h, const float* x_col, int64_t n_col, const float* aux_col,
@@ -499,6 +555,8 @@ extern "C" int pinn_engine_set_points(pinn_engine_t* h, const float* x_col, int6
   if (n_bc != h->spec.n_bc) return fail("n_bc %d != spec.n_bc %d", n_bc, h->spec.n_bc);
   if (n_col <= 0) return fail("n_col must be > 0");
   const int d = h->spec.d_in, K = h->kcol->k;
+  // the captured Adam graph bakes these six pointers by value: any change invalidates it
+  const float* const before[6] = {h->col.coords, h->col.aux, h->col.base, h->bc.coords, h->bc.aux, h->bc.base};
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   // collocation set
   const int na = h->spec.n_aux_col, na_user = h->spec.n_aux_user;
@@ -615,9 +673,15 @@ extern "C" int pinn_engine_set_points(pinn_engine_t* h, const float* x_col, int6
   }
   if (!on_device) CK(cudaStreamSynchronize(h->stream));  // host buffers may be reused by the caller
   h->points_set = true;
-  if (shape_changed || bc_changed || on_device) h->graph_valid = false;
-  h->n_col_global = 0;
-  h->n_bd_global.clear();
+  const float* const after[6] = {h->col.coords, h->col.aux, h->col.base, h->bc.coords, h->bc.aux, h->bc.base};
+  bool ptr_changed = false;
+  for (int i = 0; i < 6; ++i) ptr_changed |= (before[i] != after[i]);
+  if (shape_changed || bc_changed || on_device || ptr_changed) h->graph_valid = false;
+  // global counts (multi-GPU means) survive a resample with unchanged local shapes; a shape change resets them
+  if (shape_changed || bc_changed) {
+    h->n_col_global = 0;
+    h->n_bd_global.clear();
+  }
   return upload_meta(h);
 }
 
@@ -710,8 +774,7 @@ static int enqueue_eval(pinn_engine* h, const float* params_dev, int tick) {
   const int P = h->fmap.n_params;
   const bool has_bc = h->Lbc.n_tiles > 0, fork = has_bc && h->fork_bc;
   const int nb = fork ? h->grid_col + h->grid_bc : std::max(h->grid_col, h->grid_bc);
-  k_pack<<<(P + 255) / 256, 256, 0, st>>>(h->fmap, params_dev ? params_dev : h->d_params, h->d_wpack);
-  CK(cudaGetLastError());
+  if (enqueue_pack(h, params_dev, st)) return 1;
   CK(cudaMemsetAsync(h->d_gacc, 0, sizeof(float) * (size_t)nb * h->net.pg, st));
   CK(cudaMemsetAsync(h->d_loss_part, 0, sizeof(double) * (size_t)nb * h->n_slots, st));
   if (fork) {
@@ -835,9 +898,20 @@ extern "C" int pinn_engine_eval(pinn_engine_t* h, const float* z, int64_t n, con
   const bool has_aux_prog = h->spec.n_aux_ops > 0;
   if (na_user > 0 && !aux) return fail("aux required");
   cudaStream_t st = h->stream;
-  std::vector<void*> tmp;
-  auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr; tmp.push_back(p); return p; };
-  auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); };
+  // scratch comes from the handle (grown on demand, reused by later calls: predictF / resampling / stage-2
+  // set_data call this every 100-2000 steps); reuse is ordered by the engine stream
+  size_t n_tmp = 0;
+  auto dalloc = [&](size_t bytes) -> void* {
+    if (n_tmp == h->eval_bufs.size()) h->eval_bufs.emplace_back(nullptr, 0);
+    auto& b = h->eval_bufs[n_tmp++];
+    if (b.second < bytes) {
+      if (b.first) { cudaStreamSynchronize(st); cudaFree(b.first); b.first = nullptr; b.second = 0; }
+      if (cudaMalloc(&b.first, bytes) != cudaSuccess) { b.first = nullptr; return nullptr; }
+      b.second = bytes;
+    }
+    return b.first;
+  };
+  auto cleanup = [&]() {};
   const float *dz = z, *daux = aux, *dbase = base;
   float *du = u_out, *df = f_out, *dj = jets_out;
   if (!on_device) {
@@ -858,8 +932,7 @@ extern "C" int pinn_engine_eval(pinn_engine_t* h, const float* z, int64_t n, con
     k_eval_aux<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->prog_aux, dz, d, daux, na_user, comb, na, n);
     daux = comb;
   }
-  const int P = h->fmap.n_params;
-  k_pack<<<(P + 255) / 256, 256, 0, st>>>(h->fmap, h->d_params, h->d_wpack);
+  if (enqueue_pack(h, nullptr, st)) { cleanup(); return 1; }
   PinnLaunch L;
   fill_launch(h, L, h->kcol, h->prog_col);
   L.coords = dz; L.aux = daux; L.base = dbase; L.n_aux = na;
@@ -869,9 +942,8 @@ extern "C" int pinn_engine_eval(pinn_engine_t* h, const float* z, int64_t n, con
   L.n_tiles = (int)((n + tp - 1) / tp);
   L.seg_tile_end[0] = L.n_tiles; L.seg_pt_begin[0] = 0; L.seg_pt_end[0] = n; L.seg_slot[0] = 0;
   cudaError_t e;
-  const char* kenv = getenv("PINN_B200_KERNEL");
-  if (kenv && !strcmp(kenv, "umma")) {
-    // experimental tcgen05 family (evaluation only so far)
+  if (h->use_umma) {
+    // experimental tcgen05 family C
     if (!jet_umma_supported(h->net, K, h->spec.n1, h->spec.n2, h->spec.mix)) { cleanup(); return fail("PINN_B200_KERNEL=umma: configuration not supported by the tcgen05 family"); }
     float* images = (float*)dalloc(sizeof(float) * jet_umma_image_floats(h->net));
     long long* clk = (long long*)dalloc(sizeof(long long) * 8);
@@ -892,10 +964,6 @@ extern "C" int pinn_engine_eval(pinn_engine_t* h, const float* z, int64_t n, con
     if (f_out) cudaMemcpyAsync(f_out, df, sizeof(float) * n, cudaMemcpyDeviceToHost, st);
     if (jets_out) cudaMemcpyAsync(jets_out, dj, sizeof(float) * n * K, cudaMemcpyDeviceToHost, st);
     e = cudaStreamSynchronize(st);
-    cleanup();
-    if (e != cudaSuccess) return fail("eval: %s", cudaGetErrorString(e));
-  } else if (!tmp.empty()) {
-    e = cudaStreamSynchronize(st);  // the combined aux buffer is a temporary
     cleanup();
     if (e != cudaSuccess) return fail("eval: %s", cudaGetErrorString(e));
   }
@@ -924,7 +992,7 @@ extern "C" int pinn_engine_time_kernels(pinn_engine_t* h, int32_t reps, int64_t 
   const int nb = h->fork_bc ? h->grid_col + h->grid_bc : std::max(h->grid_col, h->grid_bc);
   void* flush = nullptr;
   if (flush_bytes > 0) CK(cudaMalloc(&flush, (size_t)flush_bytes));
-  k_pack<<<(P + 255) / 256, 256, 0, st>>>(h->fmap, h->d_params, h->d_wpack);
+  if (enqueue_pack(h, nullptr, st)) return 1;
   double tc = 0.0, tb = 0.0;
   for (int r = 0; r < reps; ++r) {
     CK(cudaMemsetAsync(h->d_gacc, 0, sizeof(float) * (size_t)nb * h->net.pg, st));
@@ -965,7 +1033,7 @@ extern "C" int pinn_engine_phase_profile(pinn_engine_t* h, int64_t* out8) {
   long long* d = nullptr;
   CK(cudaMalloc(&d, 8 * sizeof(long long)));
   CK(cudaMemsetAsync(d, 0, 8 * sizeof(long long), st));
-  k_pack<<<(P + 255) / 256, 256, 0, st>>>(h->fmap, h->d_params, h->d_wpack);
+  if (enqueue_pack(h, nullptr, st)) return 1;
   CK(cudaMemsetAsync(h->d_gacc, 0, sizeof(float) * (size_t)h->grid_col * h->net.pg, st));
   CK(cudaMemsetAsync(h->d_loss_part, 0, sizeof(double) * (size_t)h->grid_col * h->n_slots, st));
   PinnLaunch L = h->Lcol;
@@ -1082,7 +1150,7 @@ extern "C" int pinn_engine_lbfgs(pinn_engine_t* h, int32_t max_iter, double tol,
     Phi lo{0.0, fcur, dphi0}, hi{}, c{};
     bool found = false, ok = true;
     auto ev = [&](double a, Phi& p) -> bool {  // returns true when p satisfies the Wolfe test
-      if (ls.eval(a, p)) { ok = false; return false; }
+      if (ls.eval(a, p)) { ok = false; ls.error = true; return false; }
       return ls.wolfe(p);
     };
     // U3 bisection on [A, B] with phi'(A) < 0, phi(A) <= f_lim, phi'(B) < 0, phi(B) > f_lim
@@ -1155,7 +1223,7 @@ extern "C" int pinn_engine_lbfgs(pinn_engine_t* h, int32_t max_iter, double tol,
       if (hi.a - lo.a <= 1e-16 * fmax(1.0, hi.a)) break;
     }
     total_evals += ls.evals;
-    if (!ok && !g_err.empty() && ls.evals == 0) return 1;
+    if (ls.error) return 1;  // a CUDA / NCCL error inside an evaluation is an error, not a line-search failure
     if (!found) { R.failed = 1; break; }
     // accept: the last evaluation was at c (xt, fused hold x_new, g_new)
     k_lbfgs_push<<<1, 1024, 0, st>>>(P, head, h->d_x, h->d_g, h->d_xt, h->d_fused, h->d_S, h->d_Y, h->d_rho, h->d_scal);

@@ -12,7 +12,7 @@ struct JetKernelInfo {
   size_t stash_floats_per_layer;  // per CTA
   cudaError_t (*launch)(const PinnLaunch& L, bool train, int grid, cudaStream_t stream);
   cudaError_t (*prepare)(int* ctas_per_sm);  // opt in to large dynamic smem; resident CTAs per SM (train kernel)
-  int kind;          // 0: fp32 SIMT (FFMA2) kernel, 1: 3xTF32 mma.sync tensor-core kernel
+  int kind;          // 0: fp32 SIMT (FFMA2) kernel, 1: 3xTF32 mma.sync tensor-core kernel, 3: tcgen05 bf16x3 kernel (family D)
   int ldw;           // row stride of the hidden-layer matrices in the weight/gradient pack
 };
 

@@ -1,0 +1,775 @@
+// tcgen05 kernel family ("family D", kind 3): the production kernel for padded widths 128 and 256.
+//
+// All three hidden-layer GEMMs of the fused jet-MLP step run on tcgen05.mma kind::f16 (bf16 inputs,
+// fp32 accumulators in Tensor Memory), with every fp32 operand split into THREE bf16 planes
+// (x = b0 + b1 + b2, 24 significant bits) and six MMAs per product (b0*b0, b0*b1, b1*b0, b1*b1,
+// b0*b2, b2*b0: everything down to 2^-24), the same cost as 3xTF32 but with 16-bit operands, whose
+// swizzled shared-memory tiles can be read K-major AND MN-major through two descriptors.  That is
+// what makes ONE on-chip copy of the activations serve the forward GEMM, the data-gradient GEMM and
+// the (transposed) weight-gradient GEMM (layouts measured with tools/umma_probe_bf16.py,
+// profiles/r02_umma_bf16_probe.txt).
+//
+// Roles are swapped with respect to a textbook GEMM: the UNITS of a layer are the M rows (TMEM
+// lanes), the tile's (point, jet channel) pairs are the N columns:
+//     forward        D[out][n]  = sum_in  W[in][out] * Y[in][n]      A = weights (K-major image, streamed
+//     data gradient  D[in][n]   = sum_out W[in][out] * G[out][n]         through a cp.async.bulk ring),
+//                                                                     B = activation tile, MN-major view
+//     weight grad.   DW[in][out] = sum_n  Y[in][n] * G[out][n]        A, B = the same tiles, K-major view
+// An epilogue thread owns ONE unit (= its TMEM lane) and loops over points: all jet channels of a
+// (point, unit) pair are columns of the same lane, so the activation jets (sigma', sigma'' from the value
+// channel), the bias add, and the bias / first-layer / output-layer gradients need no cross-thread
+// exchange at all; operands are written with 16-byte stores along n.
+//
+// Warp roles: 4*Q epilogue warps (warp % 4 = TMEM lane quadrant = 32 units, warp / 4 = block of 8
+// points), one MMA-issue warp, one producer warp that streams the pre-split weight images.
+// Accumulation is two-level: the five small products go to a second TMEM accumulator and are added
+// to the b0*b0 accumulator in the epilogue with a round-to-nearest add (the tensor core truncates
+// when it accumulates: profiles/r02_umma_bf16_probe.txt).
+//
+// Reference semantics: pinn_app/software.py:158-184 (network), 246-297 (derivatives, residual),
+// 318-379 (loss) and grad(loss_fun) (390); math as in jet_mma_kernel.cuh / SURVEY.md 8(a) addendum.
+#pragma once
+#include "jet_kernel.cuh"
+#include "umma_common.cuh"
+
+template <int WP_, int N1_, int N2_, int MIX_>
+struct TcCfg {
+  static constexpr int WP = WP_, N1 = N1_, N2 = N2_, MIX = MIX_;
+  static constexpr bool LAP = (MIX == 2);
+  static constexpr int K = 1 + N1 + N2 + (MIX ? 1 : 0);
+  static constexpr int MB = WP / 128;                        // M blocks (128 units each)
+  static constexpr int NP = (WP == 128 && K <= 4) ? 32 : 16;  // points per tile
+  static constexpr int Q = NP / 8;                           // epilogue warps per lane quadrant (8 points each)
+  static constexpr int NROW = NP * K;                        // N of the forward / data-gradient MMAs
+  static constexpr int SWB = (NROW % 64 == 0) ? 128 : 32;    // swizzle span (bytes per line) of the activation tiles
+  static constexpr int NBLK = (NROW * 2 + SWB - 1) / SWB;    // n-blocks per plane
+  static constexpr int PLANE1 = NBLK * WP * SWB;             // region 1: all WP lines
+  static constexpr int PLANE2 = NBLK * 128 * SWB;            // region 2: one block of 128 lines
+  static constexpr int R1_BYTES = 3 * PLANE1, R2_BYTES = 3 * PLANE2;
+  static constexpr int NEPI = 4 * Q;
+  static constexpr int NEPI_T = NEPI * 32;
+  static constexpr int NT = NEPI_T + 64;                     // + MMA-issue warp + producer warp
+  static constexpr int KS = WP / 16;                         // k-steps of the forward / data-gradient GEMMs
+  static constexpr int KSW = NROW / 16;                      // k-steps of the weight-gradient GEMM
+  static constexpr int SLOT = 4096;                          // one (k-step, plane) weight image: 128 rows x 32 B
+  static constexpr int NSLOT = 6;
+  static constexpr int CHUNKS = MB * KS * 3;                 // ring chunks per forward / data-gradient GEMM
+  static constexpr int PARTLD = NROW + 4;                    // row stride of the output-layer partial products
+  // TMEM columns: per M block (big | small) accumulators, then the weight-gradient block
+  __host__ __device__ static constexpr int TC_D(int mb) { return mb * 2 * NROW; }
+  static constexpr int TC_DW = MB * 2 * NROW;                // two weight-gradient blocks (ping-pong) of 128 columns
+  static constexpr int TC_USED = TC_DW + 256;
+  static constexpr int MISC_FLOATS = NP * 4 /*z*/ + 3 * NP /*beta*/ + NP * K * 4 /*hj*/ + NROW /*ubar*/ + 4 * NROW /*psum*/ +
+                                     Q * WP /*bias-gradient partials*/ + PINN_MAX_OPS + PINN_MAX_CONSTS;
+  static constexpr size_t smem_bytes() { return (size_t)R1_BYTES + R2_BYTES + NSLOT * SLOT + MISC_FLOATS * 4 + 256; }
+  static constexpr size_t STL = (size_t)(K + 1) * WP * NP;   // stash floats per layer and CTA (K jets + cos for the sin activation)
+  static constexpr bool OK = (NROW % 16 == 0) && (NROW <= 256) && (TC_USED <= 512) && (smem_bytes() <= 232448 - 1024) &&
+                             ((size_t)WP * PARTLD * 4 <= (size_t)R1_BYTES) && (MB == 1);
+};
+
+namespace tc {
+
+// ---- bf16x3 split of a pair (x0 -> lower half, x1 -> upper half); every residual is exact
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+  p0 = cvt_bf16x2(x0, x1);
+  const float r0 = x0 - __uint_as_float(p0 << 16), r1 = x1 - __uint_as_float(p0 & 0xffff0000u);
+  p1 = cvt_bf16x2(r0, r1);
+  const float s0 = r0 - __uint_as_float(p1 << 16), s1 = r1 - __uint_as_float(p1 & 0xffff0000u);
+  p2 = cvt_bf16x2(s0, s1);
+}
+
+// byte offset of the 16-byte chunk (line, n8 = n / 8) inside a plane of `lines` lines
+template <int SWB>
+__device__ __forceinline__ uint32_t chunk_off(int line, int n8, int lines) {
+  if (SWB == 128) return (uint32_t)((n8 >> 3) * (lines * 128) + line * 128 + (((n8 & 7) ^ (line & 7)) << 4));
+  return (uint32_t)((n8 >> 1) * (lines * 32) + line * 32 + (((n8 & 1) ^ ((line >> 2) & 1)) << 4));
+}
+// byte offset of k-step ks (16 n) for the K-major view of a plane of `lines` lines
+template <int SWB>
+__device__ __forceinline__ uint32_t kmajor_koff(int ks, int lines) {
+  if (SWB == 128) return (uint32_t)((ks >> 2) * (lines * 128) + (ks & 3) * 32);
+  return (uint32_t)(ks * (lines * 32));
+}
+template <int SWB>
+__device__ __forceinline__ constexpr uint32_t layout_type() { return SWB == 128 ? 2u : 6u; }
+
+// split 8 values and store them as one chunk per plane
+template <int SWB>
+__device__ __forceinline__ void store_split8(uint8_t* region, int plane_bytes, int line, int n8, int lines, const float (&v)[8]) {
+  uint32_t p0[4], p1[4], p2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split3_pair(v[2 * j], v[2 * j + 1], p0[j], p1[j], p2[j]);
+  uint8_t* d = region + chunk_off<SWB>(line, n8, lines);
+  *reinterpret_cast<uint4*>(d) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+  *reinterpret_cast<uint4*>(d + plane_bytes) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+  *reinterpret_cast<uint4*>(d + 2 * plane_bytes) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+}
+
+// inline sin/cos: three-constant Cody-Waite reduction by pi/2 + minimax polynomials on [-pi/4, pi/4]
+// (about 1 ulp); huge arguments take the library path
+__device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
+  if (fabsf(x) > 3.0e4f) {
+    sincos_ni(x, &s, &c);
+    return;
+  }
+  const float k = rintf(x * 0.636619772f);
+  float r = fmaf(k, -1.57079601e+00f, x);
+  r = fmaf(k, -3.13916473e-07f, r);
+  r = fmaf(k, -5.39030253e-15f, r);
+  const int q = __float2int_rn(k);
+  const float r2 = r * r;
+  float sp = fmaf(r2, -1.95152959e-4f, 8.33216087e-3f);
+  sp = fmaf(sp, r2, -1.66666546e-1f);
+  sp = fmaf(sp * r2, r, r);
+  float cp = fmaf(r2, 2.44331571e-5f, -1.38873163e-3f);
+  cp = fmaf(cp, r2, 4.16666457e-2f);
+  cp = fmaf(cp, r2, -0.5f);
+  cp = fmaf(cp, r2, 1.0f);
+  const float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
+  s = (q & 2) ? -ss : ss;
+  c = ((q + 1) & 2) ? -cc : cc;
+}
+
+// y, s' and s'' (derivatives of the activation) of 8 pre-activations.  The backward pass needs no pre-activation
+// again: it restarts from the stashed y (tanh: s' = 1 - y^2 ...) or from the stashed (sin, cos) pair.
+__device__ __forceinline__ void act8_fwd(int act, const float (&a)[8], float (&y)[8], float (&d1)[8], float (&d2)[8]) {
+  if (act == PINN_TANH) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = tanh_bf(a[i]);
+      y[i] = t;
+      d1[i] = fmaf(-t, t, 1.0f);
+      d2[i] = -2.0f * t * d1[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float sn, cs;
+      sincos_cw(a[i], sn, cs);
+      y[i] = sn; d1[i] = cs; d2[i] = -sn;
+    }
+  }
+}
+// first, second and third derivative of the activation from the stashed output y (for sin: d1 holds the stashed cos)
+__device__ __forceinline__ void act8_bwd(int act, const float (&y)[8], float (&d1)[8], float (&d2)[8], float (&d3)[8]) {
+  if (act == PINN_TANH) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = y[i];
+      d1[i] = fmaf(-t, t, 1.0f);
+      d2[i] = -2.0f * t * d1[i];
+      d3[i] = d1[i] * fmaf(6.0f * t, t, -2.0f);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { d2[i] = -y[i]; d3[i] = -d1[i]; }
+  }
+}
+
+// pre-activation jets a[1..K-1] (a[0] is overwritten with y) -> output jets, in place
+template <class C>
+__device__ __forceinline__ void jets_outputs(float (&a)[C::K][8], const float (&y)[8], const float (&d1)[8], const float (&d2)[8],
+                                             const float (&beta)[3][8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int k = 0; k < C::N2; ++k) {
+      const float Ai = a[1 + k][i];
+      a[1 + C::N1 + k][i] = fmaf(d2[i] * Ai, Ai, d1[i] * a[1 + C::N1 + k][i]);
+    }
+    if (C::MIX == 1) a[C::K - 1][i] = fmaf(d2[i] * a[1][i], a[2][i], d1[i] * a[C::K - 1][i]);
+    if (C::LAP) {
+      float S = 0.f;
+#pragma unroll
+      for (int k = 0; k < C::N1; ++k) S = fmaf(beta[k][i] * a[1 + k][i], a[1 + k][i], S);
+      a[C::K - 1][i] = fmaf(d2[i], S, d1[i] * a[C::K - 1][i]);
+    }
+#pragma unroll
+    for (int k = 0; k < C::N1; ++k) a[1 + k][i] *= d1[i];
+    a[0][i] = y[i];
+  }
+}
+
+// adjoint of the activation jets: yb = adjoint of the layer outputs (in), st = stashed pre-activation jets;
+// on return yb holds the adjoint of the pre-activations
+template <class C>
+__device__ __forceinline__ void jets_adjoint(float (&yb)[C::K][8], const float (&st)[C::K][8], const float (&d1)[8], const float (&d2)[8],
+                                             const float (&d3)[8], const float (&beta)[3][8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float ab0 = d1[i] * yb[0][i];
+    float ab1[C::N1 > 0 ? C::N1 : 1];
+#pragma unroll
+    for (int k = 0; k < C::N1; ++k) {
+      const float v = yb[1 + k][i];
+      ab1[k] = d1[i] * v;
+      ab0 = fmaf(d2[i] * st[1 + k][i], v, ab0);
+    }
+#pragma unroll
+    for (int k = 0; k < C::N2; ++k) {
+      const float v = yb[1 + C::N1 + k][i];
+      const float Ai = st[1 + k][i], Aii = st[1 + C::N1 + k][i];
+      yb[1 + C::N1 + k][i] = d1[i] * v;
+      ab1[k] = fmaf(2.0f * d2[i] * Ai, v, ab1[k]);
+      ab0 = fmaf(fmaf(d3[i] * Ai, Ai, d2[i] * Aii), v, ab0);
+    }
+    if (C::MIX == 1) {
+      const float v = yb[C::K - 1][i];
+      const float A0 = st[1][i], A1 = st[2][i], A01 = st[C::K - 1][i];
+      yb[C::K - 1][i] = d1[i] * v;
+      ab1[0] = fmaf(d2[i] * A1, v, ab1[0]);
+      ab1[C::N1 > 1 ? 1 : 0] = fmaf(d2[i] * A0, v, ab1[C::N1 > 1 ? 1 : 0]);
+      ab0 = fmaf(fmaf(d3[i] * A0, A1, d2[i] * A01), v, ab0);
+    }
+    if (C::LAP) {
+      const float v = yb[C::K - 1][i];
+      float S = 0.f;
+#pragma unroll
+      for (int k = 0; k < C::N1; ++k) {
+        const float bA = beta[k][i] * st[1 + k][i];
+        S = fmaf(bA, st[1 + k][i], S);
+        ab1[k] = fmaf(2.0f * d2[i] * bA, v, ab1[k]);
+      }
+      yb[C::K - 1][i] = d1[i] * v;
+      ab0 = fmaf(fmaf(d3[i], S, d2[i] * st[C::K - 1][i]), v, ab0);
+    }
+#pragma unroll
+    for (int k = 0; k < C::N1; ++k) yb[1 + k][i] = ab1[k];
+    yb[0][i] = ab0;
+  }
+}
+
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// bounded mbarrier wait: a protocol bug traps (launch failure) instead of hanging the GPU
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
+  if (!umma::mbar_wait(bar, parity, 1u << 24)) __trap();
+}
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+}  // namespace tc
+
+enum { TC_BAR_EPI = 1, TC_BAR_OP1 = 2, TC_BAR_OP2 = 3 };
+
+
+// ---------------------------------------------------------------- the kernel
+template <class C, bool TRAIN>
+__global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant__ PinnLaunch L) {
+  static_assert(C::OK, "invalid tcgen05 kernel configuration");
+  constexpr int K = C::K, WP = C::WP, NP = C::NP, Q = C::Q, NROW = C::NROW, SWB = C::SWB;
+  constexpr int NSLOT = C::NSLOT, PB = NP / 8;
+  constexpr uint32_t LT = tc::layout_type<SWB>();
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  uint8_t* const smem = tc_smem;
+  uint8_t* const R1 = smem;                                    // forward: layer input Y; backward: adjoints G
+  uint8_t* const R2 = smem + C::R1_BYTES;                      // backward: recomputed layer input Y (128-line block)
+  uint8_t* const ring = R2 + C::R2_BYTES;                      // weight-image ring
+  float* const s_z = reinterpret_cast<float*>(ring + NSLOT * C::SLOT);  // [NP][4]: coordinates, valid flag
+  float* const s_beta = s_z + NP * 4;                          // [3][NP]
+  float* const s_hj = s_beta + 3 * NP;                         // [NP][K][4] feature jets
+  float* const s_ubar = s_hj + NP * K * 4;                     // [NROW] epsil * adjoint of the network outputs
+  float* const s_psum = s_ubar + NROW;                         // [4][NROW] output-layer partial sums
+  float* const s_bg = s_psum + 4 * NROW;                       // [Q][WP] per-warp gradient partials (fixed-order fold)
+  int* const s_ops = reinterpret_cast<int*>(s_bg + Q * WP);
+  float* const s_consts = reinterpret_cast<float*>(s_ops + PINN_MAX_OPS);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(s_consts + PINN_MAX_CONSTS);
+  uint64_t* const bar_full = bars;
+  uint64_t* const bar_empty = bars + NSLOT;
+  uint64_t* const bar_fd = bars + 2 * NSLOT;
+  uint64_t* const bar_w = bar_fd + 1;
+  __shared__ uint32_t s_tmem;
+  float* const part = reinterpret_cast<float*>(R1);            // [WP][PARTLD] output-layer partial products
+
+  const PinnNet& net = L.net;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Lh = net.n_hidden, NG = Lh - 1;
+  const int my_tiles = (L.n_tiles > (int)blockIdx.x) ? (L.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  for (int i = tid; i < L.prog.n_ops; i += C::NT) s_ops[i] = L.prog.ops[i];
+  for (int i = tid; i < PINN_MAX_CONSTS; i += C::NT) s_consts[i] = L.prog.consts[i];
+  if (warp == C::NEPI) umma::tmem_alloc(&s_tmem, 512);
+  if (tid == 0) {
+    for (int i = 0; i < NSLOT; ++i) { umma::mbar_init(&bar_full[i], 1); umma::mbar_init(&bar_empty[i], 1); }
+    umma::mbar_init(bar_fd, 1);
+    umma::mbar_init(bar_w, 1);
+    umma::fence_mbar_init();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tb = s_tmem;
+
+  if (warp == C::NEPI + 1) {
+    // ================================================================ producer: weight-image stream
+    // Every CTA walks the same chunk sequence at about the same time; one copy of the images would be served
+    // by the handful of L2 slices a 4 KB chunk maps to (measured: 7.9 B/cycle/SM).  The engine keeps
+    // `wimg_copies` replicas at different addresses and each CTA reads replica blockIdx % copies.
+    if (lane == 0) {
+      const uint8_t* img = reinterpret_cast<const uint8_t*>(L.wimg) + (size_t)(blockIdx.x % L.wimg_copies) * L.wimg_copy_bytes;
+      const int per_tile = (TRAIN ? 2 : 1) * NG * C::CHUNKS;
+      const long long total = (long long)my_tiles * per_tile;
+      int c = 0;
+      for (long long i = 0; i < total; ++i) {
+        const int s = (int)(i % NSLOT);
+        const uint32_t round = (uint32_t)(i / NSLOT);
+        if (round > 0) tc::wait_bar(&bar_empty[s], (round - 1) & 1);
+        mbar_expect_tx(&bar_full[s], C::SLOT);
+        bulk_g2s(ring + s * C::SLOT, img + (size_t)c * C::SLOT, C::SLOT, &bar_full[s]);
+        if (++c == per_tile) c = 0;
+      }
+    }
+  } else if (warp == C::NEPI) {
+    // ================================================================ MMA issue warp
+    long long ci = 0;
+    const uint32_t id_wx = umma::idesc_bf16(128, NROW, 0, 1);
+    const uint32_t id_wg = umma::idesc_bf16(128, 128, 0, 0);
+    const uint32_t r1a = umma::smem_addr(R1), r2a = umma::smem_addr(R2), rga = umma::smem_addr(ring);
+    // D (big | small) = W x act(R1), weights from the ring
+    auto gemm_wx = [&]() {
+      for (int mb = 0; mb < C::MB; ++mb) {
+        const uint32_t DB = tb + C::TC_D(mb), DS = DB + NROW;
+        for (int ks = 0; ks < C::KS; ++ks) {
+          uint64_t bd[3];
+#pragma unroll
+          for (int p = 0; p < 3; ++p) bd[p] = umma::smem_desc(r1a + p * C::PLANE1 + ks * 16 * SWB, WP * SWB, 8 * SWB, LT);
+          const uint32_t acc = ks > 0 ? 1u : 0u;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {  // weight planes b2, b1, b0 (small products first)
+            const int s = (int)(ci % NSLOT);
+            tc::wait_bar(&bar_full[s], (uint32_t)((ci / NSLOT) & 1));
+            umma::fence_after_sync();
+            const uint64_t ad = umma::smem_desc(rga + s * C::SLOT, 16, 256, 6);
+            if (j == 0) {
+              umma::mma_bf16_ss(DS, ad, bd[0], id_wx, acc);
+            } else if (j == 1) {
+              umma::mma_bf16_ss(DS, ad, bd[1], id_wx, 1u);
+              umma::mma_bf16_ss(DS, ad, bd[0], id_wx, 1u);
+            } else {
+              umma::mma_bf16_ss(DS, ad, bd[2], id_wx, 1u);
+              umma::mma_bf16_ss(DS, ad, bd[1], id_wx, 1u);
+              umma::mma_bf16_ss(DB, ad, bd[0], id_wx, acc);
+            }
+            umma::commit(&bar_empty[s]);
+            ++ci;
+          }
+        }
+      }
+      umma::commit(bar_fd);
+    };
+    // DW[out][in] = sum_n G[out][n] * Y[in][n]: G in R1 (M rows = output units: the flush then writes the
+    // gradient rows with coalesced stores), Y block in R2, both K-major views
+    auto gemm_wgrad = [&](int buf) {
+      const uint32_t DW = tb + C::TC_DW + 128 * buf;
+      for (int ks = 0; ks < C::KSW; ++ks) {
+        uint64_t ag[3], by[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          ag[p] = umma::smem_desc(r1a + p * C::PLANE1 + tc::kmajor_koff<SWB>(ks, WP), 16, 8 * SWB, LT);
+          by[p] = umma::smem_desc(r2a + p * C::PLANE2 + tc::kmajor_koff<SWB>(ks, 128), 16, 8 * SWB, LT);
+        }
+        umma::mma_bf16_ss(DW, ag[0], by[2], id_wg, ks > 0 ? 1u : 0u);
+        umma::mma_bf16_ss(DW, ag[2], by[0], id_wg, 1u);
+        umma::mma_bf16_ss(DW, ag[1], by[1], id_wg, 1u);
+        umma::mma_bf16_ss(DW, ag[0], by[1], id_wg, 1u);
+        umma::mma_bf16_ss(DW, ag[1], by[0], id_wg, 1u);
+        umma::mma_bf16_ss(DW, ag[0], by[0], id_wg, 1u);
+      }
+      umma::commit(bar_w);
+    };
+    for (int it = 0; it < my_tiles; ++it) {
+      for (int l = 1; l < Lh; ++l) {
+        tc::named_sync(TC_BAR_OP1, C::NEPI_T + 32);
+        umma::fence_after_sync();
+        if (lane == 0) gemm_wx();
+        __syncwarp();
+      }
+      if (TRAIN) {
+        for (int l = Lh - 1; l >= 1; --l) {
+          tc::named_sync(TC_BAR_OP1, C::NEPI_T + 32);
+          umma::fence_after_sync();
+          if (lane == 0) gemm_wx();
+          __syncwarp();
+          tc::named_sync(TC_BAR_OP2, C::NEPI_T + 32);
+          umma::fence_after_sync();
+          if (lane == 0) gemm_wgrad(l & 1);
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < C::NEPI) {
+    // ================================================================ epilogue warps
+    const int quad = warp & 3, q = warp >> 2;
+    const int u = 32 * quad + lane;                        // this thread's unit (= TMEM lane)
+    const uint32_t tl = tb + ((uint32_t)(32 * quad) << 16);
+    const int n8 = q;                                      // 8-point block of this warp
+    uint32_t par_fd = 0, par_w = 0;
+    auto epi_sync = [&]() { tc::named_sync(TC_BAR_EPI, C::NEPI_T); };
+    auto operands_ready = [&](int bar) {
+      umma::fence_async_smem();
+      umma::fence_before_sync();
+      tc::named_arrive(bar, C::NEPI_T + 32);
+    };
+    float* const stash = TRAIN ? (L.stash + (size_t)blockIdx.x * Lh * C::STL) : nullptr;
+    float* const gacc = TRAIN ? (L.gacc + (size_t)blockIdx.x * net.pg) : nullptr;
+    const int ldw = L.ldw;
+    float wlacc = 0.f, w0acc[3] = {0.f, 0.f, 0.f}, blacc = 0.f;
+    double lcur = 0.0;
+    const int slot = L.seg_slot[0];
+    const long long n_end = L.seg_pt_end[0];
+    const bool prof = (L.phase_clk != nullptr) && blockIdx.x == 0 && tid == 0;
+    long long pclk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tmark = prof ? clock64() : 0;
+    auto lap = [&](int ph) {
+      if (prof) { const long long now = clock64(); pclk[ph] += now - tmark; tmark = now; }
+    };
+    // accumulators of the last forward / data-gradient GEMM (big + small) -> registers
+    auto load_acc = [&](float (&a)[K][8]) {
+      float sm[K][8];
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        umma::tmem_ld8(tl + C::TC_D(0) + c * NP + 8 * n8, a[c]);
+        umma::tmem_ld8(tl + C::TC_D(0) + NROW + c * NP + 8 * n8, sm[c]);
+      }
+      umma::tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < K; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[c][i] += sm[c][i];
+    };
+    auto load_beta = [&](float (&beta)[3][8]) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (C::LAP && k < C::N1) tc::ld8(s_beta + k * NP + 8 * n8, beta[k]);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) beta[k][i] = 0.f;
+        }
+      }
+    };
+    // stash slot of (layer, channel); channel K = cos of the sin activation
+    auto stash_ptr = [&](int l, int c) -> float* { return stash + (size_t)l * C::STL + ((size_t)(c * Q + q) * 128 + u) * 8; };
+    // weight-gradient block (lane = output unit, columns = input units) -> CTA-private accumulator rows, coalesced
+    auto flush_dw = [&](int l) {
+      constexpr int NC = 128 / Q;  // input units (columns) per warp
+      float* gcol = gacc + net.off_w[l] + (size_t)(q * NC) * ldw + u;
+      const uint32_t src = tl + C::TC_DW + 128 * (l & 1) + q * NC;
+#pragma unroll
+      for (int j = 0; j < NC / 8; ++j) {
+        float w[8], g8[8];
+        umma::tmem_ld8(src + 8 * j, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g8[i] = gcol[(size_t)(8 * j + i) * ldw];
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gcol[(size_t)(8 * j + i) * ldw] = g8[i] + w[i];
+      }
+      umma::fence_before_sync();
+    };
+
+#pragma unroll 1
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const long long pbegin = L.seg_pt_begin[0] + (long long)tile * NP;
+      // ---------------- tile header: coordinates, betas, feature jets of the tile's points
+      if (tid < NP) {
+        const int pt = tid;
+        const bool valid = pbegin + pt < n_end;
+        const long long gp = valid ? pbegin + pt : pbegin;
+        const float* zp = L.coords + gp * net.d_in;
+        float z[3];
+        z[0] = __ldg(zp);
+        z[1] = (net.d_in > 1) ? __ldg(zp + 1) : 0.f;
+        z[2] = (net.d_in > 2) ? __ldg(zp + 2) : 0.f;
+        float beta[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          beta[i] = (C::LAP && net.lap_aux[i] >= 0) ? __ldg(L.aux + gp * L.n_aux + net.lap_aux[i]) : net.lap_beta[i];
+        float hj[K][3];
+        feature_jets<C>(net, z, beta, hj);
+        s_z[pt * 4 + 0] = z[0]; s_z[pt * 4 + 1] = z[1]; s_z[pt * 4 + 2] = z[2]; s_z[pt * 4 + 3] = valid ? 1.f : 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s_beta[i * NP + pt] = beta[i];
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+          *reinterpret_cast<float4*>(s_hj + (pt * K + c) * 4) = make_float4(hj[c][0], hj[c][1], hj[c][2], 0.f);
+      }
+      epi_sync();
+
+      // ---------------- forward
+#pragma unroll 1
+      for (int l = 0; l < Lh; ++l) {
+        float a[K][8];
+        if (l == 0) {
+          const float w00 = __ldg(L.wpack + net.off_w0 + u), w01 = __ldg(L.wpack + net.off_w0 + WP + u),
+                      w02 = __ldg(L.wpack + net.off_w0 + 2 * WP + u);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < K; ++c) {
+              const float4 h = *reinterpret_cast<const float4*>(s_hj + ((8 * n8 + i) * K + c) * 4);
+              a[c][i] = net.scl * fmaf(h.x, w00, fmaf(h.y, w01, h.z * w02));
+            }
+        } else {
+          tc::wait_bar(bar_fd, par_fd);
+          par_fd ^= 1;
+          umma::fence_after_sync();
+          lap(0);
+          load_acc(a);
+        }
+        const int act = (l == 0) ? net.act_first : net.act_hidden;
+        const float bias = __ldg(L.wpack + net.off_b[l] + u);
+        float beta[3][8];
+        load_beta(beta);
+        {
+          float y[8], d1[8], d2[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[0][i] += bias;
+          tc::act8_fwd(act, a[0], y, d1, d2);
+          if (TRAIN) {
+            tc::st8(stash_ptr(l, 0), y);
+            if (act == PINN_SIN) tc::st8(stash_ptr(l, K), d1);
+#pragma unroll
+            for (int c = 1; c < K; ++c) tc::st8(stash_ptr(l, c), a[c]);
+          }
+          tc::jets_outputs<C>(a, y, d1, d2, beta);
+        }
+        if (l < Lh - 1) {
+#pragma unroll
+          for (int c = 0; c < K; ++c) tc::store_split8<SWB>(R1, C::PLANE1, u, c * PB + n8, WP, a[c]);
+          operands_ready(TC_BAR_OP1);
+        } else {
+          const float wlv = __ldg(L.wpack + net.off_wl + u);
+#pragma unroll
+          for (int c = 0; c < K; ++c) {
+            float pv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pv[i] = a[c][i] * wlv;
+            tc::st8(part + (size_t)u * C::PARTLD + c * NP + 8 * n8, pv);
+          }
+        }
+        lap(1);
+      }
+
+      // ---------------- output layer (fold over units) + residual program
+      epi_sync();
+      for (int idx = tid; idx < 4 * NROW; idx += C::NEPI_T) {
+        const int n = idx % NROW, qq = idx / NROW;
+        const float* pr = part + (size_t)(qq * (WP / 4)) * C::PARTLD + n;
+        float s = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < WP / 4; ++r) s += pr[(size_t)r * C::PARTLD];
+        s_psum[qq * NROW + n] = s;
+      }
+      epi_sync();
+      if (warp == 0) {
+        const int pt = lane < NP ? lane : NP - 1;
+        const bool valid = lane < NP && s_z[pt * 4 + 3] != 0.f;
+        const long long gp = valid ? pbegin + pt : pbegin;
+        float z[1][3] = {{s_z[pt * 4], s_z[pt * 4 + 1], s_z[pt * 4 + 2]}};
+        float uo[K][1], f[1], df[K][1];
+        const float* auxp[1] = {L.aux ? (L.aux + gp * L.n_aux) : nullptr};
+        const float bl = __ldg(L.wpack + net.off_bl);
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const int n = c * NP + pt;
+          float s = (s_psum[n] + s_psum[NROW + n]) + (s_psum[2 * NROW + n] + s_psum[3 * NROW + n]);
+          s = net.epsil * (s + (c == 0 ? bl : 0.f));
+          if (L.base) s += __ldg(L.base + gp * K + c);
+          uo[c][0] = s;
+        }
+        vm_run<K, 1>(s_ops, L.prog.n_ops, s_consts, z, auxp, uo, f, df);
+        if (TRAIN) {
+          const float sc = valid ? __ldg(L.seg_scale + slot) : 0.f;
+          if (lane < NP) {
+#pragma unroll
+            for (int c = 0; c < K; ++c) s_ubar[c * NP + pt] = net.epsil * sc * f[0] * df[c][0];
+          }
+          if (valid) {
+            lcur += (double)f[0] * (double)f[0];
+            blacc += net.epsil * sc * f[0] * df[0][0];
+          }
+        } else if (valid) {
+          if (L.out_u) L.out_u[gp] = uo[0][0];
+          if (L.out_f) L.out_f[gp] = f[0];
+          if (L.out_jets) {
+#pragma unroll
+            for (int c = 0; c < K; ++c) L.out_jets[gp * K + c] = uo[c][0];
+          }
+        }
+      }
+      epi_sync();
+      lap(2);
+
+      // ---------------- backward.  Per layer l the epilogue warps run B1(l) (adjoint of the pre-activations -> G),
+      // B2(l) (the layer's input jets again -> Y) and the flush of the PREVIOUS layer's weight-gradient block,
+      // while the tensor core works on dgrad(l) and wgrad(l) (ping-pong weight-gradient blocks in TMEM).
+      if (TRAIN) {
+        const float wlv = __ldg(L.wpack + net.off_wl + u);
+#pragma unroll 1
+        for (int l = Lh - 1; l >= 0; --l) {
+          const int act = (l == 0) ? net.act_first : net.act_hidden;
+          float beta[3][8];
+          load_beta(beta);
+          {
+            // ---- B1(l)
+            float st[K][8], yb[K][8];
+            float d1[8], d2[8], d3[8];
+#pragma unroll
+            for (int c = 0; c < K; ++c) tc::ld8(stash_ptr(l, c), st[c]);
+            if (act == PINN_SIN) tc::ld8(stash_ptr(l, K), d1);
+            if (l < Lh - 1) {
+              tc::wait_bar(bar_fd, par_fd);  // dgrad(l+1)
+              par_fd ^= 1;
+              umma::fence_after_sync();
+              lap(7);
+              load_acc(yb);
+            }
+            tc::act8_bwd(act, st[0], d1, d2, d3);
+            if (l == Lh - 1) {
+              // seeds: ybar[c] = (epsil * ubar_c) * wl[u]; the output-layer weight gradient needs the layer outputs
+#pragma unroll
+              for (int c = 0; c < K; ++c) {
+                float ub[8];
+                tc::ld8(s_ubar + c * NP + 8 * n8, ub);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float o;
+                  if (c == 0) o = st[0][i];
+                  else if (c <= C::N1) o = d1[i] * st[c][i];
+                  else if (c <= C::N1 + C::N2) {
+                    const float Ai = st[c - C::N1][i];
+                    o = fmaf(d2[i] * Ai, Ai, d1[i] * st[c][i]);
+                  } else if (C::MIX == 1) o = fmaf(d2[i] * st[1][i], st[2][i], d1[i] * st[c][i]);
+                  else {
+                    float S = 0.f;
+#pragma unroll
+                    for (int k = 0; k < C::N1; ++k) S = fmaf(beta[k][i] * st[1 + k][i], st[1 + k][i], S);
+                    o = fmaf(d2[i], S, d1[i] * st[c][i]);
+                  }
+                  wlacc = fmaf(ub[i], o, wlacc);
+                  yb[c][i] = ub[i] * wlv;
+                }
+              }
+            }
+            tc::jets_adjoint<C>(yb, st, d1, d2, d3, beta);
+            float gb = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gb += yb[0][i];
+            s_bg[q * WP + u] = gb;
+            lap(3);
+            if (l > 0) {
+              if (l < Lh - 1) {
+                tc::wait_bar(bar_w, par_w);  // wgrad(l+1) has read G^(l+1) (R1) and Y^l (R2)
+                par_w ^= 1;
+                umma::fence_after_sync();
+                lap(5);
+              }
+#pragma unroll
+              for (int c = 0; c < K; ++c) tc::store_split8<SWB>(R1, C::PLANE1, u, c * PB + n8, WP, yb[c]);
+              operands_ready(TC_BAR_OP1);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int c = 0; c < K; ++c) {
+                  const float4 h = *reinterpret_cast<const float4*>(s_hj + ((8 * n8 + i) * K + c) * 4);
+                  const float t = net.scl * yb[c][i];
+                  w0acc[0] = fmaf(h.x, t, w0acc[0]);
+                  w0acc[1] = fmaf(h.y, t, w0acc[1]);
+                  w0acc[2] = fmaf(h.z, t, w0acc[2]);
+                }
+            }
+          }
+          lap(3);
+          if (l > 0) {
+            // ---- B2(l): the layer's input jets Y^(l-1) again (from the stash of layer l-1) -> R2
+            const int actp = (l - 1 == 0) ? net.act_first : net.act_hidden;
+            float st[K][8], d1[8], d2[8], d3[8];
+#pragma unroll
+            for (int c = 0; c < K; ++c) tc::ld8(stash_ptr(l - 1, c), st[c]);
+            if (actp == PINN_SIN) tc::ld8(stash_ptr(l - 1, K), d1);
+            tc::act8_bwd(actp, st[0], d1, d2, d3);
+            {
+              float y[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = st[0][i];
+              tc::jets_outputs<C>(st, y, d1, d2, beta);
+            }
+#pragma unroll
+            for (int c = 0; c < K; ++c) tc::store_split8<SWB>(R2, C::PLANE2, u, c * PB + n8, 128, st[c]);
+            operands_ready(TC_BAR_OP2);
+            lap(4);
+            // ---- F(l+1): flush the previous layer's weight-gradient block while dgrad(l) / wgrad(l) run
+            if (l < Lh - 1) flush_dw(l + 1);
+          } else if (Lh > 1) {
+            tc::wait_bar(bar_w, par_w);  // wgrad(1)
+            par_w ^= 1;
+            umma::fence_after_sync();
+            lap(5);
+            flush_dw(1);
+          }
+          lap(6);
+          // ---- bias gradient of layer l: fixed-order fold over the Q point blocks
+          epi_sync();
+          if (q == 0) {
+            float g = 0.f;
+#pragma unroll
+            for (int qq = 0; qq < Q; ++qq) g += s_bg[qq * WP + u];
+            gacc[net.off_b[l] + u] += g;
+          }
+          epi_sync();
+        }
+      }
+    }
+
+    // ---------------- per-CTA epilogue: fold the register accumulators in fixed order
+    if (TRAIN) {
+      const float vals[4] = {wlacc, w0acc[0], w0acc[1], w0acc[2]};
+#pragma unroll 1
+      for (int r = 0; r < 4; ++r) {
+        s_bg[q * WP + u] = vals[r];
+        epi_sync();
+        if (q == 0) {
+          float g = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < Q; ++qq) g += s_bg[qq * WP + u];
+          const int dst = (r == 0) ? net.off_wl + u : net.off_w0 + (r - 1) * WP + u;
+          gacc[dst] += g;
+        }
+        epi_sync();
+      }
+      if (warp == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          lcur += __shfl_xor_sync(0xffffffffu, lcur, o);
+          blacc += __shfl_xor_sync(0xffffffffu, blacc, o);
+        }
+        if (lane == 0) {
+          L.loss_part[(size_t)blockIdx.x * L.n_slots + slot] += lcur;
+          gacc[net.off_bl] += blacc;
+        }
+      }
+    }
+    if (prof) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) L.phase_clk[i] = pclk[i];
+    }
+  }
+
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == C::NEPI) umma::tmem_free(tb, 512);
+}

@@ -76,5 +76,9 @@ struct PinnLaunch {
   float* out_jets;         // eval: [n][K] or null
   int n_tiles;
   long long* phase_clk;    // optional [8] clock64 totals per phase (CTA 0, thread 0), else null
+  const void* wimg;        // tcgen05 family: pre-split bf16 weight images (stream of 4 KB chunks), else null
+  long long wimg_copy_bytes;  // bytes of one replica of the image stream
+  int wimg_copies;         // replicas (CTA b reads replica b % copies: spreads the stream over the L2 slices)
+  int ldw;                 // row stride of the hidden matrices in wpack / gacc
   PinnProgram prog;
 };

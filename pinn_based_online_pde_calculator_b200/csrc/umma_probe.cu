@@ -16,8 +16,8 @@ struct ProbeArgs {
   const float* B0;  // raw image of operand B
   const float* B1;  // second B image (second product, lanes +16; M = 64 only)
   int a_words, b_words;
-  int M, N, ksteps, a_mn, b_mn, nsets, reps, nd, a_lt, b_lt, a_tmem;
-  uint32_t a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step;
+  int M, N, ksteps, a_mn, b_mn, nsets, reps, nd, a_lt, b_lt, a_tmem, bf16;
+  uint32_t a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step, a_step2, b_step2;
   float* out;  // [128][512]
   long long* cycles;
   int* status;
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(ProbeArgs p) {
     umma::fence_after_sync();
   }
   if (tid == 0) {
-    const uint32_t idesc = umma::idesc_tf32(p.M, p.N, p.a_mn, p.b_mn);
+    const uint32_t idesc = p.bf16 ? umma::idesc_bf16(p.M, p.N, p.a_mn, p.b_mn) : umma::idesc_tf32(p.M, p.N, p.a_mn, p.b_mn);
     // descriptors precomputed; the issue loop only bumps the 14-bit start-address field
     const uint64_t a0 = umma::smem_desc(umma::smem_addr(As), p.a_lbo, p.a_sbo, p.a_lt);
     const uint64_t b0[2] = {umma::smem_desc(umma::smem_addr(Bs0), p.b_lbo, p.b_sbo, p.b_lt),
@@ -71,7 +71,15 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(ProbeArgs p) {
     for (int rep = 0; rep < p.reps; ++rep)
       for (int s = 0; s < p.nsets; ++s) {
         const uint32_t d = tb + ((uint32_t)(16 * s) << 16) + (uint32_t)((rep % nd) * p.N);
-        if (p.ksteps == 8 && !p.a_tmem) {
+        if (p.bf16) {
+          // k-step j sits at (j % 4) * step + (j / 4) * step2 when a second-level advance is given
+          const uint32_t da2 = p.a_step2 >> 4, db2 = p.b_step2 >> 4;
+          for (int j = 0; j < p.ksteps; ++j) {
+            const uint32_t oa = da2 ? (j & 3) * da + (j >> 2) * da2 : j * da;
+            const uint32_t ob = db2 ? (j & 3) * db + (j >> 2) * db2 : j * db;
+            umma::mma_bf16_ss(d, a0 + (uint64_t)oa, b0[s] + (uint64_t)ob, idesc, (rep >= nd || j) ? 1u : 0u);
+          }
+        } else if (p.ksteps == 8 && !p.a_tmem) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             umma::mma_tf32_ss(d, a0 + (uint64_t)(j * da), b0[s] + (uint64_t)(j * db), idesc, (rep >= nd || j) ? 1u : 0u);
@@ -117,7 +125,9 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(ProbeArgs p) {
 
 // cfg: [0] M, [1] N, [2] ksteps, [3] a_mn_major, [4] b_mn_major, [5] nsets, [6] reps, [7] a_words, [8] b_words,
 //      [9..11] A: lbo, sbo, k-step advance (bytes), [12..14] B: lbo, sbo, k-step advance, [15] accumulator regions (timing),
-//      [16], [17] swizzle layout type of A, B, [18] A operand from TMEM (A = row-major [128][8*ksteps])
+//      [16], [17] swizzle layout type of A, B, [18] A operand from TMEM (A = row-major [128][8*ksteps]),
+//      [19] 1 = kind::f16 with bf16 operands (images hold packed bf16 pairs, K = 16 per instruction),
+//      [20], [21] second-level k-step advance of A, B in bytes (0 = none)
 extern "C" int pinn_umma_probe(int device, const float* A, const float* B0, const float* B1, const int* cfg, float* out,
                                double* cycles, int* status) {
   CKP(cudaSetDevice(device));
@@ -143,7 +153,7 @@ extern "C" int pinn_umma_probe(int device, const float* A, const float* B0, cons
   p.A = dA; p.B0 = dB0; p.B1 = B1 ? dB1 : dB0;
   p.a_words = aw; p.b_words = bw;
   p.M = M; p.N = N; p.ksteps = cfg[2]; p.a_mn = cfg[3]; p.b_mn = cfg[4]; p.nsets = nsets; p.reps = cfg[6] < 1 ? 1 : cfg[6];
-  p.nd = cfg[15]; p.a_lt = cfg[16]; p.b_lt = cfg[17]; p.a_tmem = cfg[18]; p.a_lbo = cfg[9]; p.a_sbo = cfg[10]; p.a_step = cfg[11]; p.b_lbo = cfg[12]; p.b_sbo = cfg[13]; p.b_step = cfg[14];
+  p.nd = cfg[15]; p.a_lt = cfg[16]; p.b_lt = cfg[17]; p.a_tmem = cfg[18]; p.bf16 = cfg[19]; p.a_step2 = cfg[20]; p.b_step2 = cfg[21]; p.a_lbo = cfg[9]; p.a_sbo = cfg[10]; p.a_step = cfg[11]; p.b_lbo = cfg[12]; p.b_sbo = cfg[13]; p.b_step = cfg[14];
   p.out = dout; p.cycles = dcyc; p.status = dst;
   CKP(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_probe_kernel<<<1, 128, smem>>>(p);

@@ -209,7 +209,7 @@ class PinnEngine:
         self.n_params = int(self.lib.pinn_engine_num_params(h))
         self.n_info = int(self.lib.pinn_engine_num_loss_info(h))
         self.K = eq.K
-        self.kernel = ("simt_fp32", "mma_3xtf32", "umma_3xtf32")[int(self.lib.pinn_engine_kernel_kind(h))]
+        self.kernel = ("simt_fp32", "mma_3xtf32", "umma_3xtf32", "tc_bf16x3")[int(self.lib.pinn_engine_kernel_kind(h))]
         self._keep = []  # device tensors borrowed by the engine
         self.lref = 1.0
         self.lw = 1.0
@@ -268,6 +268,13 @@ class PinnEngine:
         if n != self.n_params:
             raise ValueError(f"expected {self.n_params} parameters, got {n}")
         _check(self.lib, self.lib.pinn_engine_set_params(self.h, _ptr(a), int(_is_device(a))))
+        if _is_device(a):
+            # the device-to-device copy runs on the engine's own stream: keep the (possibly temporary) source
+            # alive until it has completed, otherwise torch's caching allocator may hand it out again
+            self._param_src = a
+            if not getattr(self, "_shared_stream", False):
+                self.sync()
+                self._param_src = None
 
     def get_params(self) -> np.ndarray:
         out = np.empty(self.n_params, dtype=np.float32)

@@ -503,7 +503,12 @@ def linear_second_order(n: Node, d_in: int):
 
 def compile_equation(expr: str, d_in: int = 2, extended: bool = True, hoist: bool = True,
                      combine_second: bool = True) -> CompiledEquation:
-    ast = parse(expr, extended)
+    if not isinstance(expr, str):
+        raise EquationError(f"equation must be a string, got {type(expr).__name__}")
+    try:
+        ast = parse(expr, extended)
+    except (OverflowError, ZeroDivisionError, TypeError, ValueError) as e:  # constant folding left the reals
+        raise EquationError(f"constant sub-expression cannot be evaluated: {e}") from e
     firsts, seconds, aux = set(), set(), set()
     _collect(ast, d_in, firsts, seconds, aux)
     n_user = max(aux) + 1 if aux else 0
@@ -532,6 +537,8 @@ def compile_equation(expr: str, d_in: int = 2, extended: bool = True, hoist: boo
     target = ce.ops
 
     def const_index(v: float) -> int:
+        if isinstance(v, complex) or not math.isfinite(float(v)):
+            raise EquationError(f"constant sub-expression folds to {v!r}, not a finite real number")
         v = float(v)
         for i, c in enumerate(ce.consts):
             if c == v:

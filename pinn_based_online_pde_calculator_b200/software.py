@@ -270,12 +270,18 @@ def lbfgs_optimizer(model: Model, epoch: int, value_unnormalised: bool = True):
 
 
 # --------------------------------------------------------------------------- driver (sw:626-1139)
-def _compile_or_reference(equation: str, d_in: int, mode: str) -> CompiledEquation:
-    if mode != "reference":
+def _compile_or_reference(equation, d_in: int, mode: str) -> CompiledEquation:
+    """The reference ignores `equation` entirely (sw:627), so NOTHING the UI can put there may kill the
+    training thread: None (an untouched Dash input), non-strings and expressions whose constant folding
+    leaves the reals all fall back to the reference's hard-coded polar Laplacian."""
+    if mode != "reference" and isinstance(equation, str) and equation.strip():
         try:
             return compile_equation(equation, d_in=d_in)
-        except EquationError as e:
-            print(f"equation {equation!r} not compiled ({e}); using the reference's polar Laplacian", file=sys.stderr)
+        except Exception as e:  # EquationError, or anything a malformed expression provokes in the front end
+            print(f"equation {equation!r} not compiled ({type(e).__name__}: {e}); using the reference's polar Laplacian",
+                  file=sys.stderr)
+    elif mode != "reference":
+        print(f"equation {equation!r} is empty; using the reference's polar Laplacian", file=sys.stderr)
     return compile_equation(REFERENCE_POLAR_LAPLACE, d_in=d_in)
 
 

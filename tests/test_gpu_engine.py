@@ -210,6 +210,50 @@ def test_device_resident_points_and_params_roundtrip():
     eng.close()
 
 
+def test_adam_graph_follows_a_device_to_host_switch_of_the_point_set():
+    """the captured Adam graph bakes the point-set pointers by value.  set_points(device
+    tensors) -> adam_steps (captures) -> set_points(HOST arrays, same shapes, different data) must train on
+    the new points, not replay the graph against the old borrowed buffer."""
+    kw = dict(n_hidden=2, width=32, d_in=2, expr="u_xx + u_y", n_col=500, n_bd=40, n_bc=1, lb=[0, 0], ub=[1, 1])
+    pb, pb2 = make_problem(**kw), make_problem(**kw, seed=99)
+    p0 = O.ravel_params(pb["params"]).numpy().astype(np.float32)
+    f32 = lambda a: np.ascontiguousarray(a.numpy(), dtype=np.float32)
+    dev = lambda a: torch.as_tensor(a.numpy(), dtype=torch.float32).cuda()
+    eng = engine_for(pb)
+    keep = (dev(pb["x_col"]), [dev(a) for a in pb["x_bd"]], [dev(a) for a in pb["u_bd"]])
+    eng.set_points(*keep)
+    eng.adam_init()
+    eng.adam_steps(3, 1e-3)                      # graph captured against the borrowed device buffers
+    eng.set_points(f32(pb2["x_col"]), [f32(a) for a in pb2["x_bd"]], [f32(a) for a in pb2["u_bd"]])
+    eng.set_params(p0)
+    eng.adam_init()
+    rows = eng.adam_steps(3, 1e-3)
+    p_switched = eng.get_params()
+    eng.close()
+    fresh = engine_for(pb2)
+    fresh.adam_init()
+    rows_ref = fresh.adam_steps(3, 1e-3)
+    assert np.array_equal(rows, rows_ref)
+    assert np.array_equal(p_switched, fresh.get_params())
+    fresh.close()
+
+
+def test_global_counts_survive_a_resample_with_unchanged_shapes():
+    """multi-rank callers resample with set_points every 100 steps: the GLOBAL counts the means are taken over
+    must not silently fall back to the local ones (gradients would come out world times too large)."""
+    kw = dict(n_hidden=2, width=32, d_in=2, expr="u_xx + u_y", n_col=300, n_bd=20, n_bc=1, lb=[0, 0], ub=[1, 1])
+    pb = make_problem(**kw)
+    f32 = lambda a: np.ascontiguousarray(a.numpy(), dtype=np.float32)
+    eng = engine_for(pb)
+    g_local, _ = eng.loss_grad()
+    eng.set_global_counts(600, [40])
+    g_glob, _ = eng.loss_grad()
+    eng.set_points(f32(pb["x_col"]), [f32(a) for a in pb["x_bd"]], [f32(a) for a in pb["u_bd"]])
+    g_again, _ = eng.loss_grad()
+    assert torch.equal(g_again, g_glob) and not torch.equal(g_glob, g_local)
+    eng.close()
+
+
 def test_prefetch_commit_equals_set_points():
     """pinn_engine_prefetch_points / commit_points (pipelined refresh of the point set) must give the
     same bits as set_points on the same host arrays, and reject mismatching shapes."""

@@ -151,3 +151,19 @@ def test_adam_schedule_events(capsys):
     err = capsys.readouterr().err
     assert "Step: 100 | Loss: " in err and "learning rate for Adam: 5.0000e-04" in err
     assert len(loss) >= 4100
+
+
+def test_equation_front_end_never_raises_for_ui_input():
+    """The reference ignores `equation` (software.py:627): None (an untouched Dash input), non-strings and
+    expressions whose constants fold out of the reals must fall back to the polar Laplacian instead of
+    killing the daemon training thread (callbacks/training.py:111)."""
+    from pinn_based_online_pde_calculator_b200.equation import EquationError, compile_equation
+
+    ref = sw._compile_or_reference(sw.REFERENCE_POLAR_LAPLACE, 2, "compile")
+    for bad in (None, "", "   ", 17, "test equation", "u_xx + (-8)**(1/3)*u", "u_xx + (("):
+        ce = sw._compile_or_reference(bad, 2, "compile")
+        assert ce.ops == ref.ops and ce.consts == ref.consts, bad
+    with pytest.raises(EquationError):
+        compile_equation("u_xx + (-8)**(1/3)*u", d_in=2)
+    with pytest.raises(EquationError):
+        compile_equation(None, d_in=2)

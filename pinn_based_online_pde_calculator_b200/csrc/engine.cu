@@ -272,7 +272,14 @@ static int create_impl(pinn_engine* h, const pinn_spec_t* spec, int device) {
   CK(cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;
   h->grid_max_col = h->num_sms * occ_col;
+  if (const char* g = getenv("PINN_TC_GRID")) {  // experiment knob: cap the collocation grid of the tcgen05 family
+    if (h->kcol->kind == 3 && atoi(g) > 0) h->grid_max_col = std::min(h->grid_max_col, atoi(g));
+  }
   h->grid_max_bc = h->num_sms * occ_bc;
+  // tcgen05 family: one row of (stash, gradient accumulators) per SM only -- the boundary term (~1 % of the
+  // points) gets one CTA per SM too, so that the whole per-CTA scratch (C4: 148 x 0.85 MB) stays a window the
+  // 126 MB L2 can hold instead of being diluted over rows the collocation kernel never touches
+  if (h->kcol->kind == 3) h->grid_max_bc = h->num_sms;
   h->grid_max = std::max(h->grid_max_col, h->grid_max_bc);
   {
     const char* kenv = getenv("PINN_B200_KERNEL");
@@ -427,7 +434,12 @@ static void apply_l2_policy(pinn_engine* h) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return;
   if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
-  const size_t bytes = (h->stash_floats + h->gacc_floats) * sizeof(float);
+  // what the window covers: the whole per-CTA scratch [stash | gradient accumulators] (default), or only one of
+  // the two regions (PINN_B200_L2_WINDOW = both | gacc | stash; experiment knob for scratch sets near the L2 size)
+  const char* wsel = getenv("PINN_B200_L2_WINDOW");
+  const bool only_gacc = wsel && !strcmp(wsel, "gacc"), only_stash = wsel && !strcmp(wsel, "stash");
+  char* base = reinterpret_cast<char*>(only_gacc ? h->d_gacc : h->d_stash);
+  const size_t bytes = (only_gacc ? h->gacc_floats : only_stash ? h->stash_floats : h->stash_floats + h->gacc_floats) * sizeof(float);
   const size_t carve = std::min<size_t>(bytes, (size_t)prop.persistingL2CacheMaxSize);
   {
     std::lock_guard<std::mutex> lk(g_l2_mu);
@@ -439,11 +451,13 @@ static void apply_l2_policy(pinn_engine* h) {
   }
   cudaStreamAttrValue attr;
   memset(&attr, 0, sizeof attr);
-  attr.accessPolicyWindow.base_ptr = h->d_stash;
+  attr.accessPolicyWindow.base_ptr = base;
   attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
   attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)attr.accessPolicyWindow.num_bytes);
   attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  // lines of the window that do not get the persisting property stay NORMAL (not streaming / evict-first): for a
+  // scratch just above the carve-out an evict-first remainder thrashes (measured on C4: 35.2 ms vs 31.2 ms)
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
   if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
   if (getenv("PINN_B200_DEBUG"))
     fprintf(stderr, "[pinn] L2 window: %.1f MB of %.1f MB (persisting max %.1f MB, window max %.1f MB, L2 %.1f MB)\n",
@@ -470,7 +484,11 @@ extern "C" int pinn_engine_sync(pinn_engine_t* h) {
 extern "C" int64_t pinn_engine_num_params(pinn_engine_t* h) { return h->fmap.n_params; }
 extern "C" int32_t pinn_engine_num_loss_info(pinn_engine_t* h) { return h->n_info; }
 extern "C" int32_t pinn_engine_tile_points(pinn_engine_t* h) { return h->kcol->tile_points; }
-extern "C" int32_t pinn_engine_launches_per_eval(pinn_engine_t* h) { return 6; }
+// kernels one evaluation enqueues (memsets and the NCCL allreduce not counted): pack, [weight images], [boundary
+// kernel], collocation kernel, gradient reduce, loss reduce, loss_info; an Adam step adds k_adam
+extern "C" int32_t pinn_engine_launches_per_eval(pinn_engine_t* h) {
+  return 5 + (h->kcol->kind == 3 ? 1 : 0) + (h->use_umma ? 1 : 0) + ((h->points_set && h->Lbc.n_tiles > 0) ? 1 : 0);
+}
 extern "C" int32_t pinn_engine_kernel_kind(pinn_engine_t* h) { return h->use_umma ? 2 : h->kcol->kind; }
 
 extern "C" int pinn_engine_set_params(pinn_engine_t* h, const float* flat, int on_device) {
@@ -1031,18 +1049,20 @@ extern "C" int pinn_engine_phase_profile(pinn_engine_t* h, int64_t* out8) {
   cudaStream_t st = h->stream;
   const int P = h->fmap.n_params;
   long long* d = nullptr;
-  CK(cudaMalloc(&d, 8 * sizeof(long long)));
-  CK(cudaMemsetAsync(d, 0, 8 * sizeof(long long), st));
+  CK(cudaMalloc(&d, 16 * sizeof(long long)));
+  CK(cudaMemsetAsync(d, 0, 16 * sizeof(long long), st));
   if (enqueue_pack(h, nullptr, st)) return 1;
   CK(cudaMemsetAsync(h->d_gacc, 0, sizeof(float) * (size_t)h->grid_col * h->net.pg, st));
   CK(cudaMemsetAsync(h->d_loss_part, 0, sizeof(double) * (size_t)h->grid_col * h->n_slots, st));
   PinnLaunch L = h->Lcol;
   L.phase_clk = d;
   CK(h->kcol->launch(L, true, h->grid_col, st));
-  long long host[8];
+  long long host[16];
   CK(cudaMemcpyAsync(host, d, sizeof host, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   cudaFree(d);
+  if (getenv("PINN_B200_DEBUG"))  // tcgen05 family: GEMM durations seen by the issuing lane (fwd, dgrad incl. queueing, wgrad)
+    fprintf(stderr, "[pinn] GEMM clocks: fwd %lld dgrad %lld wgrad %lld\n", host[8], host[9], host[10]);
   for (int i = 0; i < 8; ++i) out8[i] = host[i];
   return 0;
 }

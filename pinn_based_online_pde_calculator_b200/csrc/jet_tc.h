@@ -5,7 +5,7 @@
 
 #include "pinn_common.h"
 
-#define PINN_TC_IMAGE_COPIES 16  // replicas of the stream (each CTA reads replica blockIdx % copies)
+#define PINN_TC_IMAGE_COPIES 2  // replicas of the stream (each CTA reads replica blockIdx % copies)
 // bytes of ONE replica of the image stream for `net` (forward + data-gradient image per hidden GEMM layer)
 size_t jet_tc_image_bytes(const PinnNet& net);
 // build the stream from the fp32 weight pack (row stride ldw): one launch per evaluation

@@ -10,7 +10,9 @@
 using Cfg = TcCfg<J_WP, J_N1, J_N2, J_MIX>;
 
 static cudaError_t launch_impl(const PinnLaunch& L, bool train, int grid, cudaStream_t stream) {
-  if (train)
+  if (train && L.phase_clk)
+    jet_tc_kernel<Cfg, true, true><<<grid, Cfg::NT, Cfg::smem_bytes(), stream>>>(L);   // phase-clock instantiation
+  else if (train)
     jet_tc_kernel<Cfg, true><<<grid, Cfg::NT, Cfg::smem_bytes(), stream>>>(L);
   else
     jet_tc_kernel<Cfg, false><<<grid, Cfg::NT, Cfg::smem_bytes(), stream>>>(L);
@@ -19,6 +21,8 @@ static cudaError_t launch_impl(const PinnLaunch& L, bool train, int grid, cudaSt
 
 static cudaError_t prepare_impl(int* ctas_per_sm) {
   cudaError_t e = cudaFuncSetAttribute(jet_tc_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes());
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(jet_tc_kernel<Cfg, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes());
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(jet_tc_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes());
   if (ctas_per_sm) *ctas_per_sm = 1;  // one CTA per SM: all 512 TMEM columns, ~225 KB of shared memory

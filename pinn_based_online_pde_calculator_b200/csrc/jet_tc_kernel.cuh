@@ -40,27 +40,34 @@ struct TcCfg {
   static constexpr int MB = WP / 128;                        // M blocks (128 units each)
   static constexpr int NP = (WP == 128 && K <= 4) ? 32 : 16;  // points per tile
   static constexpr int Q = NP / 8;                           // epilogue warps per lane quadrant (8 points each)
+  static constexpr int V = 4;                                // points an epilogue thread holds in registers at a time
   static constexpr int NROW = NP * K;                        // N of the forward / data-gradient MMAs
   static constexpr int SWB = (NROW % 64 == 0) ? 128 : 32;    // swizzle span (bytes per line) of the activation tiles
   static constexpr int NBLK = (NROW * 2 + SWB - 1) / SWB;    // n-blocks per plane
   static constexpr int PLANE1 = NBLK * WP * SWB;             // region 1: all WP lines
   static constexpr int PLANE2 = NBLK * 128 * SWB;            // region 2: one block of 128 lines
-  static constexpr int R1_BYTES = 3 * PLANE1, R2_BYTES = 3 * PLANE2;
+  static constexpr int YP = 2;                               // planes of the recomputed layer input (weight gradient only)
+  // [y0 | y1] as ONE N = 2*NROW operand (four MMAs per k-step instead of six).  Measured on C4: no gain (the tensor
+  // pipe is not the limiter) and three truncating adds per k-step in the leading accumulator instead of one
+  // (u 2.3e-7 -> 7.9e-7, gradient 6.9e-7 -> 1.2e-6), so it stays off.
+  static constexpr bool CONCAT = false;
+  static constexpr int R1_BYTES = 3 * PLANE1, R2_BYTES = YP * PLANE2;
   static constexpr int NEPI = 4 * Q;
   static constexpr int NEPI_T = NEPI * 32;
   static constexpr int NT = NEPI_T + 64;                     // + MMA-issue warp + producer warp
   static constexpr int KS = WP / 16;                         // k-steps of the forward / data-gradient GEMMs
   static constexpr int KSW = NROW / 16;                      // k-steps of the weight-gradient GEMM
-  static constexpr int SLOT = 4096;                          // one (k-step, plane) weight image: 128 rows x 32 B
-  static constexpr int NSLOT = 6;
-  static constexpr int CHUNKS = MB * KS * 3;                 // ring chunks per forward / data-gradient GEMM
+  static constexpr int PLANE_W = 4096;                       // one weight plane of a k-step: 128 rows x 32 B
+  static constexpr int SLOT = 3 * PLANE_W;                   // ring stage = one k-step, planes b2 | b1 | b0
+  static constexpr int NSLOT = 4;
+  static constexpr int CHUNKS = MB * KS;                     // ring stages per forward / data-gradient GEMM
   static constexpr int PARTLD = NROW + 4;                    // row stride of the output-layer partial products
-  // TMEM columns: per M block (big | small) accumulators, then the weight-gradient block
+  // TMEM columns: per M block (big | small) accumulators, then two weight-gradient blocks (ping-pong)
   __host__ __device__ static constexpr int TC_D(int mb) { return mb * 2 * NROW; }
-  static constexpr int TC_DW = MB * 2 * NROW;                // two weight-gradient blocks (ping-pong) of 128 columns
+  static constexpr int TC_DW = MB * 2 * NROW;
   static constexpr int TC_USED = TC_DW + 256;
   static constexpr int MISC_FLOATS = NP * 4 /*z*/ + 3 * NP /*beta*/ + NP * K * 4 /*hj*/ + NROW /*ubar*/ + 4 * NROW /*psum*/ +
-                                     Q * WP /*bias-gradient partials*/ + PINN_MAX_OPS + PINN_MAX_CONSTS;
+                                     Q * WP /*gradient partials*/ + PINN_MAX_OPS + PINN_MAX_CONSTS;
   static constexpr size_t smem_bytes() { return (size_t)R1_BYTES + R2_BYTES + NSLOT * SLOT + MISC_FLOATS * 4 + 256; }
   static constexpr size_t STL = (size_t)(K + 1) * WP * NP;   // stash floats per layer and CTA (K jets + cos for the sin activation)
   static constexpr bool OK = (NROW % 16 == 0) && (NROW <= 256) && (TC_USED <= 512) && (smem_bytes() <= 232448 - 1024) &&
@@ -69,18 +76,21 @@ struct TcCfg {
 
 namespace tc {
 
-// ---- bf16x3 split of a pair (x0 -> lower half, x1 -> upper half); every residual is exact
+// ---- bf16 split of a pair (x0 -> lower half, x1 -> upper half); every residual is exact
 __device__ __forceinline__ uint32_t cvt_bf16x2(float lo_elem, float hi_elem) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
   return r;
 }
-__device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
-  p0 = cvt_bf16x2(x0, x1);
-  const float r0 = x0 - __uint_as_float(p0 << 16), r1 = x1 - __uint_as_float(p0 & 0xffff0000u);
-  p1 = cvt_bf16x2(r0, r1);
-  const float s0 = r0 - __uint_as_float(p1 << 16), s1 = r1 - __uint_as_float(p1 & 0xffff0000u);
-  p2 = cvt_bf16x2(s0, s1);
+template <int NPL>
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t (&p)[3]) {
+  p[0] = cvt_bf16x2(x0, x1);
+  const float r0 = x0 - __uint_as_float(p[0] << 16), r1 = x1 - __uint_as_float(p[0] & 0xffff0000u);
+  p[1] = cvt_bf16x2(r0, r1);
+  if (NPL > 2) {
+    const float s0 = r0 - __uint_as_float(p[1] << 16), s1 = r1 - __uint_as_float(p[1] & 0xffff0000u);
+    p[2] = cvt_bf16x2(s0, s1);
+  }
 }
 
 // byte offset of the 16-byte chunk (line, n8 = n / 8) inside a plane of `lines` lines
@@ -98,30 +108,27 @@ __device__ __forceinline__ uint32_t kmajor_koff(int ks, int lines) {
 template <int SWB>
 __device__ __forceinline__ constexpr uint32_t layout_type() { return SWB == 128 ? 2u : 6u; }
 
-// split 8 values and store them as one chunk per plane
-template <int SWB>
-__device__ __forceinline__ void store_split8(uint8_t* region, int plane_bytes, int line, int n8, int lines, const float (&v)[8]) {
-  uint32_t p0[4], p1[4], p2[4];
+// split 4 values (half h of the 8-element chunk) and store them into NPL planes
+template <int NPL>
+__device__ __forceinline__ void store_split4(uint8_t* chunk, int plane_bytes, int h, const float (&v)[4]) {
+  uint32_t a[3], b[3];
+  split_pair<NPL>(v[0], v[1], a);
+  split_pair<NPL>(v[2], v[3], b);
+  uint8_t* d = chunk + 8 * h;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) split3_pair(v[2 * j], v[2 * j + 1], p0[j], p1[j], p2[j]);
-  uint8_t* d = region + chunk_off<SWB>(line, n8, lines);
-  *reinterpret_cast<uint4*>(d) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
-  *reinterpret_cast<uint4*>(d + plane_bytes) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-  *reinterpret_cast<uint4*>(d + 2 * plane_bytes) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+  for (int p = 0; p < NPL; ++p) *reinterpret_cast<uint2*>(d + p * plane_bytes) = make_uint2(a[p], b[p]);
 }
 
-// inline sin/cos: three-constant Cody-Waite reduction by pi/2 + minimax polynomials on [-pi/4, pi/4]
-// (about 1 ulp); huge arguments take the library path
-__device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
-  if (fabsf(x) > 3.0e4f) {
-    sincos_ni(x, &s, &c);
-    return;
-  }
-  const float k = rintf(x * 0.636619772f);
+// inline sin/cos, fast path only: three-constant Cody-Waite reduction by pi/2 (quadrant from the magic-number
+// rounding trick, no conversion instructions) + minimax polynomials on [-pi/4, pi/4] (about 1 ulp for
+// |x| <= 3e4); straight-line code, so the V evaluations of a thread interleave
+__device__ __forceinline__ void sincos_fast(float x, float& s, float& c) {
+  const float kf = fmaf(x, 0.636619772f, 12582912.0f);   // 1.5 * 2^23: the integer lands in the low mantissa bits
+  const int q = __float_as_int(kf);
+  const float k = kf - 12582912.0f;
   float r = fmaf(k, -1.57079601e+00f, x);
   r = fmaf(k, -3.13916473e-07f, r);
   r = fmaf(k, -5.39030253e-15f, r);
-  const int q = __float2int_rn(k);
   const float r2 = r * r;
   float sp = fmaf(r2, -1.95152959e-4f, 8.33216087e-3f);
   sp = fmaf(sp, r2, -1.66666546e-1f);
@@ -135,48 +142,60 @@ __device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
   c = ((q + 1) & 2) ? -cc : cc;
 }
 
-// y, s' and s'' (derivatives of the activation) of 8 pre-activations.  The backward pass needs no pre-activation
-// again: it restarts from the stashed y (tanh: s' = 1 - y^2 ...) or from the stashed (sin, cos) pair.
-__device__ __forceinline__ void act8_fwd(int act, const float (&a)[8], float (&y)[8], float (&d1)[8], float (&d2)[8]) {
+// y and the first two derivatives of the activation for V pre-activations.  The backward pass needs no
+// pre-activation again: it restarts from the stashed y (tanh) or from the stashed (sin, cos) pair.
+template <int V>
+__device__ __forceinline__ void act_fwd(int act, const float (&a)[V], float (&y)[V], float (&d1)[V], float (&d2)[V]) {
   if (act == PINN_TANH) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < V; ++i) {
       const float t = tanh_bf(a[i]);
       y[i] = t;
       d1[i] = fmaf(-t, t, 1.0f);
       d2[i] = -2.0f * t * d1[i];
     }
   } else {
+    bool huge = false;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < V; ++i) {
       float sn, cs;
-      sincos_cw(a[i], sn, cs);
+      sincos_fast(a[i], sn, cs);
       y[i] = sn; d1[i] = cs; d2[i] = -sn;
+      huge |= fabsf(a[i]) > 3.0e4f;
+    }
+    if (huge) {  // rare: arguments beyond the range of the three-constant reduction take the library path
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float sn, cs;
+        sincos_ni(a[i], &sn, &cs);
+        y[i] = sn; d1[i] = cs; d2[i] = -sn;
+      }
     }
   }
 }
-// first, second and third derivative of the activation from the stashed output y (for sin: d1 holds the stashed cos)
-__device__ __forceinline__ void act8_bwd(int act, const float (&y)[8], float (&d1)[8], float (&d2)[8], float (&d3)[8]) {
+// first, second (and third) derivative of the activation from the stashed output y (for sin: d1 holds the stashed cos)
+template <int V, bool D3>
+__device__ __forceinline__ void act_bwd(int act, const float (&y)[V], float (&d1)[V], float (&d2)[V], float (&d3)[V]) {
   if (act == PINN_TANH) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < V; ++i) {
       const float t = y[i];
       d1[i] = fmaf(-t, t, 1.0f);
       d2[i] = -2.0f * t * d1[i];
-      d3[i] = d1[i] * fmaf(6.0f * t, t, -2.0f);
+      if (D3) d3[i] = d1[i] * fmaf(6.0f * t, t, -2.0f);
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { d2[i] = -y[i]; d3[i] = -d1[i]; }
+    for (int i = 0; i < V; ++i) { d2[i] = -y[i]; if (D3) d3[i] = -d1[i]; }
   }
 }
 
 // pre-activation jets a[1..K-1] (a[0] is overwritten with y) -> output jets, in place
-template <class C>
-__device__ __forceinline__ void jets_outputs(float (&a)[C::K][8], const float (&y)[8], const float (&d1)[8], const float (&d2)[8],
-                                             const float (&beta)[3][8]) {
+template <class C, int V>
+__device__ __forceinline__ void jets_outputs(float (&a)[C::K][V], const float (&y)[V], const float (&d1)[V], const float (&d2)[V],
+                                             const float (&beta)[3][V]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < V; ++i) {
 #pragma unroll
     for (int k = 0; k < C::N2; ++k) {
       const float Ai = a[1 + k][i];
@@ -195,13 +214,13 @@ __device__ __forceinline__ void jets_outputs(float (&a)[C::K][8], const float (&
   }
 }
 
-// adjoint of the activation jets: yb = adjoint of the layer outputs (in), st = stashed pre-activation jets;
-// on return yb holds the adjoint of the pre-activations
-template <class C>
-__device__ __forceinline__ void jets_adjoint(float (&yb)[C::K][8], const float (&st)[C::K][8], const float (&d1)[8], const float (&d2)[8],
-                                             const float (&d3)[8], const float (&beta)[3][8]) {
+// adjoint of the activation jets: yb = adjoint of the layer outputs (in), st = stashed jets (st[0] = y, st[c>0] =
+// pre-activation jets); on return yb holds the adjoint of the pre-activations
+template <class C, int V>
+__device__ __forceinline__ void jets_adjoint(float (&yb)[C::K][V], const float (&st)[C::K][V], const float (&d1)[V], const float (&d2)[V],
+                                             const float (&d3)[V], const float (&beta)[3][V]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < V; ++i) {
     float ab0 = d1[i] * yb[0][i];
     float ab1[C::N1 > 0 ? C::N1 : 1];
 #pragma unroll
@@ -244,18 +263,19 @@ __device__ __forceinline__ void jets_adjoint(float (&yb)[C::K][8], const float (
   }
 }
 
-__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
 }
-__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 
 // bounded mbarrier wait: a protocol bug traps (launch failure) instead of hanging the GPU
 __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
   if (!umma::mbar_wait(bar, parity, 1u << 24)) __trap();
+}
+// TMA bulk prefetch of a contiguous global range into L2 (no destination, no completion tracking)
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -264,18 +284,17 @@ __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("ba
 
 enum { TC_BAR_EPI = 1, TC_BAR_OP1 = 2, TC_BAR_OP2 = 3 };
 
-
 // ---------------------------------------------------------------- the kernel
-template <class C, bool TRAIN>
+template <class C, bool TRAIN, bool PROF = false>
 __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant__ PinnLaunch L) {
   static_assert(C::OK, "invalid tcgen05 kernel configuration");
-  constexpr int K = C::K, WP = C::WP, NP = C::NP, Q = C::Q, NROW = C::NROW, SWB = C::SWB;
-  constexpr int NSLOT = C::NSLOT, PB = NP / 8;
+  constexpr int K = C::K, WP = C::WP, NP = C::NP, Q = C::Q, NROW = C::NROW, SWB = C::SWB, V = C::V;
+  constexpr int NSLOT = C::NSLOT, PB = NP / 8, NH = 8 / V;
   constexpr uint32_t LT = tc::layout_type<SWB>();
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   uint8_t* const smem = tc_smem;
-  uint8_t* const R1 = smem;                                    // forward: layer input Y; backward: adjoints G
-  uint8_t* const R2 = smem + C::R1_BYTES;                      // backward: recomputed layer input Y (128-line block)
+  uint8_t* const R1 = smem;                                    // forward: layer input Y; backward: adjoints G (3 planes)
+  uint8_t* const R2 = smem + C::R1_BYTES;                      // backward: recomputed layer input Y (2 planes, 128 lines)
   uint8_t* const ring = R2 + C::R2_BYTES;                      // weight-image ring
   float* const s_z = reinterpret_cast<float*>(ring + NSLOT * C::SLOT);  // [NP][4]: coordinates, valid flag
   float* const s_beta = s_z + NP * 4;                          // [3][NP]
@@ -314,9 +333,8 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
 
   if (warp == C::NEPI + 1) {
     // ================================================================ producer: weight-image stream
-    // Every CTA walks the same chunk sequence at about the same time; one copy of the images would be served
-    // by the handful of L2 slices a 4 KB chunk maps to (measured: 7.9 B/cycle/SM).  The engine keeps
-    // `wimg_copies` replicas at different addresses and each CTA reads replica blockIdx % copies.
+    // One 12 KB stage = the three bf16 planes of one k-step.  Each CTA reads replica blockIdx % copies of the
+    // image stream (every CTA walks the same sequence at about the same time).
     if (lane == 0) {
       const uint8_t* img = reinterpret_cast<const uint8_t*>(L.wimg) + (size_t)(blockIdx.x % L.wimg_copies) * L.wimg_copy_bytes;
       const int per_tile = (TRAIN ? 2 : 1) * NG * C::CHUNKS;
@@ -328,6 +346,14 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
         if (round > 0) tc::wait_bar(&bar_empty[s], (round - 1) & 1);
         mbar_expect_tx(&bar_full[s], C::SLOT);
         bulk_g2s(ring + s * C::SLOT, img + (size_t)c * C::SLOT, C::SLOT, &bar_full[s]);
+        if (TRAIN && c >= NG * C::CHUNKS && c % C::CHUNKS == 0) {
+          // first stage of dgrad(l): pull what the epilogue warps touch one layer later into L2 -- the stash of layer
+          // l-1 (B2(l), B1(l-1)) and the accumulator block of layer l (flushed during iteration l-1).  The per-CTA
+          // scratch of all SMs together is about the size of the L2, so a part of it lives in HBM between uses.
+          const int l = (Lh - 1) - (c / C::CHUNKS - NG);
+          tc::prefetch_l2(L.stash + ((size_t)blockIdx.x * Lh + (l - 1)) * C::STL, (uint32_t)(C::STL * 4));
+          tc::prefetch_l2(L.gacc + (size_t)blockIdx.x * net.pg + net.off_w[l], (uint32_t)(128 * L.ldw * 4));
+        }
         if (++c == per_tile) c = 0;
       }
     }
@@ -335,81 +361,100 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     // ================================================================ MMA issue warp
     long long ci = 0;
     const uint32_t id_wx = umma::idesc_bf16(128, NROW, 0, 1);
+    const uint32_t id_wx2 = umma::idesc_bf16(128, C::CONCAT ? 2 * NROW : NROW, 0, 1);
     const uint32_t id_wg = umma::idesc_bf16(128, 128, 0, 0);
     const uint32_t r1a = umma::smem_addr(R1), r2a = umma::smem_addr(R2), rga = umma::smem_addr(ring);
-    // D (big | small) = W x act(R1), weights from the ring
+    // D = W x act(R1), weights from the ring.  Per k-step FOUR MMAs: the activation planes b0 and b1 lie back to
+    // back in shared memory, so ONE descriptor with N = 2*NROW reads [y0 | y1] and W_p x [y0 | y1] (p = 2, 1, 0) yields
+    // the columns [sum_p w_p*y0 | sum_p w_p*y1] at the N = 256 rate (128 cycles instead of 2 x 103); the sixth
+    // product w0*y2 goes into the second block.  The epilogue adds the two blocks with a round-to-nearest add
+    // (two-level accumulation; the extra w2*y1 term is 2^-24 of the leading one).
     auto gemm_wx = [&]() {
       for (int mb = 0; mb < C::MB; ++mb) {
         const uint32_t DB = tb + C::TC_D(mb), DS = DB + NROW;
         for (int ks = 0; ks < C::KS; ++ks) {
-          uint64_t bd[3];
-#pragma unroll
-          for (int p = 0; p < 3; ++p) bd[p] = umma::smem_desc(r1a + p * C::PLANE1 + ks * 16 * SWB, WP * SWB, 8 * SWB, LT);
+          const uint64_t b01 = umma::smem_desc(r1a + ks * 16 * SWB, WP * SWB, 8 * SWB, LT);
+          const uint64_t b2 = umma::smem_desc(r1a + 2 * C::PLANE1 + ks * 16 * SWB, WP * SWB, 8 * SWB, LT);
           const uint32_t acc = ks > 0 ? 1u : 0u;
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {  // weight planes b2, b1, b0 (small products first)
-            const int s = (int)(ci % NSLOT);
-            tc::wait_bar(&bar_full[s], (uint32_t)((ci / NSLOT) & 1));
-            umma::fence_after_sync();
-            const uint64_t ad = umma::smem_desc(rga + s * C::SLOT, 16, 256, 6);
-            if (j == 0) {
-              umma::mma_bf16_ss(DS, ad, bd[0], id_wx, acc);
-            } else if (j == 1) {
-              umma::mma_bf16_ss(DS, ad, bd[1], id_wx, 1u);
-              umma::mma_bf16_ss(DS, ad, bd[0], id_wx, 1u);
-            } else {
-              umma::mma_bf16_ss(DS, ad, bd[2], id_wx, 1u);
-              umma::mma_bf16_ss(DS, ad, bd[1], id_wx, 1u);
-              umma::mma_bf16_ss(DB, ad, bd[0], id_wx, acc);
-            }
-            umma::commit(&bar_empty[s]);
-            ++ci;
+          const int s = (int)(ci % NSLOT);
+          tc::wait_bar(&bar_full[s], (uint32_t)((ci / NSLOT) & 1));
+          umma::fence_after_sync();
+          const uint64_t w2 = umma::smem_desc(rga + s * C::SLOT, 16, 256, 6);
+          const uint64_t w1 = umma::smem_desc(rga + s * C::SLOT + C::PLANE_W, 16, 256, 6);
+          const uint64_t w0 = umma::smem_desc(rga + s * C::SLOT + 2 * C::PLANE_W, 16, 256, 6);
+          if (C::CONCAT) {
+            umma::mma_bf16_ss(DB, w2, b01, id_wx2, acc);
+            umma::mma_bf16_ss(DB, w1, b01, id_wx2, 1u);
+            umma::mma_bf16_ss(DB, w0, b01, id_wx2, 1u);
+            umma::mma_bf16_ss(DS, w0, b2, id_wx, 1u);
+          } else {
+            const uint64_t b1 = umma::smem_desc(r1a + C::PLANE1 + ks * 16 * SWB, WP * SWB, 8 * SWB, LT);
+            umma::mma_bf16_ss(DS, w2, b01, id_wx, acc);
+            umma::mma_bf16_ss(DS, w1, b1, id_wx, 1u);
+            umma::mma_bf16_ss(DS, w1, b01, id_wx, 1u);
+            umma::mma_bf16_ss(DS, w0, b2, id_wx, 1u);
+            umma::mma_bf16_ss(DS, w0, b1, id_wx, 1u);
+            umma::mma_bf16_ss(DB, w0, b01, id_wx, acc);
           }
+          umma::commit(&bar_empty[s]);
+          ++ci;
         }
       }
       umma::commit(bar_fd);
     };
-    // DW[out][in] = sum_n G[out][n] * Y[in][n]: G in R1 (M rows = output units: the flush then writes the
-    // gradient rows with coalesced stores), Y block in R2, both K-major views
+    // DW[out][in] = sum_n G[out][n] * Y[in][n]: G in R1 (M rows = output units: the flush then writes the gradient
+    // with coalesced accesses), Y block in R2 (two planes), both K-major views; five products (everything down
+    // to 2^-16 of the leading term; the sum over the points averages the remaining rounding noise)
     auto gemm_wgrad = [&](int buf) {
       const uint32_t DW = tb + C::TC_DW + 128 * buf;
       for (int ks = 0; ks < C::KSW; ++ks) {
-        uint64_t ag[3], by[3];
+        uint64_t ag[3], by[2];
 #pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          ag[p] = umma::smem_desc(r1a + p * C::PLANE1 + tc::kmajor_koff<SWB>(ks, WP), 16, 8 * SWB, LT);
-          by[p] = umma::smem_desc(r2a + p * C::PLANE2 + tc::kmajor_koff<SWB>(ks, 128), 16, 8 * SWB, LT);
-        }
-        umma::mma_bf16_ss(DW, ag[0], by[2], id_wg, ks > 0 ? 1u : 0u);
-        umma::mma_bf16_ss(DW, ag[2], by[0], id_wg, 1u);
+        for (int p = 0; p < 3; ++p) ag[p] = umma::smem_desc(r1a + p * C::PLANE1 + tc::kmajor_koff<SWB>(ks, WP), 16, 8 * SWB, LT);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) by[p] = umma::smem_desc(r2a + p * C::PLANE2 + tc::kmajor_koff<SWB>(ks, 128), 16, 8 * SWB, LT);
+        umma::mma_bf16_ss(DW, ag[2], by[0], id_wg, ks > 0 ? 1u : 0u);
         umma::mma_bf16_ss(DW, ag[1], by[1], id_wg, 1u);
-        umma::mma_bf16_ss(DW, ag[0], by[1], id_wg, 1u);
         umma::mma_bf16_ss(DW, ag[1], by[0], id_wg, 1u);
+        umma::mma_bf16_ss(DW, ag[0], by[1], id_wg, 1u);
         umma::mma_bf16_ss(DW, ag[0], by[0], id_wg, 1u);
       }
       umma::commit(bar_w);
     };
+    // PROF: the issuing lane also waits for each GEMM and accumulates its duration (slots 8 fwd, 9 dgrad, 10 wgrad)
+    const bool mprof = PROF && (L.phase_clk != nullptr) && blockIdx.x == 0 && lane == 0;
+    long long gclk[3] = {0, 0, 0};
+    uint32_t mp_fd = 0, mp_w = 0;
     for (int it = 0; it < my_tiles; ++it) {
       for (int l = 1; l < Lh; ++l) {
         tc::named_sync(TC_BAR_OP1, C::NEPI_T + 32);
         umma::fence_after_sync();
+        const long long t0 = PROF ? clock64() : 0;
         if (lane == 0) gemm_wx();
+        if (PROF && lane == 0) { tc::wait_bar(bar_fd, mp_fd); mp_fd ^= 1; gclk[0] += clock64() - t0; }
         __syncwarp();
       }
       if (TRAIN) {
         for (int l = Lh - 1; l >= 1; --l) {
           tc::named_sync(TC_BAR_OP1, C::NEPI_T + 32);
           umma::fence_after_sync();
+          const long long t0 = PROF ? clock64() : 0;
           if (lane == 0) gemm_wx();
           __syncwarp();
           tc::named_sync(TC_BAR_OP2, C::NEPI_T + 32);
           umma::fence_after_sync();
+          const long long t1 = PROF ? clock64() : 0;
           if (lane == 0) gemm_wgrad(l & 1);
+          if (PROF && lane == 0) {
+            tc::wait_bar(bar_fd, mp_fd); mp_fd ^= 1; gclk[1] += clock64() - t0;
+            tc::wait_bar(bar_w, mp_w); mp_w ^= 1; gclk[2] += clock64() - t1;
+          }
           __syncwarp();
         }
       }
     }
-  } else if (warp < C::NEPI) {
+    if (mprof) { L.phase_clk[8] = gclk[0]; L.phase_clk[9] = gclk[1]; L.phase_clk[10] = gclk[2]; }
+  } else {
     // ================================================================ epilogue warps
     const int quad = warp & 3, q = warp >> 2;
     const int u = 32 * quad + lane;                        // this thread's unit (= TMEM lane)
@@ -429,52 +474,63 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     double lcur = 0.0;
     const int slot = L.seg_slot[0];
     const long long n_end = L.seg_pt_end[0];
-    const bool prof = (L.phase_clk != nullptr) && blockIdx.x == 0 && tid == 0;
-    long long pclk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tmark = prof ? clock64() : 0;
+    // phase clocks (PROF instantiation only: the counters live in local memory, which this kernel's 225 KB of
+    // shared memory leaves no L1 for -- in the production instantiation lap() is a no-op)
+    const bool prof = PROF && (L.phase_clk != nullptr) && blockIdx.x == 0 && tid == 0;
+    long long pclk[PROF ? 8 : 1];
+    long long tmark = 0;
+    if (PROF) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pclk[i] = 0;
+      tmark = prof ? clock64() : 0;
+    }
     auto lap = [&](int ph) {
-      if (prof) { const long long now = clock64(); pclk[ph] += now - tmark; tmark = now; }
+      if (PROF) {
+        if (prof) { const long long now = clock64(); pclk[ph] += now - tmark; tmark = now; }
+      }
     };
-    // accumulators of the last forward / data-gradient GEMM (big + small) -> registers
-    auto load_acc = [&](float (&a)[K][8]) {
-      float sm[K][8];
+    // accumulators of the last forward / data-gradient GEMM (big + small), points 4h..4h+3 of the block
+    auto load_acc = [&](float (&a)[K][V], int h) {
+      float sm[K][V];
 #pragma unroll
       for (int c = 0; c < K; ++c) {
-        umma::tmem_ld8(tl + C::TC_D(0) + c * NP + 8 * n8, a[c]);
-        umma::tmem_ld8(tl + C::TC_D(0) + NROW + c * NP + 8 * n8, sm[c]);
+        umma::tmem_ld4(tl + C::TC_D(0) + c * NP + 8 * n8 + V * h, a[c]);
+        umma::tmem_ld4(tl + C::TC_D(0) + NROW + c * NP + 8 * n8 + V * h, sm[c]);
       }
       umma::tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < K; ++c)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[c][i] += sm[c][i];
+        for (int i = 0; i < V; ++i) a[c][i] += sm[c][i];
     };
-    auto load_beta = [&](float (&beta)[3][8]) {
+    auto load_beta = [&](float (&beta)[3][V], int h) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        if (C::LAP && k < C::N1) tc::ld8(s_beta + k * NP + 8 * n8, beta[k]);
+        if (C::LAP && k < C::N1) tc::ld4(s_beta + k * NP + 8 * n8 + V * h, beta[k]);
         else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) beta[k][i] = 0.f;
+          for (int i = 0; i < V; ++i) beta[k][i] = 0.f;
         }
       }
     };
-    // stash slot of (layer, channel); channel K = cos of the sin activation
-    auto stash_ptr = [&](int l, int c) -> float* { return stash + (size_t)l * C::STL + ((size_t)(c * Q + q) * 128 + u) * 8; };
+    // stash slot of (layer, channel, half); channel K = cos of the sin activation
+    auto stash_ptr = [&](int l, int c, int h) -> float* {
+      return stash + (size_t)l * C::STL + ((size_t)(c * Q + q) * 128 + u) * 8 + V * h;
+    };
     // weight-gradient block (lane = output unit, columns = input units) -> CTA-private accumulator rows, coalesced
     auto flush_dw = [&](int l) {
       constexpr int NC = 128 / Q;  // input units (columns) per warp
       float* gcol = gacc + net.off_w[l] + (size_t)(q * NC) * ldw + u;
       const uint32_t src = tl + C::TC_DW + 128 * (l & 1) + q * NC;
 #pragma unroll
-      for (int j = 0; j < NC / 8; ++j) {
-        float w[8], g8[8];
-        umma::tmem_ld8(src + 8 * j, w);
+      for (int b = 0; b < NC / 16; ++b) {   // 16 accumulator loads in flight per round trip
+        float g[16], w[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g8[i] = gcol[(size_t)(8 * j + i) * ldw];
+        for (int i = 0; i < 16; ++i) g[i] = gcol[(size_t)(16 * b + i) * ldw];
+        umma::tmem_ld16(src + 16 * b, w);
         umma::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) gcol[(size_t)(8 * j + i) * ldw] = g8[i] + w[i];
+        for (int i = 0; i < 16; ++i) gcol[(size_t)(16 * b + i) * ldw] = g[i] + w[i];
       }
       umma::fence_before_sync();
     };
@@ -511,55 +567,73 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
       // ---------------- forward
 #pragma unroll 1
       for (int l = 0; l < Lh; ++l) {
-        float a[K][8];
+        const int act = (l == 0) ? net.act_first : net.act_hidden;
+        const float bias = __ldg(L.wpack + net.off_b[l] + u);
+        const bool last = (l == Lh - 1);
+        const float wlv = last ? __ldg(L.wpack + net.off_wl + u) : 0.f;
+        float w00 = 0.f, w01 = 0.f, w02 = 0.f;
         if (l == 0) {
-          const float w00 = __ldg(L.wpack + net.off_w0 + u), w01 = __ldg(L.wpack + net.off_w0 + WP + u),
-                      w02 = __ldg(L.wpack + net.off_w0 + 2 * WP + u);
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int c = 0; c < K; ++c) {
-              const float4 h = *reinterpret_cast<const float4*>(s_hj + ((8 * n8 + i) * K + c) * 4);
-              a[c][i] = net.scl * fmaf(h.x, w00, fmaf(h.y, w01, h.z * w02));
-            }
+          w00 = __ldg(L.wpack + net.off_w0 + u); w01 = __ldg(L.wpack + net.off_w0 + WP + u); w02 = __ldg(L.wpack + net.off_w0 + 2 * WP + u);
         } else {
           tc::wait_bar(bar_fd, par_fd);
           par_fd ^= 1;
           umma::fence_after_sync();
           lap(0);
-          load_acc(a);
         }
-        const int act = (l == 0) ? net.act_first : net.act_hidden;
-        const float bias = __ldg(L.wpack + net.off_b[l] + u);
-        float beta[3][8];
-        load_beta(beta);
-        {
-          float y[8], d1[8], d2[8];
+        float sv[K + 1][V];   // stash values of the half in flight
+#pragma unroll 1
+        for (int h = 0; h < NH; ++h) {
+          float a[K][V];
+          if (l == 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) a[0][i] += bias;
-          tc::act8_fwd(act, a[0], y, d1, d2);
+            for (int i = 0; i < V; ++i)
+#pragma unroll
+              for (int c = 0; c < K; ++c) {
+                const float4 hh = *reinterpret_cast<const float4*>(s_hj + ((8 * n8 + V * h + i) * K + c) * 4);
+                a[c][i] = net.scl * fmaf(hh.x, w00, fmaf(hh.y, w01, hh.z * w02));
+              }
+          } else {
+            load_acc(a, h);
+          }
+          float beta[3][V];
+          load_beta(beta, h);
+          {
+            float y[V], d1[V], d2[V];
+#pragma unroll
+            for (int i = 0; i < V; ++i) a[0][i] += bias;
+            tc::act_fwd<V>(act, a[0], y, d1, d2);
+            if (TRAIN) {
+              // stash: y, (cos), pre-activation jets.  The global stores of the LAST half are issued after the
+              // operand hand-over below: fence.proxy.async is a MEMBAR that would wait for them to drain
+#pragma unroll
+              for (int i = 0; i < V; ++i) { sv[0][i] = y[i]; sv[K][i] = d1[i]; }
+#pragma unroll
+              for (int c = 1; c < K; ++c)
+#pragma unroll
+                for (int i = 0; i < V; ++i) sv[c][i] = a[c][i];
+            }
+            tc::jets_outputs<C, V>(a, y, d1, d2, beta);
+          }
+          if (!last) {
+#pragma unroll
+            for (int c = 0; c < K; ++c) tc::store_split4<3>(R1 + tc::chunk_off<SWB>(u, c * PB + n8, WP), C::PLANE1, h, a[c]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < K; ++c) {
+              float pv[V];
+#pragma unroll
+              for (int i = 0; i < V; ++i) pv[i] = a[c][i] * wlv;
+              tc::st4(part + (size_t)u * C::PARTLD + c * NP + 8 * n8 + V * h, pv);
+            }
+          }
           if (TRAIN) {
-            tc::st8(stash_ptr(l, 0), y);
-            if (act == PINN_SIN) tc::st8(stash_ptr(l, K), d1);
+            if (h == NH - 1 && !last) operands_ready(TC_BAR_OP1);
 #pragma unroll
-            for (int c = 1; c < K; ++c) tc::st8(stash_ptr(l, c), a[c]);
-          }
-          tc::jets_outputs<C>(a, y, d1, d2, beta);
-        }
-        if (l < Lh - 1) {
-#pragma unroll
-          for (int c = 0; c < K; ++c) tc::store_split8<SWB>(R1, C::PLANE1, u, c * PB + n8, WP, a[c]);
-          operands_ready(TC_BAR_OP1);
-        } else {
-          const float wlv = __ldg(L.wpack + net.off_wl + u);
-#pragma unroll
-          for (int c = 0; c < K; ++c) {
-            float pv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pv[i] = a[c][i] * wlv;
-            tc::st8(part + (size_t)u * C::PARTLD + c * NP + 8 * n8, pv);
+            for (int c = 0; c < K; ++c) tc::st4(stash_ptr(l, c, h), sv[c]);
+            if (act == PINN_SIN) tc::st4(stash_ptr(l, K, h), sv[K]);
           }
         }
+        if (!TRAIN && !last) operands_ready(TC_BAR_OP1);
         lap(1);
       }
 
@@ -621,31 +695,44 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
 #pragma unroll 1
         for (int l = Lh - 1; l >= 0; --l) {
           const int act = (l == 0) ? net.act_first : net.act_hidden;
-          float beta[3][8];
-          load_beta(beta);
-          {
-            // ---- B1(l)
-            float st[K][8], yb[K][8];
-            float d1[8], d2[8], d3[8];
+          // stash of BOTH halves in flight before the wait for dgrad(l+1): the L2 round trip hides behind it.
+          // (Keeping the values B2(l+1) loaded in registers instead -- one L2 read per layer -- was measured
+          // slower: the 40 extra live registers spill, and this kernel's shared-memory footprint leaves no L1.)
+          float stA[NH][K][V], csA[NH][V];
 #pragma unroll
-            for (int c = 0; c < K; ++c) tc::ld8(stash_ptr(l, c), st[c]);
-            if (act == PINN_SIN) tc::ld8(stash_ptr(l, K), d1);
-            if (l < Lh - 1) {
-              tc::wait_bar(bar_fd, par_fd);  // dgrad(l+1)
-              par_fd ^= 1;
-              umma::fence_after_sync();
-              lap(7);
-              load_acc(yb);
+          for (int h = 0; h < NH; ++h) {
+#pragma unroll
+            for (int c = 0; c < K; ++c) tc::ld4(stash_ptr(l, c, h), stA[h][c]);
+            if (act == PINN_SIN) tc::ld4(stash_ptr(l, K, h), csA[h]);
+          }
+          if (l < Lh - 1) {
+            tc::wait_bar(bar_fd, par_fd);  // dgrad(l+1)
+            par_fd ^= 1;
+            umma::fence_after_sync();
+            lap(7);
+          }
+          float gb = 0.f;
+          // ---- B1(l)
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+            float yb[K][V];
+            float d1[V], d2[V], d3[V], beta[3][V];
+            float (&st)[K][V] = stA[h];
+            if (act == PINN_SIN) {
+#pragma unroll
+              for (int i = 0; i < V; ++i) d1[i] = csA[h][i];
             }
-            tc::act8_bwd(act, st[0], d1, d2, d3);
+            load_beta(beta, h);
+            if (l < Lh - 1) load_acc(yb, h);
+            tc::act_bwd<V, true>(act, st[0], d1, d2, d3);
             if (l == Lh - 1) {
               // seeds: ybar[c] = (epsil * ubar_c) * wl[u]; the output-layer weight gradient needs the layer outputs
 #pragma unroll
               for (int c = 0; c < K; ++c) {
-                float ub[8];
-                tc::ld8(s_ubar + c * NP + 8 * n8, ub);
+                float ub[V];
+                tc::ld4(s_ubar + c * NP + 8 * n8 + V * h, ub);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < V; ++i) {
                   float o;
                   if (c == 0) o = st[0][i];
                   else if (c <= C::N1) o = d1[i] * st[c][i];
@@ -664,64 +751,69 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
                 }
               }
             }
-            tc::jets_adjoint<C>(yb, st, d1, d2, d3, beta);
-            float gb = 0.f;
+            tc::jets_adjoint<C, V>(yb, st, d1, d2, d3, beta);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) gb += yb[0][i];
-            s_bg[q * WP + u] = gb;
-            lap(3);
+            for (int i = 0; i < V; ++i) gb += yb[0][i];
             if (l > 0) {
-              if (l < Lh - 1) {
+              if (h == 0 && l < Lh - 1) {
+                lap(3);
                 tc::wait_bar(bar_w, par_w);  // wgrad(l+1) has read G^(l+1) (R1) and Y^l (R2)
                 par_w ^= 1;
                 umma::fence_after_sync();
                 lap(5);
               }
 #pragma unroll
-              for (int c = 0; c < K; ++c) tc::store_split8<SWB>(R1, C::PLANE1, u, c * PB + n8, WP, yb[c]);
-              operands_ready(TC_BAR_OP1);
+              for (int c = 0; c < K; ++c) tc::store_split4<3>(R1 + tc::chunk_off<SWB>(u, c * PB + n8, WP), C::PLANE1, h, yb[c]);
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
+              for (int i = 0; i < V; ++i)
 #pragma unroll
                 for (int c = 0; c < K; ++c) {
-                  const float4 h = *reinterpret_cast<const float4*>(s_hj + ((8 * n8 + i) * K + c) * 4);
+                  const float4 hh = *reinterpret_cast<const float4*>(s_hj + ((8 * n8 + V * h + i) * K + c) * 4);
                   const float t = net.scl * yb[c][i];
-                  w0acc[0] = fmaf(h.x, t, w0acc[0]);
-                  w0acc[1] = fmaf(h.y, t, w0acc[1]);
-                  w0acc[2] = fmaf(h.z, t, w0acc[2]);
+                  w0acc[0] = fmaf(hh.x, t, w0acc[0]);
+                  w0acc[1] = fmaf(hh.y, t, w0acc[1]);
+                  w0acc[2] = fmaf(hh.z, t, w0acc[2]);
                 }
             }
           }
+          s_bg[q * WP + u] = gb;
+          if (l > 0) operands_ready(TC_BAR_OP1);
           lap(3);
           if (l > 0) {
-            // ---- B2(l): the layer's input jets Y^(l-1) again (from the stash of layer l-1) -> R2
+            // ---- F(l+1): flush the previous layer's weight-gradient block (wgrad(l+1) completed: B1 waited for it)
+            // first -- global traffic only, dgrad(l) has the shared-memory bandwidth to itself meanwhile
+            if (l < Lh - 1) flush_dw(l + 1);
+            lap(6);
+            // ---- B2(l): the layer's input jets Y^(l-1) again (from the stash of layer l-1) -> R2 (two planes)
             const int actp = (l - 1 == 0) ? net.act_first : net.act_hidden;
-            float st[K][8], d1[8], d2[8], d3[8];
+#pragma unroll 1
+            for (int h = 0; h < NH; ++h) {
+              float st[K][V], d1[V], d2[V], d3[V], beta[3][V];
 #pragma unroll
-            for (int c = 0; c < K; ++c) tc::ld8(stash_ptr(l - 1, c), st[c]);
-            if (actp == PINN_SIN) tc::ld8(stash_ptr(l - 1, K), d1);
-            tc::act8_bwd(actp, st[0], d1, d2, d3);
-            {
-              float y[8];
+              for (int c = 0; c < K; ++c) tc::ld4(stash_ptr(l - 1, c, h), st[c]);
+              if (actp == PINN_SIN) tc::ld4(stash_ptr(l - 1, K, h), d1);
+              load_beta(beta, h);
+              tc::act_bwd<V, false>(actp, st[0], d1, d2, d3);
+              {
+                float y[V];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) y[i] = st[0][i];
-              tc::jets_outputs<C>(st, y, d1, d2, beta);
+                for (int i = 0; i < V; ++i) y[i] = st[0][i];
+                tc::jets_outputs<C, V>(st, y, d1, d2, beta);
+              }
+#pragma unroll
+              for (int c = 0; c < K; ++c) tc::store_split4<C::YP>(R2 + tc::chunk_off<SWB>(u, c * PB + n8, 128), C::PLANE2, h, st[c]);
             }
-#pragma unroll
-            for (int c = 0; c < K; ++c) tc::store_split8<SWB>(R2, C::PLANE2, u, c * PB + n8, 128, st[c]);
             operands_ready(TC_BAR_OP2);
             lap(4);
-            // ---- F(l+1): flush the previous layer's weight-gradient block while dgrad(l) / wgrad(l) run
-            if (l < Lh - 1) flush_dw(l + 1);
           } else if (Lh > 1) {
             tc::wait_bar(bar_w, par_w);  // wgrad(1)
             par_w ^= 1;
             umma::fence_after_sync();
             lap(5);
             flush_dw(1);
+            lap(6);
           }
-          lap(6);
           // ---- bias gradient of layer l: fixed-order fold over the Q point blocks
           epi_sync();
           if (q == 0) {
@@ -763,9 +855,11 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
         }
       }
     }
-    if (prof) {
+    if (PROF) {
+      if (prof) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) L.phase_clk[i] = pclk[i];
+        for (int i = 0; i < 8; ++i) L.phase_clk[i] = pclk[i];
+      }
     }
   }
 

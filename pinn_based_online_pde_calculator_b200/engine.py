@@ -345,6 +345,10 @@ class PinnEngine:
         _check(self.lib, self.lib.pinn_engine_adam_steps(self.h, int(n_steps), float(lr), _ptr(rows)))
         return rows
 
+    def launches_per_eval(self) -> int:
+        """kernels one loss/gradient evaluation enqueues (an Adam step adds one)"""
+        return int(self.lib.pinn_engine_launches_per_eval(self.h))
+
     def last_ms(self) -> float:
         return float(self.lib.pinn_engine_last_ms(self.h))
 

@@ -63,3 +63,22 @@ def engine_for(pb, lref=1.0, device=0):
 def rel_err(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def problem_from_workload(name, n_col, n_bd=64):
+    """The LITERAL BASELINE.json workload (workloads.make_workload: network, scl, equation string, source terms,
+    boundary data) on a slice of its seeded points, in the dict layout of make_problem."""
+    from pinn_based_online_pde_calculator_b200.workloads import init_params, make_points, make_workload, unflatten
+
+    wl = make_workload(name, n_col)
+    wl.n_bd = [min(n, n_bd) for n in wl.n_bd]
+    x_col, x_bd, u_bd = make_points(wl)
+    net = wl.net
+    t64 = lambda a: torch.tensor(np.asarray(a, dtype=np.float32), dtype=torch.float32).double()
+    params = [[t64(W), t64(b)] for W, b in unflatten(net, init_params(net))]
+    names = COORD_NAMES[net.d_in]
+    if net.d_in == 2 and "u_t" in wl.expr and "u_y" not in wl.expr:
+        names = ("x", "t")
+    return dict(net=net, eq=wl.eq, params=params, x_col=t64(x_col), x_bd=[t64(a) for a in x_bd],
+                u_bd=[t64(a)[:, None] for a in u_bd], lw=wl.lw, expr=wl.expr,
+                limit=[torch.tensor(net.lb, dtype=torch.float64), torch.tensor(net.ub, dtype=torch.float64)], names=names)

@@ -33,7 +33,7 @@ CASES = {
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kernel", ["simt", "mma"])
+@pytest.mark.parametrize("kernel", ["simt", "mma", "tc"])
 @pytest.mark.parametrize("name", list(CASES))
 def test_loss_and_grad_match_oracle(name, kernel, monkeypatch):
     """Both kernel families: fp32 SIMT (FFMA2) and the 3xTF32 tensor-core kernel (padded widths 64..256)."""
@@ -41,10 +41,12 @@ def test_loss_and_grad_match_oracle(name, kernel, monkeypatch):
     wide = pb["net"].width > 32
     if kernel == "mma" and not wide:
         pytest.skip("no tensor-core instantiation below padded width 64")
+    if kernel == "tc" and not name.startswith("C4"):
+        pytest.skip("tcgen05 family D is instantiated for padded width 128 (Laplacian-type jets)")
     monkeypatch.setenv("PINN_B200_KERNEL", kernel)
     g_ref, info_ref, f_u, residual = oracle_loss_grad(pb, lref=1.7)
     eng = engine_for(pb, lref=1.7)
-    assert eng.kernel == {"simt": "simt_fp32", "mma": "mma_3xtf32"}[kernel]
+    assert eng.kernel == {"simt": "simt_fp32", "mma": "mma_3xtf32", "tc": "tc_bf16x3"}[kernel]
     g, info = eng.loss_grad()
     g = g.cpu().numpy()
     assert info.shape == info_ref.shape
@@ -56,8 +58,49 @@ def test_loss_and_grad_match_oracle(name, kernel, monkeypatch):
     u_ref = fu(pb["x_col"]).numpy()[:, 0]
     f_ref = (O.gov_eqn(fu, pb["x_col"]) if residual is None else residual(fu, pb["x_col"])).numpy()[:, 0]
     assert rel_err(u, u_ref) < TOL
-    # the 5x256 heat residual is a small difference of large terms: measured 1.1e-5 in fp32
-    assert rel_err(f, f_ref) < (2e-5 if name.startswith("C5") else TOL)
+    # The 5x256 heat residual is a small difference of large terms.  The production (tensor-core) kernels hold
+    # the 1e-5 bar; only the plain-fp32 SIMT kernel -- production for padded width 32 only, forced here on a
+    # width it is never selected for -- measures 1.1e-5 there.
+    assert rel_err(f, f_ref) < (2e-5 if (name.startswith("C5") and kernel == "simt") else TOL)
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n_col", [("C3", 3000), ("C4", 2048), ("C5", 1000), ("C2", 4000), ("R0", 2600)])
+def test_literal_baseline_workloads_match_oracle(name, n_col, monkeypatch):
+    """the workloads bench.py times (make_workload: C4 with scl = 8, k^2 = (8 pi)^2 and the
+    sin(8 pi x) source, C3 Burgers, C5 heat ...) on a slice of their own seeded points, through whatever kernel
+    `auto` selects: loss_info, gradient, u and f within 1e-5 of the float64 oracle."""
+    from tests.helpers import problem_from_workload
+
+    monkeypatch.delenv("PINN_B200_KERNEL", raising=False)
+    pb = problem_from_workload(name, n_col)
+    g_ref, info_ref, f_u, residual = oracle_loss_grad(pb, lref=1.0)
+    eng = engine_for(pb, lref=1.0)
+    if name in ("C4", "C5") and name == "C4":
+        assert eng.kernel == "tc_bf16x3"   # the tcgen05 family is the production kernel for padded width 128
+    g, info = eng.loss_grad()
+    assert np.allclose(info, info_ref, rtol=TOL, atol=0), (info, info_ref)
+    assert rel_err(g.cpu().numpy(), g_ref) < TOL, rel_err(g.cpu().numpy(), g_ref)
+    u, f, _ = eng.eval(pb["x_col"].numpy())
+    fu = lambda z: f_u(pb["params"], z)
+    u_ref = fu(pb["x_col"]).numpy()[:, 0]
+    f_ref = (O.gov_eqn(fu, pb["x_col"]) if residual is None else residual(fu, pb["x_col"])).numpy()[:, 0]
+    assert rel_err(u, u_ref) < TOL and rel_err(f, f_ref) < TOL, (rel_err(u, u_ref), rel_err(f, f_ref))
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_gradient_parity_on_a_131072_point_slice_of_c2():
+    """gradient parity at (near) full size, not only on a few thousand points."""
+    from tests.helpers import problem_from_workload
+
+    pb = problem_from_workload("C2", 131072, n_bd=10_000)
+    g_ref, info_ref, _, _ = oracle_loss_grad(pb, lref=1.0)
+    eng = engine_for(pb, lref=1.0)
+    g, info = eng.loss_grad()
+    assert np.allclose(info, info_ref, rtol=TOL, atol=0), (info, info_ref)
+    assert rel_err(g.cpu().numpy(), g_ref) < TOL, rel_err(g.cpu().numpy(), g_ref)
     eng.close()
 
 

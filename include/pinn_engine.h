@@ -81,6 +81,7 @@ int64_t pinn_engine_num_params(pinn_engine_t* h);
 int32_t pinn_engine_num_loss_info(pinn_engine_t* h);
 /* points per CTA tile / grid size of the collocation kernel (for roofline maths) */
 int32_t pinn_engine_tile_points(pinn_engine_t* h);
+/* kernels one loss/gradient evaluation enqueues (an Adam step adds one) -- the bench's gpu_launches claim */
 int32_t pinn_engine_launches_per_eval(pinn_engine_t* h);
 /* kernel family chosen at create: 0 = fp32 SIMT (packed FFMA2), 1 = 3xTF32 mma.sync tensor-core kernel.
  * Selection: environment PINN_B200_KERNEL = simt | mma | auto (auto: tensor-core kernel for padded
@@ -139,6 +140,11 @@ int pinn_engine_eval(pinn_engine_t* h, const float* z, int64_t n, const float* a
  * (un-normalised value, normalised gradient) pairing (sw:479-490). */
 int pinn_engine_lbfgs(pinn_engine_t* h, int32_t max_iter, double tol, int32_t value_unnormalised,
                       pinn_eval_cb cb, void* user, pinn_lbfgs_result_t* out);
+/* The loop runs ON THE DEVICE (one CUDA-graph WHILE node: trial point, evaluation, Hager-Zhang state machine,
+ * history push, two-loop recursion, loop condition); the host synchronises once per batch and then delivers the
+ * loss_info rows (one per evaluation, in order) to `cb`.  PINN_B200_LBFGS = device | host | legacy selects the
+ * device-resident loop (default on one GPU), the same kernels enqueued trip by trip with a synchronisation per
+ * evaluation (default with a communicator), or the round-1 host line search; all three give bit-identical iterates. */
 
 /* NCCL data parallelism: one fused allreduce [grad | loss partial sums] per evaluation.
  * pinn_nccl_unique_id fills 128 bytes; every rank then calls pinn_engine_init_nccl. */
@@ -153,27 +159,6 @@ int pinn_sample_lhs(int device, void* stream, uint32_t seed, int64_t n, int32_t 
                     const float* hi, float* out_dev, int32_t ld, int32_t col0);
 int pinn_sample_cdf2d(int device, void* stream, uint32_t seed, int64_t n, const double* cum_host, int32_t ncy,
                       int32_t ncx, float x0, float y0, float dx, float dy, float* out_dev, int32_t ld);
-
-/* fp32 FMA-pipe microbenchmark (roofline denominator of the SIMT path):
- * returns achieved TFLOP/s; variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2 */
-int pinn_fma_peak(int device, int variant, double* tflops_out);
-/* phase clocks (CTA 0) of the last launch of the experimental tcgen05 kernel family (PINN_B200_KERNEL=umma) */
-int pinn_engine_umma_clocks(pinn_engine_t* h, long long* out8);
-/* tcgen05 probe (measurement helper): D = A * B^T on one CTA, tf32 inputs / fp32 TMEM accumulator.  A, B0, B1
- * are RAW shared-memory images (the host lays the operands out), cfg = {M, N, k-steps, A MN-major, B MN-major,
- * products (2 = second one with B1 into lanes +16, M = 64), repetitions, words of A, words of B,
- * A: LBO, SBO, k-step advance in bytes, B: the same}; dumps TMEM as out[128 lanes][512 columns]. */
-int pinn_umma_probe(int device, const float* A, const float* B0, const float* B1, const int* cfg, float* out,
-                    double* cycles, int* status);
-
-/* roofline helper: average device time (ms) of the collocation kernel and of the
- * boundary kernel launched alone, CUDA events on the engine stream, an L2 flush of
- * flush_bytes between launches. */
-int pinn_engine_time_kernels(pinn_engine_t* h, int32_t reps, int64_t flush_bytes, double* col_ms, double* bc_ms);
-
-/* phase profile of the collocation kernel (tensor-core kernel only): clock64 totals of CTA 0 for
- * {fwd GEMM, activation fwd, output+residual, activation bwd, smem restage, wgrad, dgrad, rest} */
-int pinn_engine_phase_profile(pinn_engine_t* h, int64_t* out8);
 
 /* timing helper: device time (ms) of the last adam_steps / loss_grad call measured
  * with CUDA events on the engine stream */

@@ -13,11 +13,13 @@
 #include <vector>
 
 #include "../../include/pinn_engine.h"
+#include "../../include/pinn_engine_debug.h"
 #include "aux_kernels.cuh"
 #include "sampler_kernels.cuh"
 #include "jet_launch.h"
 #include "jet_umma.h"
 #include "jet_tc.h"
+#include "lbfgs_dev.h"
 #include "pinn_common.h"
 
 static thread_local std::string g_err;
@@ -147,6 +149,16 @@ struct pinn_engine {
   // reusable scratch of pinn_engine_eval (grown on demand, freed with the handle)
   std::vector<std::pair<void*, size_t>> eval_bufs;
   size_t l2_carve = 0;  // this engine's share of the device-wide persisting-L2 carve-out
+
+  // device-resident L-BFGS loop: controller state, second scalar pair, optional trace of the trial points, and the
+  // instantiated WHILE graph (rebuilt when the point set / communicator / stream changes)
+  LbfgsCtl* d_ctl = nullptr;
+  double* d_scal2 = nullptr;
+  float* d_trace = nullptr;
+  int trace_cap = 0, trace_rows = 0;
+  cudaGraphExec_t lb_exec = nullptr;
+  bool lb_valid = false;
+  int lbfgs_syncs = 0;  // host synchronisations of the last pinn_engine_lbfgs call
 
   // lbfgs buffers
   float *d_x = nullptr, *d_g = nullptr, *d_d = nullptr, *d_xt = nullptr, *d_S = nullptr, *d_Y = nullptr;
@@ -382,6 +394,10 @@ extern "C" void pinn_engine_destroy(pinn_engine_t* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->lb_exec) cudaGraphExecDestroy(h->lb_exec);
+  if (h->d_ctl) cudaFree(h->d_ctl);
+  if (h->d_scal2) cudaFree(h->d_scal2);
+  if (h->d_trace) cudaFree(h->d_trace);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void* bufs[] = {h->d_params, h->d_fused, h->d_m, h->d_v, h->d_wpack, h->d_stash, h->d_seg_scale,
                   h->d_lr, h->d_adam_c, h->d_loss_part, h->d_ring, h->d_ring_pos, h->d_adam_count, h->d_meta,
@@ -436,8 +452,12 @@ static void apply_l2_policy(pinn_engine* h) {
   if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
   // what the window covers: the whole per-CTA scratch [stash | gradient accumulators] (default), or only one of
   // the two regions (PINN_B200_L2_WINDOW = both | gacc | stash; experiment knob for scratch sets near the L2 size)
+  // Default: both regions, except for the tcgen05 family, whose scratch (C4: 148 x 0.85 MB) exceeds the persisting
+  // carve-out: there the gradient accumulators (read-modify-written every tile) persist and the stash competes for
+  // the rest of the L2 (measured on C4: gacc 21.2 ms, stash 21.6, both 22.2, no window 22.1).
   const char* wsel = getenv("PINN_B200_L2_WINDOW");
-  const bool only_gacc = wsel && !strcmp(wsel, "gacc"), only_stash = wsel && !strcmp(wsel, "stash");
+  const bool tcfam = h->kcol && h->kcol->kind == 3;
+  const bool only_gacc = wsel ? !strcmp(wsel, "gacc") : tcfam, only_stash = wsel && !strcmp(wsel, "stash");
   char* base = reinterpret_cast<char*>(only_gacc ? h->d_gacc : h->d_stash);
   const size_t bytes = (only_gacc ? h->gacc_floats : only_stash ? h->stash_floats : h->stash_floats + h->gacc_floats) * sizeof(float);
   const size_t carve = std::min<size_t>(bytes, (size_t)prop.persistingL2CacheMaxSize);
@@ -470,7 +490,7 @@ extern "C" int pinn_engine_set_stream(pinn_engine_t* h, void* s) {
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   h->stream = (cudaStream_t)s;
   h->own_stream = false;
-  h->graph_valid = false;
+  h->graph_valid = false; h->lb_valid = false;
   if (!getenv("PINN_B200_NO_L2_WINDOW")) apply_l2_policy(h);
   return 0;
 }
@@ -694,7 +714,7 @@ extern "C" int pinn_engine_set_points(pinn_engine_t* h, const float* x_col, int6
   const float* const after[6] = {h->col.coords, h->col.aux, h->col.base, h->bc.coords, h->bc.aux, h->bc.base};
   bool ptr_changed = false;
   for (int i = 0; i < 6; ++i) ptr_changed |= (before[i] != after[i]);
-  if (shape_changed || bc_changed || on_device || ptr_changed) h->graph_valid = false;
+  if (shape_changed || bc_changed || on_device || ptr_changed) { h->graph_valid = false; h->lb_valid = false; }
   // global counts (multi-GPU means) survive a resample with unchanged local shapes; a shape change resets them
   if (shape_changed || bc_changed) {
     h->n_col_global = 0;
@@ -1109,6 +1129,7 @@ int LineSearch::eval(double a, Phi& out) {
   CK(cudaMemcpyAsync(sc, e->d_scal, sizeof sc, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   ++evals;
+  ++e->lbfgs_syncs;
   if (cb) cb(info.data(), e->n_info, user);
   out.a = a;
   out.f = value_unnorm ? info[0] : info[0] / e->lref;
@@ -1133,14 +1154,15 @@ static int lbfgs_alloc(pinn_engine* h) {
   return 0;
 }
 
-extern "C" int pinn_engine_lbfgs(pinn_engine_t* h, int32_t max_iter, double tol, int32_t value_unnorm,
-                                 pinn_eval_cb cb, void* user, pinn_lbfgs_result_t* out) {
-  CK(cudaSetDevice(h->device));
-  if (lbfgs_alloc(h)) return 1;
+// Round-1 implementation: the line search runs on the HOST, one stream synchronisation per evaluation.  Kept as
+// PINN_B200_LBFGS=legacy: the regression reference the new loops are compared with bit for bit.
+static int lbfgs_legacy(pinn_engine_t* h, int32_t max_iter, double tol, int32_t value_unnorm,
+                        pinn_eval_cb cb, void* user, pinn_lbfgs_result_t* out) {
   const int P = h->fmap.n_params, m = 10;
   cudaStream_t st = h->stream;
   pinn_lbfgs_result_t R{};
   LineSearch ls{h, value_unnorm, cb, user};
+  h->lbfgs_syncs = 0;
   CK(cudaMemcpyAsync(h->d_x, h->d_params, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemsetAsync(h->d_d, 0, sizeof(float) * P, st));
   // initial evaluation at x0 (tfp evaluates value_and_gradients at the initial position)
@@ -1265,6 +1287,148 @@ extern "C" int pinn_engine_lbfgs(pinn_engine_t* h, int32_t max_iter, double tol,
   return 0;
 }
 
+// ---------------------------------------------------------------- L-BFGS, controller on the device
+// One loop trip = one objective evaluation:  xt = x + a*d  ->  loss/gradient at xt (the same kernels as an Adam
+// step)  ->  g.d  ->  k_lb_post (Hager-Zhang state machine, lbfgs_ctl.h)  ->  k_lb_push  ->  k_lb_direction (iteration
+// bookkeeping, two-loop recursion, next line search, loop condition).  "device" mode replays the trip as the body of
+// a CUDA-graph WHILE node: the host launches ONE graph and synchronises once per batch (the whole optimisation, or
+// every ring_cap evaluations when loss_info rows have to be drained); "host" mode enqueues the same kernels trip
+// by trip and synchronises after each one (per-evaluation callbacks, multi-GPU runs).
+static int lb_enqueue_trip(pinn_engine* h, unsigned long long cond, int set_cond) {
+  cudaStream_t st = h->stream;
+  const int P = h->fmap.n_params;
+  CK(lb_begin_eval(P, h->d_x, h->d_d, h->d_ctl, h->d_xt, h->d_trace, st));
+  if (enqueue_eval(h, h->d_xt, 0)) return 1;
+  k_dot_inf<<<1, 1024, 0, st>>>(P, h->d_fused, h->d_d, h->d_scal);
+  CK(cudaGetLastError());
+  CK(lb_post_eval(h->d_ctl, h->d_ring, h->d_ring_pos, h->n_info, h->d_scal, st));
+  CK(lb_push(P, h->d_ctl, h->d_x, h->d_g, h->d_xt, h->d_fused, h->d_S, h->d_Y, h->d_rho, h->d_scal2, st));
+  CK(lb_direction(P, h->d_ctl, h->d_g, h->d_S, h->d_Y, h->d_rho, h->d_d, h->d_alpha, h->d_scal2, cond, set_cond, st));
+  return 0;
+}
+
+static int lb_build_graph(pinn_engine* h) {
+  if (h->lb_exec) { cudaGraphExecDestroy(h->lb_exec); h->lb_exec = nullptr; }
+  cudaGraph_t g = nullptr;
+  CK(cudaGraphCreate(&g, 0));
+  cudaGraphConditionalHandle handle;
+  cudaError_t e = cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault);
+  if (e != cudaSuccess) { cudaGraphDestroy(g); return fail("cudaGraphConditionalHandleCreate: %s", cudaGetErrorString(e)); }
+  cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+  memset(&np, 0, sizeof np);
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = handle;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t node;
+  e = cudaGraphAddNode(&node, g, nullptr, 0, &np);
+  if (e != cudaSuccess) { cudaGraphDestroy(g); return fail("cudaGraphAddNode(conditional): %s", cudaGetErrorString(e)); }
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  e = cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) { cudaGraphDestroy(g); return fail("cudaStreamBeginCaptureToGraph: %s", cudaGetErrorString(e)); }
+  const int rc = lb_enqueue_trip(h, (unsigned long long)handle, 1);
+  cudaGraph_t captured = nullptr;
+  e = cudaStreamEndCapture(h->stream, &captured);
+  if (rc) { cudaGraphDestroy(g); return 1; }
+  if (e != cudaSuccess) { cudaGraphDestroy(g); return fail("L-BFGS loop capture: %s", cudaGetErrorString(e)); }
+  e = cudaGraphInstantiate(&h->lb_exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) { h->lb_exec = nullptr; return fail("L-BFGS loop instantiate: %s", cudaGetErrorString(e)); }
+  h->lb_valid = true;
+  return 0;
+}
+
+extern "C" int pinn_engine_lbfgs(pinn_engine_t* h, int32_t max_iter, double tol, int32_t value_unnorm,
+                                 pinn_eval_cb cb, void* user, pinn_lbfgs_result_t* out) {
+  CK(cudaSetDevice(h->device));
+  if (lbfgs_alloc(h)) return 1;
+  const char* env = getenv("PINN_B200_LBFGS");
+  std::string mode = env ? env : "auto";
+  if (mode == "legacy") return lbfgs_legacy(h, max_iter, tol, value_unnorm, cb, user, out);
+  // auto: the device-resident loop on one GPU; with a communicator the collective is enqueued trip by trip
+  if (mode == "auto") mode = h->comm ? "host" : "device";
+  const int P = h->fmap.n_params;
+  cudaStream_t st = h->stream;
+  if (!h->d_ctl) {
+    CK(cudaMalloc(&h->d_ctl, sizeof(LbfgsCtl)));
+    CK(cudaMalloc(&h->d_scal2, sizeof(double) * 2));
+  }
+  LbfgsCtl c;
+  memset(&c, 0, sizeof c);
+  c.max_iter = max_iter; c.m = 10; c.value_unnorm = value_unnorm; c.ls_max_evals = 50; c.ring_cap = h->ring_cap;
+  c.trace_cap = h->d_trace ? h->trace_cap : 0;
+  c.tol = tol; c.lref = h->lref;
+  c.init_eval = 1; c.a_next = 0.0;
+  CK(cudaMemcpyAsync(h->d_ctl, &c, sizeof c, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->d_x, h->d_params, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemsetAsync(h->d_d, 0, sizeof(float) * P, st));
+  CK(cudaMemsetAsync(h->d_g, 0, sizeof(float) * P, st));
+  h->lbfgs_syncs = 0;
+  h->trace_rows = 0;
+  if (mode == "device" && !h->lb_valid) {
+    CK(cudaStreamSynchronize(st));  // the copy of the host-side controller above must not be captured
+    if (lb_build_graph(h)) {
+      if (getenv("PINN_B200_DEBUG")) fprintf(stderr, "[pinn] device L-BFGS loop unavailable (%s); host loop\n", g_err.c_str());
+      cudaGetLastError();
+      mode = "host";
+    }
+  }
+  std::vector<double> rows;
+  bool finished = false;
+  while (!finished) {
+    CK(cudaMemsetAsync(h->d_ring_pos, 0, sizeof(int), st));
+    if (mode == "device") {
+      CK(cudaGraphLaunch(h->lb_exec, st));
+    } else {
+      if (lb_enqueue_trip(h, 0ull, 0)) return 1;
+    }
+    CK(cudaMemcpyAsync(&c, h->d_ctl, sizeof c, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ++h->lbfgs_syncs;
+    const int n_new = mode == "device" ? c.rows : 1;
+    if (cb && n_new > 0) {
+      rows.resize((size_t)n_new * h->n_info);
+      CK(cudaMemcpy(rows.data(), h->d_ring, sizeof(double) * rows.size(), cudaMemcpyDeviceToHost));
+      for (int r = 0; r < n_new; ++r) cb(rows.data() + (size_t)r * h->n_info, h->n_info, user);
+    }
+    finished = c.converged || c.failed || c.iter >= c.max_iter;
+    if (!finished && mode == "device") {  // ring drained: continue the loop where it stopped
+      c.rows = 0; c.stop = 0;
+      CK(cudaMemcpyAsync(h->d_ctl, &c, sizeof c, cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+    }
+  }
+  h->trace_rows = std::min(c.total_evals, c.trace_cap);
+  CK(cudaMemcpyAsync(h->d_params, h->d_x, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  pinn_lbfgs_result_t R{};
+  R.iterations = c.iter; R.evaluations = c.total_evals; R.converged = c.converged; R.failed = c.failed;
+  R.final_loss = value_unnorm ? c.fcur : c.fcur * h->lref;
+  if (out) *out = R;
+  return 0;
+}
+
+/* trace of the L-BFGS trial points (test / debugging aid): keep the first `cap` evaluated parameter vectors */
+extern "C" int pinn_engine_lbfgs_trace(pinn_engine_t* h, int32_t cap) {
+  CK(cudaSetDevice(h->device));
+  if (h->d_trace) { cudaFree(h->d_trace); h->d_trace = nullptr; }
+  h->trace_cap = 0; h->trace_rows = 0;
+  h->lb_valid = false;  // the trace pointer is baked into the loop graph
+  if (cap > 0) {
+    CK(cudaMalloc(&h->d_trace, sizeof(float) * (size_t)cap * h->fmap.n_params));
+    h->trace_cap = cap;
+  }
+  return 0;
+}
+extern "C" int32_t pinn_engine_lbfgs_trace_rows(pinn_engine_t* h) { return h->trace_rows; }
+extern "C" int pinn_engine_lbfgs_trace_get(pinn_engine_t* h, float* out_host, int32_t rows) {
+  CK(cudaSetDevice(h->device));
+  if (rows > h->trace_rows) return fail("trace holds %d rows", h->trace_rows);
+  if (rows > 0) CK(cudaMemcpy(out_host, h->d_trace, sizeof(float) * (size_t)rows * h->fmap.n_params, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int32_t pinn_engine_lbfgs_host_syncs(pinn_engine_t* h) { return h->lbfgs_syncs; }
+
 // ---------------------------------------------------------------- NCCL
 extern "C" int pinn_nccl_unique_id(uint8_t id_out[128]) {
   if (nccl_load()) return 1;
@@ -1286,7 +1450,7 @@ extern "C" int pinn_engine_init_nccl(pinn_engine_t* h, const uint8_t id[128], in
   h->comm = comm;
   h->rank = rank;
   h->world = world;
-  h->graph_valid = false;
+  h->graph_valid = false; h->lb_valid = false;
   return 0;
 }
 

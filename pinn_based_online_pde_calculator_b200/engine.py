@@ -33,6 +33,7 @@ EXPORTS = [
     "pinn_engine_set_loss", "pinn_engine_loss_grad", "pinn_engine_adam_init", "pinn_engine_adam_steps",
     "pinn_engine_eval", "pinn_engine_lbfgs", "pinn_nccl_unique_id", "pinn_engine_init_nccl",
     "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels", "pinn_engine_kernel_kind", "pinn_engine_phase_profile", "pinn_sample_lhs", "pinn_sample_cdf2d", "pinn_engine_sync", "pinn_umma_probe", "pinn_engine_prefetch_points", "pinn_engine_commit_points", "pinn_engine_umma_clocks",
+    "pinn_engine_lbfgs_trace", "pinn_engine_lbfgs_trace_rows", "pinn_engine_lbfgs_trace_get", "pinn_engine_lbfgs_host_syncs",
 ]
 
 
@@ -101,6 +102,10 @@ def load_library(path: Optional[str] = None):
                                      C.c_void_p, C.c_void_p, C.c_int]
     lib.pinn_engine_lbfgs.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_int32, EVAL_CB, C.c_void_p,
                                       C.POINTER(LbfgsResultC)]
+    lib.pinn_engine_lbfgs_trace.argtypes = [C.c_void_p, C.c_int32]
+    lib.pinn_engine_lbfgs_trace_rows.argtypes = [C.c_void_p]
+    lib.pinn_engine_lbfgs_trace_get.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    lib.pinn_engine_lbfgs_host_syncs.argtypes = [C.c_void_p]
     lib.pinn_nccl_unique_id.argtypes = [C.c_void_p]
     lib.pinn_engine_init_nccl.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
     lib.pinn_fma_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
@@ -403,6 +408,19 @@ class PinnEngine:
                                                     None, C.byref(res)))
         return dict(iterations=res.iterations, evaluations=res.evaluations, converged=bool(res.converged),
                     failed=bool(res.failed), final_loss=res.final_loss), rows
+
+    def lbfgs_trace(self, cap: int):
+        """test hook: keep the first `cap` trial parameter vectors of the following lbfgs() calls"""
+        _check(self.lib, self.lib.pinn_engine_lbfgs_trace(self.h, int(cap)))
+
+    def lbfgs_trace_get(self) -> np.ndarray:
+        n = int(self.lib.pinn_engine_lbfgs_trace_rows(self.h))
+        out = np.empty((n, self.n_params), dtype=np.float32)
+        _check(self.lib, self.lib.pinn_engine_lbfgs_trace_get(self.h, _ptr(out), n))
+        return out
+
+    def lbfgs_host_syncs(self) -> int:
+        return int(self.lib.pinn_engine_lbfgs_host_syncs(self.h))
 
     # ---- NCCL
     def init_nccl(self, unique_id: bytes, rank: int, world: int):

@@ -1,0 +1,133 @@
+"""GPU tests of the L-BFGS leg (software.py:464-514): the device-resident loop (CUDA-graph WHILE node), the same
+kernels driven trip by trip from the host, and the round-1 host line search give bit-identical iterates; every
+loss_info row the evaluation callback delivers matches the float64 oracle at the SAME trial parameters; the final
+solution agrees with an independent L-BFGS (scipy L-BFGS-B driving the oracle's value and gradient)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_oracle as O
+from tests.helpers import engine_for, make_problem, oracle_loss_grad, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def poisson1d():
+    pb = make_problem(n_hidden=3, width=20, d_in=1, expr="u_xx + 2", n_col=1000, n_bd=1, n_bc=2, lb=[0.0], ub=[1.0])
+    pb["x_bd"] = [torch.zeros(1, 1, dtype=torch.float64), torch.ones(1, 1, dtype=torch.float64)]
+    pb["u_bd"] = [torch.zeros(1, 1, dtype=torch.float64), torch.zeros(1, 1, dtype=torch.float64)]
+    return pb
+
+
+def polar_r0(n_col=1500):
+    return make_problem(n_hidden=6, width=60, d_in=2, expr="u_rr + 1/r*u_r + 1/(r**2)*u_tt", n_col=n_col, n_bd=100, n_bc=2,
+                        lb=[0.1, 0.0], ub=[1.0, 1.0], feature_map="polar", lw=0.05, coord_names=("r", "t"))
+
+
+def poisson2d():
+    """well-posed 2-D problem (Dirichlet data on all four edges): u* = x(1-x)y(1-y)"""
+    pb = make_problem(n_hidden=3, width=32, d_in=2, expr="u_xx + u_yy + 2*y*(1-y) + 2*x*(1-x)", n_col=1500, n_bd=64, n_bc=4,
+                      lb=[0.0, 0.0], ub=[1.0, 1.0])
+    pb["u_bd"] = [torch.zeros_like(u) for u in pb["u_bd"]]
+    return pb
+
+
+def prepared_engine(pb, adam_steps):
+    eng = engine_for(pb, lref=1.0)
+    _, info0 = eng.loss_grad(want_grad=False)
+    eng.set_loss(pb["lw"], float(info0[0]))
+    eng.adam_init()
+    if adam_steps:
+        eng.adam_steps(adam_steps, 1e-3, want_rows=False)
+    return eng, float(info0[0])
+
+
+@pytest.mark.parametrize("case", ["C1", "R0"])
+def test_device_host_and_legacy_loops_are_bit_identical(case, monkeypatch):
+    pb = poisson1d() if case == "C1" else polar_r0()
+    out = {}
+    for mode in ("legacy", "host", "device"):
+        monkeypatch.setenv("PINN_B200_LBFGS", mode)
+        eng, _ = prepared_engine(pb, 200)
+        res, rows = eng.lbfgs(40, 1e-10, value_unnormalised=True)
+        out[mode] = (eng.get_params(), np.array(rows), res, eng.lbfgs_host_syncs())
+        eng.close()
+    p_leg, r_leg, res_leg, sync_leg = out["legacy"]
+    for mode in ("host", "device"):
+        p, r, res, syncs = out[mode]
+        assert res["iterations"] == res_leg["iterations"] and res["evaluations"] == res_leg["evaluations"], (mode, res, res_leg)
+        assert np.array_equal(r, r_leg), mode                      # every loss_info row, bit for bit
+        assert np.array_equal(p, p_leg), mode                      # final iterate, bit for bit
+    # at most one host synchronisation per iteration BATCH in the device loop
+    assert out["device"][3] <= 2, out["device"][3]
+    assert out["host"][3] == res_leg["evaluations"] and sync_leg >= res_leg["evaluations"]
+    assert res_leg["iterations"] >= 5
+
+
+def test_every_evaluation_row_matches_the_oracle_at_the_same_parameters():
+    """not only the final point -- each row of the per-evaluation callback against the oracle
+    evaluated at the trial parameters of that very evaluation (trace hook of the debug header)."""
+    pb = poisson1d()
+    eng, lref = prepared_engine(pb, 300)
+    eng.lbfgs_trace(64)
+    res, rows = eng.lbfgs(12, 1e-10, value_unnormalised=True)
+    trial = eng.lbfgs_trace_get()
+    assert len(trial) == min(64, res["evaluations"]) and len(rows) == res["evaluations"]
+    worst = 0.0
+    for p, row in zip(trial, rows):
+        params = O.unravel_params(torch.tensor(p, dtype=torch.float64), pb["params"])
+        _, info_ref, _, _ = oracle_loss_grad(dict(pb, params=params), lref=lref)
+        # the data terms (two boundary points) and the total are sums of few numbers: 1e-5; the equation term is a
+        # mean of 1000 squared residuals of ~1e-3 each -> relative to the total loss
+        assert np.allclose(row[:3], info_ref[:3], rtol=1e-5, atol=1e-5 * info_ref[0]), (row, info_ref)
+        worst = max(worst, abs(row[0] / info_ref[0] - 1))
+    assert worst < 1e-5, worst
+    eng.close()
+
+
+@pytest.mark.parametrize("case", ["C1", "P2"])
+def test_final_solution_agrees_with_an_independent_lbfgs(case):
+    """Same start (the engine's parameters after Adam), same loss, same iteration budget: scipy's L-BFGS-B (More-
+    Thuente line search, m = 10) drives the float64 ORACLE; tfp's Hager-Zhang iterates cannot be reproduced here
+    (SURVEY.md 8c), so the comparison is on where both end up: solution on the test grid within 1 %.  (The
+    reference's own smoke problem R0 has no condition on the theta edges -- its harmonic solution is not unique and two
+    optimisers drift apart along the flat direction: measured 6.8 % -- so the 2-D case is a well-posed Poisson problem.)"""
+    from scipy.optimize import minimize
+
+    pb = poisson1d() if case == "C1" else poisson2d()
+    eng, lref = prepared_engine(pb, 600)
+    p0 = eng.get_params().astype(np.float64)
+    res, rows = eng.lbfgs(300, 1e-10, value_unnormalised=True)
+    p_gpu = eng.get_params()
+
+    net = pb["net"]
+    f_u = O.sol_pred_create(pb["limit"], net.scl, net.epsil, act_s=net.act_first, feature_map=net.feature_map)
+    residual = O.make_gov_eqn_expr(pb["expr"], pb["names"])
+    lossf = O.loss_create(f_u, torch.tensor([pb["lw"], 0.0], dtype=torch.float64), lref, residual=residual)
+    data = dict(x_col=pb["x_col"], cond_bd=[pb["x_bd"], pb["u_bd"]])
+
+    def fun(x):
+        params = O.unravel_params(torch.tensor(x, dtype=torch.float64), pb["params"])
+        grads, info = O.loss_and_grad(lossf, params, data)
+        return float(info[0]) / lref, O.ravel_params(grads).numpy().astype(np.float64)
+
+    sp = minimize(fun, p0, jac=True, method="L-BFGS-B", options=dict(maxiter=300, maxcor=10, ftol=0.0, gtol=1e-10, maxls=50))
+    if case == "C1":
+        grid = torch.linspace(0, 1, 111, dtype=torch.float64)[:, None]
+        exact = (grid[:, 0] * (1 - grid[:, 0])).numpy()
+    else:
+        xx, yy = np.meshgrid(np.linspace(0, 1, 41), np.linspace(0, 1, 41))
+        grid = torch.tensor(np.stack([xx.ravel(), yy.ravel()], 1), dtype=torch.float64)
+        exact = (grid[:, 0] * (1 - grid[:, 0]) * grid[:, 1] * (1 - grid[:, 1])).numpy()
+    u_gpu = eng.eval(grid.numpy().astype(np.float32))[0]
+    u_ref = f_u(O.unravel_params(torch.tensor(sp.x, dtype=torch.float64), pb["params"]), grid).numpy()[:, 0]
+    if exact is not None:  # well-posed: both reach the exact solution to the same accuracy
+        l2_gpu = np.linalg.norm(u_gpu - exact) / np.linalg.norm(exact)
+        l2_ref = np.linalg.norm(u_ref - exact) / np.linalg.norm(exact)
+        assert l2_gpu < 2e-2 and l2_ref < 2e-2, (l2_gpu, l2_ref)
+    # the two solutions agree on the test grid within 1 %
+    assert rel_err(u_gpu, u_ref) < 1e-2, rel_err(u_gpu, u_ref)
+    # and the losses they reach are comparable (neither optimiser is stuck far above the other)
+    f_gpu, f_ref = rows[-1][0] / lref, sp.fun
+    assert f_gpu < 5 * f_ref + 1e-12 or f_gpu < 1e-6, (f_gpu, f_ref)
+    eng.close()

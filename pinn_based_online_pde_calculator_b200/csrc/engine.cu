@@ -271,6 +271,8 @@ static int create_impl(pinn_engine* h, const pinn_spec_t* spec, int device) {
     else if (c3 && b1) { h->kcol = c3; h->kbc = b1; }
     else if (c1 && b1) { h->kcol = c1; h->kbc = b1; }
     else { h->kcol = c0; h->kbc = b0; }
+    if (want == "umma" && (!h->kcol || !h->kbc))
+      return fail("PINN_B200_KERNEL=umma: the experimental tcgen05 family C supports padded width 64 with jets (value, 2 first, combined second order), 2..4 hidden layers");
     if (!h->kcol || !h->kbc) {
       return fail("no %s kernel instantiation for WP=%d jets (n1=%d,n2=%d,mix=%d)", want.c_str(), wp, spec->n1, spec->n2, spec->mix);
     }

@@ -231,6 +231,7 @@ def test_adam_graph_follows_a_device_to_host_switch_of_the_point_set():
     p_switched = eng.get_params()
     eng.close()
     fresh = engine_for(pb2)
+    fresh.set_params(p0)
     fresh.adam_init()
     rows_ref = fresh.adam_steps(3, 1e-3)
     assert np.array_equal(rows, rows_ref)

@@ -26,7 +26,7 @@ def polar_r0(n_col=1500):
 
 def poisson2d():
     """well-posed 2-D problem (Dirichlet data on all four edges): u* = x(1-x)y(1-y)"""
-    pb = make_problem(n_hidden=3, width=32, d_in=2, expr="u_xx + u_yy + 2*y*(1-y) + 2*x*(1-x)", n_col=1500, n_bd=64, n_bc=4,
+    pb = make_problem(n_hidden=2, width=24, d_in=2, expr="u_xx + u_yy + 2*y*(1-y) + 2*x*(1-x)", n_col=800, n_bd=64, n_bc=4,
                       lb=[0.0, 0.0], ub=[1.0, 1.0])
     pb["u_bd"] = [torch.zeros_like(u) for u in pb["u_bd"]]
     return pb
@@ -95,9 +95,10 @@ def test_final_solution_agrees_with_an_independent_lbfgs(case):
     from scipy.optimize import minimize
 
     pb = poisson1d() if case == "C1" else poisson2d()
-    eng, lref = prepared_engine(pb, 600)
+    n_adam, n_lb = (600, 300) if case == "C1" else (2000, 1500)
+    eng, lref = prepared_engine(pb, n_adam)
     p0 = eng.get_params().astype(np.float64)
-    res, rows = eng.lbfgs(300, 1e-10, value_unnormalised=True)
+    res, rows = eng.lbfgs(n_lb, 1e-10, value_unnormalised=True)
     p_gpu = eng.get_params()
 
     net = pb["net"]
@@ -111,7 +112,7 @@ def test_final_solution_agrees_with_an_independent_lbfgs(case):
         grads, info = O.loss_and_grad(lossf, params, data)
         return float(info[0]) / lref, O.ravel_params(grads).numpy().astype(np.float64)
 
-    sp = minimize(fun, p0, jac=True, method="L-BFGS-B", options=dict(maxiter=300, maxcor=10, ftol=0.0, gtol=1e-10, maxls=50))
+    sp = minimize(fun, p0, jac=True, method="L-BFGS-B", options=dict(maxiter=n_lb, maxfun=3 * n_lb, maxcor=10, ftol=0.0, gtol=1e-10, maxls=50))
     if case == "C1":
         grid = torch.linspace(0, 1, 111, dtype=torch.float64)[:, None]
         exact = (grid[:, 0] * (1 - grid[:, 0])).numpy()
@@ -124,6 +125,7 @@ def test_final_solution_agrees_with_an_independent_lbfgs(case):
     if exact is not None:  # well-posed: both reach the exact solution to the same accuracy
         l2_gpu = np.linalg.norm(u_gpu - exact) / np.linalg.norm(exact)
         l2_ref = np.linalg.norm(u_ref - exact) / np.linalg.norm(exact)
+        print(f"{case}: rel L2 vs exact: engine {l2_gpu:.3e}, scipy-on-oracle {l2_ref:.3e}; evals {res['evaluations']} / {sp.nfev}")
         assert l2_gpu < 2e-2 and l2_ref < 2e-2, (l2_gpu, l2_ref)
     # the two solutions agree on the test grid within 1 %
     assert rel_err(u_gpu, u_ref) < 1e-2, rel_err(u_gpu, u_ref)

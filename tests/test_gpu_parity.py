@@ -25,6 +25,18 @@ CASES = {
                                    act_hidden=1, scl=2.0),
     "C5_heat3d_5x256": dict(n_hidden=5, width=256, d_in=3, expr="u_t - 0.1*(u_xx + u_yy)", n_col=600, n_bd=100,
                             n_bc=5, lb=[0.0, 0.0, 0.0], ub=[1.0, 1.0, 1.0]),
+    # padded width 128, one case per jet structure of the tcgen05 family D (3 .. 6 channels, 128 B and 32 B swizzle)
+    "W128_burgers_3x100": dict(n_hidden=3, width=100, d_in=2, expr="u_y + u*u_x - 0.01*u_xx", n_col=900, n_bd=60, n_bc=3,
+                               lb=[-1.0, 0.0], ub=[1.0, 1.0]),
+    "W128_mixed_2x128": dict(n_hidden=2, width=128, d_in=2, expr="u_xx + 2*u_xy + 3*u_yy - u*u_y + x", n_col=500, n_bd=50,
+                             n_bc=2, lb=[0.0, -1.0], ub=[2.0, 1.0]),
+    "W128_heat3d_3x128": dict(n_hidden=3, width=128, d_in=3, expr="u_t - 0.1*(u_xx + u_yy)", n_col=700, n_bd=50, n_bc=5,
+                              lb=[0.0, 0.0, 0.0], ub=[1.0, 1.0, 1.0]),
+    "W128_poisson1d_2x120": dict(n_hidden=2, width=120, d_in=1, expr="u_xx + 2*sin(3*x)", n_col=400, n_bd=1, n_bc=2, lb=[0.0], ub=[1.0]),
+    "W128_nonlinear2nd_3x128": dict(n_hidden=3, width=128, d_in=2, expr="u*u_xx + u_yy - u_x", n_col=600, n_bd=40, n_bc=4,
+                                    lb=[0.0, 0.0], ub=[1.0, 1.0], act_first=1),
+    "W128_3d_general_2x128": dict(n_hidden=2, width=128, d_in=3, expr="u*u_xx + u_yy - u_t", n_col=300, n_bd=30, n_bc=3,
+                                  lb=[0.0, 0.0, 0.0], ub=[1.0, 1.0, 1.0]),
     "mixed_2x32": dict(n_hidden=2, width=32, d_in=2, expr="u_xx + 2*u_xy + 3*u_yy - u*u_y + x", n_col=700, n_bd=50,
                        n_bc=1, lb=[0.0, -1.0], ub=[2.0, 1.0]),
     "single_hidden_1x16": dict(n_hidden=1, width=16, d_in=2, expr="u_xx + u_y", n_col=300, n_bd=20, n_bc=1,
@@ -41,8 +53,8 @@ def test_loss_and_grad_match_oracle(name, kernel, monkeypatch):
     wide = pb["net"].width > 32
     if kernel == "mma" and not wide:
         pytest.skip("no tensor-core instantiation below padded width 64")
-    if kernel == "tc" and not name.startswith("C4"):
-        pytest.skip("tcgen05 family D is instantiated for padded width 128 (Laplacian-type jets)")
+    if kernel == "tc" and not (64 < pb["net"].width <= 128 and pb["eq"].K >= 3):
+        pytest.skip("tcgen05 family D is instantiated for padded width 128, jets with at least three channels")
     monkeypatch.setenv("PINN_B200_KERNEL", kernel)
     g_ref, info_ref, f_u, residual = oracle_loss_grad(pb, lref=1.7)
     eng = engine_for(pb, lref=1.7)

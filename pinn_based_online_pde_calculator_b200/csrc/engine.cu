@@ -1078,6 +1078,7 @@ extern "C" int pinn_engine_phase_profile(pinn_engine_t* h, int64_t* out8) {
   CK(cudaMemsetAsync(h->d_loss_part, 0, sizeof(double) * (size_t)h->grid_col * h->n_slots, st));
   PinnLaunch L = h->Lcol;
   L.phase_clk = d;
+  if (const char* ex = getenv("PINN_TC_EXP")) L.exp_flags = atoi(ex);
   CK(h->kcol->launch(L, true, h->grid_col, st));
   long long host[16];
   CK(cudaMemcpyAsync(host, d, sizeof host, cudaMemcpyDeviceToHost, st));

@@ -32,6 +32,10 @@
 #include "jet_kernel.cuh"
 #include "umma_common.cuh"
 
+#ifndef TC_EXP
+#define TC_EXP 0   // timing experiments (wrong results): 1 no accumulator flush, 2 no B2 stash read, 4 no stash write, 8 no B1 stash read
+#endif
+
 template <int WP_, int N1_, int N2_, int MIX_>
 struct TcCfg {
   static constexpr int WP = WP_, N1 = N1_, N2 = N2_, MIX = MIX_;
@@ -51,6 +55,11 @@ struct TcCfg {
   // pipe is not the limiter) and three truncating adds per k-step in the leading accumulator instead of one
   // (u 2.3e-7 -> 7.9e-7, gradient 6.9e-7 -> 1.2e-6), so it stays off.
   static constexpr bool CONCAT = false;
+  // two-level accumulation (second TMEM block for the small products) also in the data-gradient GEMM?
+  // Measured on C4: one accumulator saves TMEM reads in B1 (5.9 -> 5.2 k cycles per layer) but not a microsecond of
+  // the step (the backward pass is bound by the dgrad -> wgrad chain on the tensor pipe), and doubles the gradient
+  // error (6.9e-7 -> 1.5e-6): stays on.
+  static constexpr bool DGRAD_TWO_LEVEL = true;
   static constexpr int R1_BYTES = 3 * PLANE1, R2_BYTES = YP * PLANE2;
   static constexpr int NEPI = 4 * Q;
   static constexpr int NEPI_T = NEPI * 32;
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
         if (round > 0) tc::wait_bar(&bar_empty[s], (round - 1) & 1);
         mbar_expect_tx(&bar_full[s], C::SLOT);
         bulk_g2s(ring + s * C::SLOT, img + (size_t)c * C::SLOT, C::SLOT, &bar_full[s]);
-        if (TRAIN && c >= NG * C::CHUNKS && c % C::CHUNKS == 0) {
+        if (TRAIN && c >= NG * C::CHUNKS && c % C::CHUNKS == 0 && !(PROF && (L.exp_flags & 4))) {
           // first stage of dgrad(l): pull what the epilogue warps touch one layer later into L2 -- the stash of layer
           // l-1 (B2(l), B1(l-1)) and the accumulator block of layer l (flushed during iteration l-1).  The per-CTA
           // scratch of all SMs together is about the size of the L2, so a part of it lives in HBM between uses.
@@ -369,9 +378,9 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     // the columns [sum_p w_p*y0 | sum_p w_p*y1] at the N = 256 rate (128 cycles instead of 2 x 103); the sixth
     // product w0*y2 goes into the second block.  The epilogue adds the two blocks with a round-to-nearest add
     // (two-level accumulation; the extra w2*y1 term is 2^-24 of the leading one).
-    auto gemm_wx = [&]() {
+    auto gemm_wx = [&](bool two_level) {
       for (int mb = 0; mb < C::MB; ++mb) {
-        const uint32_t DB = tb + C::TC_D(mb), DS = DB + NROW;
+        const uint32_t DB = tb + C::TC_D(mb), DS = two_level ? DB + NROW : DB;
         for (int ks = 0; ks < C::KS; ++ks) {
           const uint64_t b01 = umma::smem_desc(r1a + ks * 16 * SWB, WP * SWB, 8 * SWB, LT);
           const uint64_t b2 = umma::smem_desc(r1a + 2 * C::PLANE1 + ks * 16 * SWB, WP * SWB, 8 * SWB, LT);
@@ -394,7 +403,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
             umma::mma_bf16_ss(DS, w1, b01, id_wx, 1u);
             umma::mma_bf16_ss(DS, w0, b2, id_wx, 1u);
             umma::mma_bf16_ss(DS, w0, b1, id_wx, 1u);
-            umma::mma_bf16_ss(DB, w0, b01, id_wx, acc);
+            umma::mma_bf16_ss(DB, w0, b01, id_wx, two_level ? acc : 1u);
           }
           umma::commit(&bar_empty[s]);
           ++ci;
@@ -430,7 +439,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
         tc::named_sync(TC_BAR_OP1, C::NEPI_T + 32);
         umma::fence_after_sync();
         const long long t0 = PROF ? clock64() : 0;
-        if (lane == 0) gemm_wx();
+        if (lane == 0) gemm_wx(true);   // forward: two-level accumulation (loss / residual precision)
         if (PROF && lane == 0) { tc::wait_bar(bar_fd, mp_fd); mp_fd ^= 1; gclk[0] += clock64() - t0; }
         __syncwarp();
       }
@@ -439,7 +448,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           tc::named_sync(TC_BAR_OP1, C::NEPI_T + 32);
           umma::fence_after_sync();
           const long long t0 = PROF ? clock64() : 0;
-          if (lane == 0) gemm_wx();
+          if (lane == 0) gemm_wx(C::DGRAD_TWO_LEVEL);
           __syncwarp();
           tc::named_sync(TC_BAR_OP2, C::NEPI_T + 32);
           umma::fence_after_sync();
@@ -462,6 +471,10 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     const int n8 = q;                                      // 8-point block of this warp
     uint32_t par_fd = 0, par_w = 0;
     auto epi_sync = [&]() { tc::named_sync(TC_BAR_EPI, C::NEPI_T); };
+    // Hand an operand tile to the MMA warp: writer-side generic -> async proxy fence (the conventional place), then a
+    // non-blocking arrive.  fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: it also waits for this
+    // thread's outstanding GLOBAL stores, which is why the stash stores of the last half are issued after it.
+    // (A consumer-side fence -- legal under the PTX memory model -- was measured: same speed, 20.39 vs 20.34 ms.)
     auto operands_ready = [&](int bar) {
       umma::fence_async_smem();
       umma::fence_before_sync();
@@ -503,6 +516,13 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < V; ++i) a[c][i] += sm[c][i];
     };
+    // data-gradient GEMM with ONE accumulator: half the TMEM read traffic of B1 (TMEM reads run at ~64 B/cycle/SM:
+    // measured 1.1 k cycles per half-pass for the two-block read)
+    auto load_acc1 = [&](float (&a)[K][V], int h) {
+#pragma unroll
+      for (int c = 0; c < K; ++c) umma::tmem_ld4(tl + C::TC_D(0) + c * NP + 8 * n8 + V * h, a[c]);
+      umma::tmem_ld_wait();
+    };
     auto load_beta = [&](float (&beta)[3][V], int h) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -519,18 +539,23 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     };
     // weight-gradient block (lane = output unit, columns = input units) -> CTA-private accumulator rows, coalesced
     auto flush_dw = [&](int l) {
+      if ((PROF && (L.exp_flags & 1)) || (TC_EXP & 1)) return;   // experiment: no accumulator flush (timing only, wrong gradient)
       constexpr int NC = 128 / Q;  // input units (columns) per warp
       float* gcol = gacc + net.off_w[l] + (size_t)(q * NC) * ldw + u;
       const uint32_t src = tl + C::TC_DW + 128 * (l & 1) + q * NC;
+      // The block is ADDED to the CTA-private accumulator rows with red.global.add.f32: the L2 performs the
+      // read-modify-write, nothing returns to the SM and the warps do not wait for a round trip (measured on C4:
+      // the load + add + store version cost 17 % of the step).  Each address is only ever updated by this one
+      // thread of this one CTA, tile after tile, so the order of the additions -- and with it every bit of the
+      // gradient -- is fixed by program order.
 #pragma unroll
-      for (int b = 0; b < NC / 16; ++b) {   // 16 accumulator loads in flight per round trip
-        float g[16], w[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) g[i] = gcol[(size_t)(16 * b + i) * ldw];
+      for (int b = 0; b < NC / 16; ++b) {
+        float w[16];
         umma::tmem_ld16(src + 16 * b, w);
         umma::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) gcol[(size_t)(16 * b + i) * ldw] = g[i] + w[i];
+        for (int i = 0; i < 16; ++i)
+          asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(gcol + (size_t)(16 * b + i) * ldw), "f"(w[i]) : "memory");
       }
       umma::fence_before_sync();
     };
@@ -628,9 +653,11 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           }
           if (TRAIN) {
             if (h == NH - 1 && !last) operands_ready(TC_BAR_OP1);
+            if (!(TC_EXP & 4)) {
 #pragma unroll
-            for (int c = 0; c < K; ++c) tc::st4(stash_ptr(l, c, h), sv[c]);
-            if (act == PINN_SIN) tc::st4(stash_ptr(l, K, h), sv[K]);
+              for (int c = 0; c < K; ++c) tc::st4(stash_ptr(l, c, h), sv[c]);
+              if (act == PINN_SIN) tc::st4(stash_ptr(l, K, h), sv[K]);
+            }
           }
         }
         if (!TRAIN && !last) operands_ready(TC_BAR_OP1);
@@ -701,9 +728,16 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           float stA[NH][K][V], csA[NH][V];
 #pragma unroll
           for (int h = 0; h < NH; ++h) {
+            if (TC_EXP & 8) {
 #pragma unroll
-            for (int c = 0; c < K; ++c) tc::ld4(stash_ptr(l, c, h), stA[h][c]);
-            if (act == PINN_SIN) tc::ld4(stash_ptr(l, K, h), csA[h]);
+              for (int c = 0; c < K; ++c)
+#pragma unroll
+                for (int i = 0; i < V; ++i) { stA[h][c][i] = 0.25f; csA[h][i] = 0.5f; }
+            } else {
+#pragma unroll
+              for (int c = 0; c < K; ++c) tc::ld4(stash_ptr(l, c, h), stA[h][c]);
+              if (act == PINN_SIN) tc::ld4(stash_ptr(l, K, h), csA[h]);
+            }
           }
           if (l < Lh - 1) {
             tc::wait_bar(bar_fd, par_fd);  // dgrad(l+1)
@@ -723,7 +757,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
               for (int i = 0; i < V; ++i) d1[i] = csA[h][i];
             }
             load_beta(beta, h);
-            if (l < Lh - 1) load_acc(yb, h);
+            if (l < Lh - 1) { if (C::DGRAD_TWO_LEVEL) load_acc(yb, h); else load_acc1(yb, h); }
             tc::act_bwd<V, true>(act, st[0], d1, d2, d3);
             if (l == Lh - 1) {
               // seeds: ybar[c] = (epsil * ubar_c) * wl[u]; the output-layer weight gradient needs the layer outputs
@@ -790,9 +824,16 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
 #pragma unroll 1
             for (int h = 0; h < NH; ++h) {
               float st[K][V], d1[V], d2[V], d3[V], beta[3][V];
+              if ((PROF && (L.exp_flags & 2)) || (TC_EXP & 2)) {  // experiment: B2 without its stash read (timing only)
 #pragma unroll
-              for (int c = 0; c < K; ++c) tc::ld4(stash_ptr(l - 1, c, h), st[c]);
-              if (actp == PINN_SIN) tc::ld4(stash_ptr(l - 1, K, h), d1);
+                for (int c = 0; c < K; ++c)
+#pragma unroll
+                  for (int i = 0; i < V; ++i) { st[c][i] = 0.25f; d1[i] = 0.5f; }
+              } else {
+#pragma unroll
+                for (int c = 0; c < K; ++c) tc::ld4(stash_ptr(l - 1, c, h), st[c]);
+                if (actp == PINN_SIN) tc::ld4(stash_ptr(l - 1, K, h), d1);
+              }
               load_beta(beta, h);
               tc::act_bwd<V, false>(actp, st[0], d1, d2, d3);
               {

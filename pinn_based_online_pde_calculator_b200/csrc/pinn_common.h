@@ -80,5 +80,6 @@ struct PinnLaunch {
   long long wimg_copy_bytes;  // bytes of one replica of the image stream
   int wimg_copies;         // replicas (CTA b reads replica b % copies: spreads the stream over the L2 slices)
   int ldw;                 // row stride of the hidden matrices in wpack / gacc
+  int exp_flags;           // experiment switches of the profiling instantiation (PINN_TC_EXP; 0 in production)
   PinnProgram prog;
 };

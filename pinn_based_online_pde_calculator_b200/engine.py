@@ -62,7 +62,7 @@ def load_library(path: Optional[str] = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or _LIB_PATH
+    p = path or os.environ.get("PINN_B200_LIB") or _LIB_PATH   # PINN_B200_LIB: alternative build (kernel experiments)
     if not os.path.exists(p):
         raise RuntimeError(
             f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

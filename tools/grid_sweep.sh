@@ -1,2 +1,2 @@
-timeout 300 python tools/tc_check.py C4s 2>&1 | grep -E "tc|grad|eval|info"
-for w in gacc; do echo "window $w"; PINN_B200_L2_WINDOW=$w timeout 300 python tools/tc_check.py timing 2>&1 | grep -E "tc:|phases"; done
+echo "production"; timeout 300 python tools/tc_check.py timing 2>&1 | grep -E "tc:"
+for e in 1 2 4 8 15; do echo "TC_EXP=$e"; PINN_B200_LIB=$PWD/pinn_based_online_pde_calculator_b200/libpinn_exp_$e.so timeout 300 python tools/tc_check.py timing 2>&1 | grep -E "tc:"; done

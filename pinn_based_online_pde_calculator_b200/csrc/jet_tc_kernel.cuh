@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           // l-1 (B2(l), B1(l-1)) and the accumulator block of layer l (flushed during iteration l-1).  The per-CTA
           // scratch of all SMs together is about the size of the L2, so a part of it lives in HBM between uses.
           const int l = (Lh - 1) - (c / C::CHUNKS - NG);
-          tc::prefetch_l2(L.stash + ((size_t)blockIdx.x * Lh + (l - 1)) * C::STL, (uint32_t)(C::STL * 4));
+          if (l > 1) tc::prefetch_l2(L.stash + ((size_t)blockIdx.x * Lh + (l - 1)) * C::STL, (uint32_t)(C::STL * 4));  // layer 0 has no stash
           tc::prefetch_l2(L.gacc + (size_t)blockIdx.x * net.pg + net.off_w[l], (uint32_t)(128 * L.ldw * 4));
         }
         if (++c == per_tile) c = 0;
@@ -533,6 +533,27 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
         }
       }
     };
+    // Layer 0 has no stash: its pre-activation jets are three FMAs per value away from the tile's feature jets
+    // (shared memory), so the backward pass recomputes them (and the activation) instead of a global round trip.
+    // st[0] = y, st[c > 0] = pre-activation jets, cs = cos for the sin activation -- the layout of a stash read.
+    auto layer0_stash = [&](float (&st)[K][V], float (&cs)[V], int h) {
+      const float w00 = __ldg(L.wpack + net.off_w0 + u), w01 = __ldg(L.wpack + net.off_w0 + WP + u),
+                  w02 = __ldg(L.wpack + net.off_w0 + 2 * WP + u);
+      const float bias = __ldg(L.wpack + net.off_b[0] + u);
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const float4 hh = *reinterpret_cast<const float4*>(s_hj + ((8 * n8 + V * h + i) * K + c) * 4);
+          st[c][i] = net.scl * fmaf(hh.x, w00, fmaf(hh.y, w01, hh.z * w02));
+        }
+      float a0[V], y[V], d2[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) a0[i] = st[0][i] + bias;
+      tc::act_fwd<V>(net.act_first, a0, y, cs, d2);
+#pragma unroll
+      for (int i = 0; i < V; ++i) st[0][i] = y[i];
+    };
     // stash slot of (layer, channel, half); channel K = cos of the sin activation
     auto stash_ptr = [&](int l, int c, int h) -> float* {
       return stash + (size_t)l * C::STL + ((size_t)(c * Q + q) * 128 + u) * 8 + V * h;
@@ -653,7 +674,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           }
           if (TRAIN) {
             if (h == NH - 1 && !last) operands_ready(TC_BAR_OP1);
-            if (!(TC_EXP & 4)) {
+            if (!(TC_EXP & 4) && l > 0) {
 #pragma unroll
               for (int c = 0; c < K; ++c) tc::st4(stash_ptr(l, c, h), sv[c]);
               if (act == PINN_SIN) tc::st4(stash_ptr(l, K, h), sv[K]);
@@ -733,6 +754,8 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
               for (int c = 0; c < K; ++c)
 #pragma unroll
                 for (int i = 0; i < V; ++i) { stA[h][c][i] = 0.25f; csA[h][i] = 0.5f; }
+            } else if (l == 0) {
+              layer0_stash(stA[h], csA[h], h);
             } else {
 #pragma unroll
               for (int c = 0; c < K; ++c) tc::ld4(stash_ptr(l, c, h), stA[h][c]);
@@ -829,6 +852,8 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
                 for (int c = 0; c < K; ++c)
 #pragma unroll
                   for (int i = 0; i < V; ++i) { st[c][i] = 0.25f; d1[i] = 0.5f; }
+              } else if (l == 1) {
+                layer0_stash(st, d1, h);
               } else {
 #pragma unroll
                 for (int c = 0; c < K; ++c) tc::ld4(stash_ptr(l - 1, c, h), st[c]);

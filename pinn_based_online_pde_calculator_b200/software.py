@@ -45,17 +45,19 @@ class Key:
 
 
 # --------------------------------------------------------------------------- sampling (sw:71-136, 521-577)
-def lhs(n: int, samples: int) -> np.ndarray:
-    """pyDOE.lhs(n, samples) (criterion=None), consuming the GLOBAL numpy stream the
-    reference seeds at sw:687: stratified (i+U)/N per dimension, then one independent
-    permutation per dimension."""
+def lhs(n: int, samples: int, rs=None) -> np.ndarray:
+    """pyDOE.lhs(n, samples) (criterion=None): stratified (i+U)/N per dimension, then one independent
+    permutation per dimension.  The reference draws from the GLOBAL numpy stream it seeds at sw:687 (two
+    concurrent sessions clobber each other); here every run_pinn_training call owns a RandomState(seed) --
+    the same legacy stream, so a single run draws exactly what the seeded global stream would give."""
+    rs = rs if rs is not None else np.random
     cut = np.linspace(0, 1, samples + 1)
-    u = np.random.rand(samples, n)
+    u = rs.rand(samples, n)
     a, b = cut[:samples], cut[1:samples + 1]
     rd = u * (b - a)[:, None] + a[:, None]
     H = np.zeros_like(rd)
     for j in range(n):
-        order = np.random.permutation(range(samples))
+        order = rs.permutation(range(samples))
         H[:, j] = rd[order, j]
     return H
 
@@ -93,7 +95,7 @@ def colloc2D_set(key: Key, X: np.ndarray, Y: np.ndarray, F: np.ndarray, Ns: int)
 
 
 def data_func_create(N_col: Sequence[int], N_bd: int, boundary: Dict[str, float], domain: Dict[str, float],
-                     sampler: str = "host", device: int = 0):
+                     sampler: str = "host", device: int = 0, rs=None):
     """sw:521-577. N_col = [n_col (LHS interior), n_bd (border-ring collocation), n_add
     (residual-adaptive)]; N_bd = points per boundary condition (sw:694).
     sampler='device' draws the collocation set with the CUDA samplers (pinn_sample_lhs /
@@ -115,7 +117,7 @@ def data_func_create(N_col: Sequence[int], N_bd: int, boundary: Dict[str, float]
         for i in range(num):
             lo = np.array([boundary[f"bd_x{i + 1}_min"], boundary[f"bd_y{i + 1}_min"]], dtype=np.float64)
             hi = np.array([boundary[f"bd_x{i + 1}_max"], boundary[f"bd_y{i + 1}_max"]], dtype=np.float64)
-            x_bd.append(lhs(2, N_bd) * (hi - lo) + lo)
+            x_bd.append(lhs(2, N_bd, rs) * (hi - lo) + lo)
             u_bd.append(boundary[f"bd_u{i + 1}"] * np.ones((N_bd, 1)))
         if sampler == "device":
             import torch
@@ -128,7 +130,7 @@ def data_func_create(N_col: Sequence[int], N_bd: int, boundary: Dict[str, float]
             parts += [torch.as_tensor(a, dtype=torch.float32, device=f"cuda:{device}") for a in x_bd]
             parts.append(sample_cdf2d_device(int(N_col[2]), R_add, T_add, np.asarray(F), s2, device))
             return dict(x_col=torch.cat(parts, 0), cond_bd=[x_bd, u_bd])
-        x_col = lhs(2, int(N_col[0])) * span + org
+        x_col = lhs(2, int(N_col[0]), rs) * span + org
         xc_bd = colloc2D_set(keys[0], R, T, F_bd, N_col[1])
         xc_add = colloc2D_set(keys[1], R_add, T_add, np.asarray(F), N_col[2])
         x_col = np.vstack([x_col, xc_bd] + x_bd + [xc_add])  # BC points join the collocation set (sw:569)
@@ -328,7 +330,7 @@ def run_pinn_training(
     base_dir.mkdir(parents=True, exist_ok=True)
 
     key = Key(seed)
-    np.random.seed(seed)
+    rs = np.random.RandomState(seed)  # per-call stream (the reference seeds the process-global one, sw:687)
     keys = key.split(10)
     N_col = np.array([sample_points["n_col"], sample_points["n_bd"], sample_points["n_add"]])
     N_bd = n_bd_points
@@ -350,7 +352,7 @@ def run_pinn_training(
                        feature_map=feature_map, d_in=2)
     model1 = Model(net1, eq, n_bc, lw_eqn=m_f, device=device)
     model1.engine.set_params(init_params(net1, seed))
-    dataf1 = data_func_create(N_col, N_bd, boundary, domain, sampler=sampler, device=device)
+    dataf1 = data_func_create(N_col, N_bd, boundary, domain, sampler=sampler, device=device, rs=rs)
     Fs = R * 0 + 1
     key_adam = keys[1]
     key_lbfgs = keys[2].split(1)
@@ -401,7 +403,7 @@ def run_pinn_training(
                        feature_map=feature_map, d_in=2)
     model2 = Model(net2, eq, n_bc, lw_eqn=lw2, device=device, base=model1)
     model2.engine.set_params(init_params(net2, seed + 3))
-    dataf2 = data_func_create(N_col * 2, N_bd * 2, boundary, domain, sampler=sampler, device=device)
+    dataf2 = data_func_create(N_col * 2, N_bd * 2, boundary, domain, sampler=sampler, device=device, rs=rs)
     key_adam = keys[4]
     key_lbfgs = keys[5].split(1)
     Fg = Rg * 0 + 1

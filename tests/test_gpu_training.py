@@ -82,3 +82,47 @@ def test_compiled_equation_is_used_when_it_parses(tmp_path):
     rel_l2 = np.sqrt(np.mean(res["Error1"] ** 2)) / np.sqrt(np.mean(exact(X, Y) ** 2))
     print("poisson rel_l2", rel_l2)
     assert rel_l2 < 5e-2, rel_l2
+
+
+def test_daemon_thread_call_next_to_a_second_handle(tmp_path):
+    """The reference starts run_pinn_training on a NON-MAIN daemon thread (callbacks/training.py:111) and nothing
+    stops a second click while a run is alive: per-call engine state, no globals.  A daemon thread trains the
+    reference's smoke problem while the main thread trains a different problem on its own handles; both must
+    produce exactly what they produce alone (bitwise: every engine owns its stream, scratch and graphs)."""
+    import threading
+
+    from pinn_based_online_pde_calculator_b200.software import run_pinn_training
+    from tests.helpers import engine_for, make_problem
+
+    pb = make_problem(n_hidden=3, width=48, d_in=2, expr="u_xx + u_yy + x*y", n_col=4000, n_bd=100, n_bc=4, lb=[0, 0], ub=[1, 1])
+
+    def train_alone():
+        eng = engine_for(pb)
+        eng.adam_init()
+        rows = eng.adam_steps(200, 1e-3)
+        res, _ = eng.lbfgs(20, 1e-10)
+        p = eng.get_params()
+        eng.close()
+        return rows, p, res
+
+    rows_ref, p_ref, res_ref = train_alone()
+    solo = run_pinn_training(**KW, epochs={"adam": 300, "lbfgs": 30}, output_dir=str(tmp_path / "solo"), stage2=False)
+
+    box = {}
+
+    def daemon():
+        try:
+            box["res"] = run_pinn_training(**KW, epochs={"adam": 300, "lbfgs": 30}, output_dir=str(tmp_path / "thr"), stage2=False)
+        except BaseException as e:  # noqa: BLE001 - the test reports it
+            box["err"] = e
+
+    t = threading.Thread(target=daemon, daemon=True)
+    t.start()
+    outs = [train_alone() for _ in range(3)]   # main thread: other handles, same device, while the daemon trains
+    t.join(timeout=600)
+    assert not t.is_alive() and "err" not in box, box.get("err")
+    for rows, p, res in outs:
+        assert np.array_equal(rows, rows_ref) and np.array_equal(p, p_ref) and res == res_ref
+    assert np.array_equal(box["res"]["loss_1"], solo["loss_1"])
+    assert np.array_equal(box["res"]["U1"], solo["U1"])
+    assert (tmp_path / "thr" / "loss_1.npz").exists()

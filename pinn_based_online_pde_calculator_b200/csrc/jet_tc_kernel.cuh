@@ -54,7 +54,14 @@ struct TcCfg {
   // [y0 | y1] as ONE N = 2*NROW operand (four MMAs per k-step instead of six).  Measured on C4: no gain (the tensor
   // pipe is not the limiter) and three truncating adds per k-step in the leading accumulator instead of one
   // (u 2.3e-7 -> 7.9e-7, gradient 6.9e-7 -> 1.2e-6), so it stays off.
-  static constexpr bool CONCAT = false;
+#ifndef TC_CONCAT_FWD
+#define TC_CONCAT_FWD 0
+#endif
+  static constexpr bool CONCAT = (TC_CONCAT_FWD != 0) && (MB == 2) && (2 * NROW <= 256);
+  // ... but in the DATA-GRADIENT GEMM of the two-block kernel (padded width 256: N = 80 per plane, the tensor pipe is
+  // the limiter there and an MMA costs 103 cycles for any N <= 192) the concatenated form saves a third of the MMAs;
+  // the gradient tolerates the two extra truncating adds per k-step (measured on C5: see DESIGN.md).
+  static constexpr bool CONCAT_DGRAD = (MB == 2) && (2 * NROW <= 256);
   // two-level accumulation (second TMEM block for the small products) also in the data-gradient GEMM?
   // Measured on C4: one accumulator saves TMEM reads in B1 (5.9 -> 5.2 k cycles per layer) but not a microsecond of
   // the step (the backward pass is bound by the dgrad -> wgrad chain on the tensor pipe), and doubles the gradient
@@ -73,14 +80,15 @@ struct TcCfg {
   static constexpr int PARTLD = NROW + 4;                    // row stride of the output-layer partial products
   // TMEM columns: per M block (big | small) accumulators, then two weight-gradient blocks (ping-pong)
   __host__ __device__ static constexpr int TC_D(int mb) { return mb * 2 * NROW; }
-  static constexpr int TC_DW = MB * 2 * NROW;
-  static constexpr int TC_USED = TC_DW + 256;
+  static constexpr int TC_DW = MB * 2 * NROW;                // weight-gradient blocks of 128 columns: two (ping-pong) for one M block,
+  static constexpr int NDW = (MB == 1) ? 2 : 1;              // one for two (the accumulators of both M blocks take 4*NROW columns)
+  static constexpr int TC_USED = TC_DW + 128 * NDW;
   static constexpr int MISC_FLOATS = NP * 4 /*z*/ + 3 * NP /*beta*/ + NP * K * 4 /*hj*/ + NROW /*ubar*/ + 4 * NROW /*psum*/ +
                                      Q * WP /*gradient partials*/ + PINN_MAX_OPS + PINN_MAX_CONSTS;
   static constexpr size_t smem_bytes() { return (size_t)R1_BYTES + R2_BYTES + NSLOT * SLOT + MISC_FLOATS * 4 + 256; }
   static constexpr size_t STL = (size_t)(K + 1) * WP * NP;   // stash floats per layer and CTA (K jets + cos for the sin activation)
   static constexpr bool OK = (NROW % 16 == 0) && (NROW <= 256) && (TC_USED <= 512) && (smem_bytes() <= 232448 - 1024) &&
-                             ((size_t)WP * PARTLD * 4 <= (size_t)R1_BYTES) && (MB == 1);
+                             ((size_t)WP * PARTLD * 4 <= (size_t)R1_BYTES) && (MB <= 2);
 };
 
 namespace tc {
@@ -291,7 +299,7 @@ __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("ba
 
 }  // namespace tc
 
-enum { TC_BAR_EPI = 1, TC_BAR_OP1 = 2, TC_BAR_OP2 = 3 };
+enum { TC_BAR_EPI = 1, TC_BAR_OP1 = 2, TC_BAR_OP2 = 3, TC_BAR_OP3 = 4 };
 
 // ---------------------------------------------------------------- the kernel
 template <class C, bool TRAIN, bool PROF = false>
@@ -361,7 +369,8 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           // scratch of all SMs together is about the size of the L2, so a part of it lives in HBM between uses.
           const int l = (Lh - 1) - (c / C::CHUNKS - NG);
           if (l > 1) tc::prefetch_l2(L.stash + ((size_t)blockIdx.x * Lh + (l - 1)) * C::STL, (uint32_t)(C::STL * 4));  // layer 0 has no stash
-          tc::prefetch_l2(L.gacc + (size_t)blockIdx.x * net.pg + net.off_w[l], (uint32_t)(128 * L.ldw * 4));
+          for (int blk = 0; blk < C::MB; ++blk)
+            tc::prefetch_l2(L.gacc + (size_t)blockIdx.x * net.pg + net.off_w[l] + (size_t)blk * 128 * L.ldw, (uint32_t)(128 * L.ldw * 4));
         }
         if (++c == per_tile) c = 0;
       }
@@ -370,7 +379,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     // ================================================================ MMA issue warp
     long long ci = 0;
     const uint32_t id_wx = umma::idesc_bf16(128, NROW, 0, 1);
-    const uint32_t id_wx2 = umma::idesc_bf16(128, C::CONCAT ? 2 * NROW : NROW, 0, 1);
+    const uint32_t id_wx2 = umma::idesc_bf16(128, (2 * NROW <= 256) ? 2 * NROW : NROW, 0, 1);
     const uint32_t id_wg = umma::idesc_bf16(128, 128, 0, 0);
     const uint32_t r1a = umma::smem_addr(R1), r2a = umma::smem_addr(R2), rga = umma::smem_addr(ring);
     // D = W x act(R1), weights from the ring.  Per k-step FOUR MMAs: the activation planes b0 and b1 lie back to
@@ -378,7 +387,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     // the columns [sum_p w_p*y0 | sum_p w_p*y1] at the N = 256 rate (128 cycles instead of 2 x 103); the sixth
     // product w0*y2 goes into the second block.  The epilogue adds the two blocks with a round-to-nearest add
     // (two-level accumulation; the extra w2*y1 term is 2^-24 of the leading one).
-    auto gemm_wx = [&](bool two_level) {
+    auto gemm_wx = [&](bool two_level, bool concat) {
       for (int mb = 0; mb < C::MB; ++mb) {
         const uint32_t DB = tb + C::TC_D(mb), DS = two_level ? DB + NROW : DB;
         for (int ks = 0; ks < C::KS; ++ks) {
@@ -391,7 +400,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           const uint64_t w2 = umma::smem_desc(rga + s * C::SLOT, 16, 256, 6);
           const uint64_t w1 = umma::smem_desc(rga + s * C::SLOT + C::PLANE_W, 16, 256, 6);
           const uint64_t w0 = umma::smem_desc(rga + s * C::SLOT + 2 * C::PLANE_W, 16, 256, 6);
-          if (C::CONCAT) {
+          if (concat) {
             umma::mma_bf16_ss(DB, w2, b01, id_wx2, acc);
             umma::mma_bf16_ss(DB, w1, b01, id_wx2, 1u);
             umma::mma_bf16_ss(DB, w0, b01, id_wx2, 1u);
@@ -414,12 +423,12 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     // DW[out][in] = sum_n G[out][n] * Y[in][n]: G in R1 (M rows = output units: the flush then writes the gradient
     // with coalesced accesses), Y block in R2 (two planes), both K-major views; five products (everything down
     // to 2^-16 of the leading term; the sum over the points averages the remaining rounding noise)
-    auto gemm_wgrad = [&](int buf) {
+    auto gemm_wgrad = [&](int buf, int iblk) {   // iblk: block of 128 OUTPUT units (rows of G) -> TMEM lanes
       const uint32_t DW = tb + C::TC_DW + 128 * buf;
       for (int ks = 0; ks < C::KSW; ++ks) {
         uint64_t ag[3], by[2];
 #pragma unroll
-        for (int p = 0; p < 3; ++p) ag[p] = umma::smem_desc(r1a + p * C::PLANE1 + tc::kmajor_koff<SWB>(ks, WP), 16, 8 * SWB, LT);
+        for (int p = 0; p < 3; ++p) ag[p] = umma::smem_desc(r1a + p * C::PLANE1 + iblk * 128 * SWB + tc::kmajor_koff<SWB>(ks, WP), 16, 8 * SWB, LT);
 #pragma unroll
         for (int p = 0; p < 2; ++p) by[p] = umma::smem_desc(r2a + p * C::PLANE2 + tc::kmajor_koff<SWB>(ks, 128), 16, 8 * SWB, LT);
         umma::mma_bf16_ss(DW, ag[2], by[0], id_wg, ks > 0 ? 1u : 0u);
@@ -439,8 +448,8 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
         tc::named_sync(TC_BAR_OP1, C::NEPI_T + 32);
         umma::fence_after_sync();
         const long long t0 = PROF ? clock64() : 0;
-        if (lane == 0) gemm_wx(true);   // forward: two-level accumulation (loss / residual precision)
-        if (PROF && lane == 0) { tc::wait_bar(bar_fd, mp_fd); mp_fd ^= 1; gclk[0] += clock64() - t0; }
+        if (lane == 0) gemm_wx(true, C::CONCAT);   // forward: two-level accumulation (loss / residual precision)
+        if (PROF && C::MB == 1 && lane == 0) { tc::wait_bar(bar_fd, mp_fd); mp_fd ^= 1; gclk[0] += clock64() - t0; }
         __syncwarp();
       }
       if (TRAIN) {
@@ -448,17 +457,32 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           tc::named_sync(TC_BAR_OP1, C::NEPI_T + 32);
           umma::fence_after_sync();
           const long long t0 = PROF ? clock64() : 0;
-          if (lane == 0) gemm_wx(C::DGRAD_TWO_LEVEL);
+          if (lane == 0) gemm_wx(C::DGRAD_TWO_LEVEL, C::CONCAT_DGRAD);
           __syncwarp();
-          tc::named_sync(TC_BAR_OP2, C::NEPI_T + 32);
-          umma::fence_after_sync();
-          const long long t1 = PROF ? clock64() : 0;
-          if (lane == 0) gemm_wgrad(l & 1);
-          if (PROF && lane == 0) {
-            tc::wait_bar(bar_fd, mp_fd); mp_fd ^= 1; gclk[1] += clock64() - t0;
-            tc::wait_bar(bar_w, mp_w); mp_w ^= 1; gclk[2] += clock64() - t1;
+          if (C::MB == 1) {
+            tc::named_sync(TC_BAR_OP2, C::NEPI_T + 32);
+            umma::fence_after_sync();
+            const long long t1 = PROF ? clock64() : 0;
+            if (lane == 0) gemm_wgrad(l & 1, 0);
+            if (PROF && lane == 0) {
+              tc::wait_bar(bar_fd, mp_fd); mp_fd ^= 1; gclk[1] += clock64() - t0;
+              tc::wait_bar(bar_w, mp_w); mp_w ^= 1; gclk[2] += clock64() - t1;
+            }
+            __syncwarp();
+          } else {
+            // two blocks of input units (the Y block in R2 is recomputed per block) x two blocks of output units;
+            // ONE weight-gradient block in TMEM: the epilogue warps drain it between the two output blocks
+            for (int j = 0; j < C::MB; ++j) {
+              tc::named_sync(TC_BAR_OP2, C::NEPI_T + 32);
+              umma::fence_after_sync();
+              if (lane == 0) gemm_wgrad(0, 0);
+              __syncwarp();
+              tc::named_sync(TC_BAR_OP3, C::NEPI_T + 32);
+              umma::fence_after_sync();
+              if (lane == 0) gemm_wgrad(0, 1);
+              __syncwarp();
+            }
           }
-          __syncwarp();
         }
       }
     }
@@ -483,7 +507,9 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     float* const stash = TRAIN ? (L.stash + (size_t)blockIdx.x * Lh * C::STL) : nullptr;
     float* const gacc = TRAIN ? (L.gacc + (size_t)blockIdx.x * net.pg) : nullptr;
     const int ldw = L.ldw;
-    float wlacc = 0.f, w0acc[3] = {0.f, 0.f, 0.f}, blacc = 0.f;
+    float wlacc[C::MB], w0acc[C::MB][3], blacc = 0.f;   // this thread's units: u, u + 128 (one per M block)
+#pragma unroll
+    for (int mb = 0; mb < C::MB; ++mb) { wlacc[mb] = 0.f; w0acc[mb][0] = w0acc[mb][1] = w0acc[mb][2] = 0.f; }
     double lcur = 0.0;
     const int slot = L.seg_slot[0];
     const long long n_end = L.seg_pt_end[0];
@@ -503,12 +529,12 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
       }
     };
     // accumulators of the last forward / data-gradient GEMM (big + small), points 4h..4h+3 of the block
-    auto load_acc = [&](float (&a)[K][V], int h) {
+    auto load_acc = [&](float (&a)[K][V], int h, int mb) {
       float sm[K][V];
 #pragma unroll
       for (int c = 0; c < K; ++c) {
-        umma::tmem_ld4(tl + C::TC_D(0) + c * NP + 8 * n8 + V * h, a[c]);
-        umma::tmem_ld4(tl + C::TC_D(0) + NROW + c * NP + 8 * n8 + V * h, sm[c]);
+        umma::tmem_ld4(tl + C::TC_D(mb) + c * NP + 8 * n8 + V * h, a[c]);
+        umma::tmem_ld4(tl + C::TC_D(mb) + NROW + c * NP + 8 * n8 + V * h, sm[c]);
       }
       umma::tmem_ld_wait();
 #pragma unroll
@@ -518,9 +544,9 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     };
     // data-gradient GEMM with ONE accumulator: half the TMEM read traffic of B1 (TMEM reads run at ~64 B/cycle/SM:
     // measured 1.1 k cycles per half-pass for the two-block read)
-    auto load_acc1 = [&](float (&a)[K][V], int h) {
+    auto load_acc1 = [&](float (&a)[K][V], int h, int mb) {
 #pragma unroll
-      for (int c = 0; c < K; ++c) umma::tmem_ld4(tl + C::TC_D(0) + c * NP + 8 * n8 + V * h, a[c]);
+      for (int c = 0; c < K; ++c) umma::tmem_ld4(tl + C::TC_D(mb) + c * NP + 8 * n8 + V * h, a[c]);
       umma::tmem_ld_wait();
     };
     auto load_beta = [&](float (&beta)[3][V], int h) {
@@ -536,10 +562,10 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     // Layer 0 has no stash: its pre-activation jets are three FMAs per value away from the tile's feature jets
     // (shared memory), so the backward pass recomputes them (and the activation) instead of a global round trip.
     // st[0] = y, st[c > 0] = pre-activation jets, cs = cos for the sin activation -- the layout of a stash read.
-    auto layer0_stash = [&](float (&st)[K][V], float (&cs)[V], int h) {
-      const float w00 = __ldg(L.wpack + net.off_w0 + u), w01 = __ldg(L.wpack + net.off_w0 + WP + u),
-                  w02 = __ldg(L.wpack + net.off_w0 + 2 * WP + u);
-      const float bias = __ldg(L.wpack + net.off_b[0] + u);
+    auto layer0_stash = [&](float (&st)[K][V], float (&cs)[V], int h, int uu) {
+      const float w00 = __ldg(L.wpack + net.off_w0 + uu), w01 = __ldg(L.wpack + net.off_w0 + WP + uu),
+                  w02 = __ldg(L.wpack + net.off_w0 + 2 * WP + uu);
+      const float bias = __ldg(L.wpack + net.off_b[0] + uu);
 #pragma unroll
       for (int i = 0; i < V; ++i)
 #pragma unroll
@@ -555,15 +581,15 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
       for (int i = 0; i < V; ++i) st[0][i] = y[i];
     };
     // stash slot of (layer, channel, half); channel K = cos of the sin activation
-    auto stash_ptr = [&](int l, int c, int h) -> float* {
-      return stash + (size_t)l * C::STL + ((size_t)(c * Q + q) * 128 + u) * 8 + V * h;
+    auto stash_ptr = [&](int l, int c, int h, int mb) -> float* {
+      return stash + (size_t)l * C::STL + ((size_t)((mb * (K + 1) + c) * Q + q) * 128 + u) * 8 + V * h;
     };
     // weight-gradient block (lane = output unit, columns = input units) -> CTA-private accumulator rows, coalesced
-    auto flush_dw = [&](int l) {
+    auto flush_dw = [&](int l, int buf, int iblk, int jblk) {   // block (output units 128*iblk.., input units 128*jblk..)
       if ((PROF && (L.exp_flags & 1)) || (TC_EXP & 1)) return;   // experiment: no accumulator flush (timing only, wrong gradient)
       constexpr int NC = 128 / Q;  // input units (columns) per warp
-      float* gcol = gacc + net.off_w[l] + (size_t)(q * NC) * ldw + u;
-      const uint32_t src = tl + C::TC_DW + 128 * (l & 1) + q * NC;
+      float* gcol = gacc + net.off_w[l] + (size_t)(128 * jblk + q * NC) * ldw + 128 * iblk + u;
+      const uint32_t src = tl + C::TC_DW + 128 * buf + q * NC;
       // The block is ADDED to the CTA-private accumulator rows with red.global.add.f32: the L2 performs the
       // read-modify-write, nothing returns to the SM and the warps do not wait for a round trip (measured on C4:
       // the load + add + store version cost 17 % of the step).  Each address is only ever updated by this one
@@ -614,17 +640,21 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
 #pragma unroll 1
       for (int l = 0; l < Lh; ++l) {
         const int act = (l == 0) ? net.act_first : net.act_hidden;
-        const float bias = __ldg(L.wpack + net.off_b[l] + u);
         const bool last = (l == Lh - 1);
-        const float wlv = last ? __ldg(L.wpack + net.off_wl + u) : 0.f;
-        float w00 = 0.f, w01 = 0.f, w02 = 0.f;
-        if (l == 0) {
-          w00 = __ldg(L.wpack + net.off_w0 + u); w01 = __ldg(L.wpack + net.off_w0 + WP + u); w02 = __ldg(L.wpack + net.off_w0 + 2 * WP + u);
-        } else {
+        if (l > 0) {
           tc::wait_bar(bar_fd, par_fd);
           par_fd ^= 1;
           umma::fence_after_sync();
           lap(0);
+        }
+#pragma unroll 1
+        for (int mb = 0; mb < C::MB; ++mb) {
+        const int uu = u + 128 * mb;                       // unit of this pass (= line of the operand tiles)
+        const float bias = __ldg(L.wpack + net.off_b[l] + uu);
+        const float wlv = last ? __ldg(L.wpack + net.off_wl + uu) : 0.f;
+        float w00 = 0.f, w01 = 0.f, w02 = 0.f;
+        if (l == 0) {
+          w00 = __ldg(L.wpack + net.off_w0 + uu); w01 = __ldg(L.wpack + net.off_w0 + WP + uu); w02 = __ldg(L.wpack + net.off_w0 + 2 * WP + uu);
         }
         float sv[K + 1][V];   // stash values of the half in flight
 #pragma unroll 1
@@ -639,7 +669,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
                 a[c][i] = net.scl * fmaf(hh.x, w00, fmaf(hh.y, w01, hh.z * w02));
               }
           } else {
-            load_acc(a, h);
+            load_acc(a, h, mb);
           }
           float beta[3][V];
           load_beta(beta, h);
@@ -662,25 +692,26 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           }
           if (!last) {
 #pragma unroll
-            for (int c = 0; c < K; ++c) tc::store_split4<3>(R1 + tc::chunk_off<SWB>(u, c * PB + n8, WP), C::PLANE1, h, a[c]);
+            for (int c = 0; c < K; ++c) tc::store_split4<3>(R1 + tc::chunk_off<SWB>(uu, c * PB + n8, WP), C::PLANE1, h, a[c]);
           } else {
 #pragma unroll
             for (int c = 0; c < K; ++c) {
               float pv[V];
 #pragma unroll
               for (int i = 0; i < V; ++i) pv[i] = a[c][i] * wlv;
-              tc::st4(part + (size_t)u * C::PARTLD + c * NP + 8 * n8 + V * h, pv);
+              tc::st4(part + (size_t)uu * C::PARTLD + c * NP + 8 * n8 + V * h, pv);
             }
           }
           if (TRAIN) {
-            if (h == NH - 1 && !last) operands_ready(TC_BAR_OP1);
+            if (mb == C::MB - 1 && h == NH - 1 && !last) operands_ready(TC_BAR_OP1);
             if (!(TC_EXP & 4) && l > 0) {
 #pragma unroll
-              for (int c = 0; c < K; ++c) tc::st4(stash_ptr(l, c, h), sv[c]);
-              if (act == PINN_SIN) tc::st4(stash_ptr(l, K, h), sv[K]);
+              for (int c = 0; c < K; ++c) tc::st4(stash_ptr(l, c, h, mb), sv[c]);
+              if (act == PINN_SIN) tc::st4(stash_ptr(l, K, h, mb), sv[K]);
             }
           }
         }
+        }  // mb
         if (!TRAIN && !last) operands_ready(TC_BAR_OP1);
         lap(1);
       }
@@ -738,7 +769,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
       // ---------------- backward.  Per layer l the epilogue warps run B1(l) (adjoint of the pre-activations -> G),
       // B2(l) (the layer's input jets again -> Y) and the flush of the PREVIOUS layer's weight-gradient block,
       // while the tensor core works on dgrad(l) and wgrad(l) (ping-pong weight-gradient blocks in TMEM).
-      if (TRAIN) {
+      if (TRAIN && C::MB == 1) {
         const float wlv = __ldg(L.wpack + net.off_wl + u);
 #pragma unroll 1
         for (int l = Lh - 1; l >= 0; --l) {
@@ -755,11 +786,11 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < V; ++i) { stA[h][c][i] = 0.25f; csA[h][i] = 0.5f; }
             } else if (l == 0) {
-              layer0_stash(stA[h], csA[h], h);
+              layer0_stash(stA[h], csA[h], h, u);
             } else {
 #pragma unroll
-              for (int c = 0; c < K; ++c) tc::ld4(stash_ptr(l, c, h), stA[h][c]);
-              if (act == PINN_SIN) tc::ld4(stash_ptr(l, K, h), csA[h]);
+              for (int c = 0; c < K; ++c) tc::ld4(stash_ptr(l, c, h, 0), stA[h][c]);
+              if (act == PINN_SIN) tc::ld4(stash_ptr(l, K, h, 0), csA[h]);
             }
           }
           if (l < Lh - 1) {
@@ -780,7 +811,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
               for (int i = 0; i < V; ++i) d1[i] = csA[h][i];
             }
             load_beta(beta, h);
-            if (l < Lh - 1) { if (C::DGRAD_TWO_LEVEL) load_acc(yb, h); else load_acc1(yb, h); }
+            if (l < Lh - 1) { if (C::DGRAD_TWO_LEVEL) load_acc(yb, h, 0); else load_acc1(yb, h, 0); }
             tc::act_bwd<V, true>(act, st[0], d1, d2, d3);
             if (l == Lh - 1) {
               // seeds: ybar[c] = (epsil * ubar_c) * wl[u]; the output-layer weight gradient needs the layer outputs
@@ -803,7 +834,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
                     for (int k = 0; k < C::N1; ++k) S = fmaf(beta[k][i] * st[1 + k][i], st[1 + k][i], S);
                     o = fmaf(d2[i], S, d1[i] * st[c][i]);
                   }
-                  wlacc = fmaf(ub[i], o, wlacc);
+                  wlacc[0] = fmaf(ub[i], o, wlacc[0]);
                   yb[c][i] = ub[i] * wlv;
                 }
               }
@@ -828,9 +859,9 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
                 for (int c = 0; c < K; ++c) {
                   const float4 hh = *reinterpret_cast<const float4*>(s_hj + ((8 * n8 + V * h + i) * K + c) * 4);
                   const float t = net.scl * yb[c][i];
-                  w0acc[0] = fmaf(hh.x, t, w0acc[0]);
-                  w0acc[1] = fmaf(hh.y, t, w0acc[1]);
-                  w0acc[2] = fmaf(hh.z, t, w0acc[2]);
+                  w0acc[0][0] = fmaf(hh.x, t, w0acc[0][0]);
+                  w0acc[0][1] = fmaf(hh.y, t, w0acc[0][1]);
+                  w0acc[0][2] = fmaf(hh.z, t, w0acc[0][2]);
                 }
             }
           }
@@ -840,7 +871,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           if (l > 0) {
             // ---- F(l+1): flush the previous layer's weight-gradient block (wgrad(l+1) completed: B1 waited for it)
             // first -- global traffic only, dgrad(l) has the shared-memory bandwidth to itself meanwhile
-            if (l < Lh - 1) flush_dw(l + 1);
+            if (l < Lh - 1) flush_dw(l + 1, (l + 1) & 1, 0, 0);
             lap(6);
             // ---- B2(l): the layer's input jets Y^(l-1) again (from the stash of layer l-1) -> R2 (two planes)
             const int actp = (l - 1 == 0) ? net.act_first : net.act_hidden;
@@ -853,11 +884,11 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
 #pragma unroll
                   for (int i = 0; i < V; ++i) { st[c][i] = 0.25f; d1[i] = 0.5f; }
               } else if (l == 1) {
-                layer0_stash(st, d1, h);
+                layer0_stash(st, d1, h, u);
               } else {
 #pragma unroll
-                for (int c = 0; c < K; ++c) tc::ld4(stash_ptr(l - 1, c, h), st[c]);
-                if (actp == PINN_SIN) tc::ld4(stash_ptr(l - 1, K, h), d1);
+                for (int c = 0; c < K; ++c) tc::ld4(stash_ptr(l - 1, c, h, 0), st[c]);
+                if (actp == PINN_SIN) tc::ld4(stash_ptr(l - 1, K, h, 0), d1);
               }
               load_beta(beta, h);
               tc::act_bwd<V, false>(actp, st[0], d1, d2, d3);
@@ -877,7 +908,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
             par_w ^= 1;
             umma::fence_after_sync();
             lap(5);
-            flush_dw(1);
+            flush_dw(1, 1, 0, 0);
             lap(6);
           }
           // ---- bias gradient of layer l: fixed-order fold over the Q point blocks
@@ -891,21 +922,159 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           epi_sync();
         }
       }
+      // ---------------- backward, two M blocks (padded width 256).  Each thread owns units u and u + 128.  TMEM holds the
+      // accumulators of both blocks (4*NROW columns) and ONE weight-gradient block, so per layer: B1 (both units) ->
+      // dgrad; then per block j of INPUT units: B2 (Y block j -> R2) -> wgrad(output block 0, j) -> flush ->
+      // wgrad(output block 1, j) -> flush.
+      if (TRAIN && C::MB == 2) {
+#pragma unroll 1
+        for (int l = Lh - 1; l >= 0; --l) {
+          const int act = (l == 0) ? net.act_first : net.act_hidden;
+          if (l < Lh - 1) {
+            tc::wait_bar(bar_fd, par_fd);  // dgrad(l+1)
+            par_fd ^= 1;
+            umma::fence_after_sync();
+            lap(7);
+          }
+          // ---- B1(l)
+#pragma unroll
+          for (int mb = 0; mb < C::MB; ++mb) {
+            const int uu = u + 128 * mb;
+            const float wlv = __ldg(L.wpack + net.off_wl + uu);
+            float gb = 0.f;
+#pragma unroll 1
+            for (int h = 0; h < NH; ++h) {
+              float st[K][V], yb[K][V], d1[V], d2[V], d3[V], beta[3][V];
+              if (l == 0) {
+                layer0_stash(st, d1, h, uu);
+              } else {
+#pragma unroll
+                for (int c = 0; c < K; ++c) tc::ld4(stash_ptr(l, c, h, mb), st[c]);
+                if (act == PINN_SIN) tc::ld4(stash_ptr(l, K, h, mb), d1);
+              }
+              load_beta(beta, h);
+              if (l < Lh - 1) { if (C::DGRAD_TWO_LEVEL) load_acc(yb, h, mb); else load_acc1(yb, h, mb); }
+              tc::act_bwd<V, true>(act, st[0], d1, d2, d3);
+              if (l == Lh - 1) {
+#pragma unroll
+                for (int c = 0; c < K; ++c) {
+                  float ub[V];
+                  tc::ld4(s_ubar + c * NP + 8 * n8 + V * h, ub);
+#pragma unroll
+                  for (int i = 0; i < V; ++i) {
+                    float o;
+                    if (c == 0) o = st[0][i];
+                    else if (c <= C::N1) o = d1[i] * st[c][i];
+                    else if (c <= C::N1 + C::N2) {
+                      const float Ai = st[c - C::N1][i];
+                      o = fmaf(d2[i] * Ai, Ai, d1[i] * st[c][i]);
+                    } else if (C::MIX == 1) o = fmaf(d2[i] * st[1][i], st[2][i], d1[i] * st[c][i]);
+                    else {
+                      float S = 0.f;
+#pragma unroll
+                      for (int k = 0; k < C::N1; ++k) S = fmaf(beta[k][i] * st[1 + k][i], st[1 + k][i], S);
+                      o = fmaf(d2[i], S, d1[i] * st[c][i]);
+                    }
+                    wlacc[mb] = fmaf(ub[i], o, wlacc[mb]);
+                    yb[c][i] = ub[i] * wlv;
+                  }
+                }
+              }
+              tc::jets_adjoint<C, V>(yb, st, d1, d2, d3, beta);
+#pragma unroll
+              for (int i = 0; i < V; ++i) gb += yb[0][i];
+              if (l > 0) {
+#pragma unroll
+                for (int c = 0; c < K; ++c) tc::store_split4<3>(R1 + tc::chunk_off<SWB>(uu, c * PB + n8, WP), C::PLANE1, h, yb[c]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < V; ++i)
+#pragma unroll
+                  for (int c = 0; c < K; ++c) {
+                    const float4 hh = *reinterpret_cast<const float4*>(s_hj + ((8 * n8 + V * h + i) * K + c) * 4);
+                    const float t = net.scl * yb[c][i];
+                    w0acc[mb][0] = fmaf(hh.x, t, w0acc[mb][0]);
+                    w0acc[mb][1] = fmaf(hh.y, t, w0acc[mb][1]);
+                    w0acc[mb][2] = fmaf(hh.z, t, w0acc[mb][2]);
+                  }
+              }
+            }
+            s_bg[q * WP + uu] = gb;
+          }
+          if (l > 0) operands_ready(TC_BAR_OP1);
+          lap(3);
+          if (l > 0) {
+            const int actp = (l - 1 == 0) ? net.act_first : net.act_hidden;
+#pragma unroll 1
+            for (int j = 0; j < C::MB; ++j) {
+              // ---- B2(l), input-unit block j: Y^(l-1) of unit u + 128 j -> line u of R2
+#pragma unroll 1
+              for (int h = 0; h < NH; ++h) {
+                float st[K][V], d1[V], d2[V], d3[V], beta[3][V];
+                if (l == 1) {
+                  layer0_stash(st, d1, h, u + 128 * j);
+                } else {
+#pragma unroll
+                  for (int c = 0; c < K; ++c) tc::ld4(stash_ptr(l - 1, c, h, j), st[c]);
+                  if (actp == PINN_SIN) tc::ld4(stash_ptr(l - 1, K, h, j), d1);
+                }
+                load_beta(beta, h);
+                tc::act_bwd<V, false>(actp, st[0], d1, d2, d3);
+                {
+                  float y[V];
+#pragma unroll
+                  for (int i = 0; i < V; ++i) y[i] = st[0][i];
+                  tc::jets_outputs<C, V>(st, y, d1, d2, beta);
+                }
+#pragma unroll
+                for (int c = 0; c < K; ++c) tc::store_split4<C::YP>(R2 + tc::chunk_off<SWB>(u, c * PB + n8, 128), C::PLANE2, h, st[c]);
+              }
+              operands_ready(TC_BAR_OP2);
+              lap(4);
+#pragma unroll 1
+              for (int i = 0; i < C::MB; ++i) {
+                tc::wait_bar(bar_w, par_w);  // wgrad(output block i, input block j)
+                par_w ^= 1;
+                umma::fence_after_sync();
+                lap(5);
+                flush_dw(l, 0, i, j);
+                if (i == 0) tc::named_arrive(TC_BAR_OP3, C::NEPI_T + 32);  // block drained: the next one may be issued
+                lap(6);
+              }
+            }
+          }
+          // ---- bias gradients of layer l: fixed-order fold over the Q point blocks
+          epi_sync();
+          if (q == 0) {
+#pragma unroll
+            for (int mb = 0; mb < C::MB; ++mb) {
+              float g = 0.f;
+#pragma unroll
+              for (int qq = 0; qq < Q; ++qq) g += s_bg[qq * WP + u + 128 * mb];
+              gacc[net.off_b[l] + u + 128 * mb] += g;
+            }
+          }
+          epi_sync();
+        }
+      }
     }
 
     // ---------------- per-CTA epilogue: fold the register accumulators in fixed order
     if (TRAIN) {
-      const float vals[4] = {wlacc, w0acc[0], w0acc[1], w0acc[2]};
-#pragma unroll 1
+#pragma unroll
       for (int r = 0; r < 4; ++r) {
-        s_bg[q * WP + u] = vals[r];
+#pragma unroll
+        for (int mb = 0; mb < C::MB; ++mb) s_bg[q * WP + u + 128 * mb] = (r == 0) ? wlacc[mb] : w0acc[mb][r - 1];
         epi_sync();
         if (q == 0) {
-          float g = 0.f;
 #pragma unroll
-          for (int qq = 0; qq < Q; ++qq) g += s_bg[qq * WP + u];
-          const int dst = (r == 0) ? net.off_wl + u : net.off_w0 + (r - 1) * WP + u;
-          gacc[dst] += g;
+          for (int mb = 0; mb < C::MB; ++mb) {
+            float g = 0.f;
+#pragma unroll
+            for (int qq = 0; qq < Q; ++qq) g += s_bg[qq * WP + u + 128 * mb];
+            const int dst = ((r == 0) ? net.off_wl : net.off_w0 + (r - 1) * WP) + u + 128 * mb;
+            gacc[dst] += g;
+          }
         }
         epi_sync();
       }

@@ -14,6 +14,8 @@ from oracle import reference_oracle as O  # noqa: E402
 CASES = {
     "C4s": dict(n_hidden=6, width=128, d_in=2, expr="u_xx + u_yy + 9*u - sin(3*x)*sin(2*y)", n_col=1000, n_bd=100, n_bc=4,
                 lb=[0.0, 0.0], ub=[1.0, 1.0], act_first=1, act_hidden=1, scl=2.0),
+    "C5s": dict(n_hidden=5, width=256, d_in=3, expr="u_t - 0.1*(u_xx + u_yy)", n_col=600, n_bd=100, n_bc=5, lb=[0.0, 0.0, 0.0],
+                ub=[1.0, 1.0, 1.0]),
     "W128tanh": dict(n_hidden=3, width=100, d_in=2, expr="u_xx + u_yy + 2*y*(1-y) + 2*x*(1-x)", n_col=777, n_bd=50, n_bc=4,
                      lb=[0.0, 0.0], ub=[1.0, 1.0]),
 }
@@ -50,11 +52,11 @@ def check(name):
           f"grad {rel_err(res['tc'][3], res['mma'][3]):.2e}", flush=True)
 
 
-def timing(n_col=1 << 20):
+def timing(n_col=1 << 20, name="C4"):
     from pinn_based_online_pde_calculator_b200 import PinnEngine
     from pinn_based_online_pde_calculator_b200.workloads import init_params, make_points, make_workload
 
-    wl = make_workload("C4", n_col=n_col)
+    wl = make_workload(name, n_col=n_col)
     x_col, x_bd, u_bd = make_points(wl)
     fl = wl.flops_per_point()
     for kern in ("mma", "tc"):
@@ -68,7 +70,7 @@ def timing(n_col=1 << 20):
         eng.adam_steps(5, 1e-3)
         ms = eng.last_ms() / 5
         col_ms, bc_ms = eng.time_kernels(3)
-        print(f"C4 {n_col} pts {kern}: {ms:.3f} ms/step  col kernel {col_ms:.3f} ms  bc {bc_ms:.3f} ms  -> "
+        print(f"{name} {n_col} pts {kern}: {ms:.3f} ms/step  col kernel {col_ms:.3f} ms  bc {bc_ms:.3f} ms  -> "
               f"{fl['col'] * n_col / (col_ms * 1e-3) / 1e12:.1f} algorithmic TFLOP/s", flush=True)
         if kern == "tc":
             print("   phases", eng.phase_profile())
@@ -80,5 +82,7 @@ if __name__ == "__main__":
     for w in what:
         if w == "timing":
             timing()
+        elif w == "timing5":
+            timing(1 << 19, "C5")
         else:
             check(w)

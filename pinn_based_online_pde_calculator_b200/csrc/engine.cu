@@ -166,6 +166,16 @@ struct pinn_engine {
 };
 
 static void apply_l2_policy(pinn_engine* h);
+// replicas of the tcgen05 family's weight-image stream (all CTAs walk the same sequence at the same time: replicas
+// spread the reads over more L2 slices); PINN_TC_COPIES overrides the default for experiments
+static int tc_image_copies() {
+  static const int n = [] {
+    const char* e = getenv("PINN_TC_COPIES");
+    const int v = e ? atoi(e) : PINN_TC_IMAGE_COPIES;
+    return v < 1 ? 1 : (v > 64 ? 64 : v);
+  }();
+  return n;
+}
 static void l2_release(pinn_engine* h);
 
 static int pad_width(int w) {
@@ -353,7 +363,7 @@ static int create_impl(pinn_engine* h, const pinn_spec_t* spec, int device) {
   CK(cudaMalloc(&h->d_meta, sizeof(LossMeta)));
   CK(cudaMemset(h->d_ring_pos, 0, sizeof(int)));
   CK(cudaMemset(h->d_adam_count, 0, sizeof(int)));
-  if (h->kcol->kind == 3) CK(cudaMalloc(&h->d_wimg, jet_tc_image_bytes(h->net) * PINN_TC_IMAGE_COPIES));
+  if (h->kcol->kind == 3) CK(cudaMalloc(&h->d_wimg, jet_tc_image_bytes(h->net) * tc_image_copies()));
   if (h->use_umma) {
     CK(cudaMalloc(&h->d_uimg, sizeof(float) * jet_umma_image_floats(h->net)));
     CK(cudaMalloc(&h->d_uclk, sizeof(long long) * 8));
@@ -572,7 +582,7 @@ static void fill_launch(pinn_engine* h, PinnLaunch& L, const JetKernelInfo* k, c
   L.prog = prog;
   L.wimg = h->d_wimg;
   L.wimg_copy_bytes = (long long)jet_tc_image_bytes(h->net);
-  L.wimg_copies = PINN_TC_IMAGE_COPIES;
+  L.wimg_copies = tc_image_copies();
   L.ldw = h->kcol->ldw;
   (void)k;
 }
@@ -583,7 +593,7 @@ static int enqueue_pack(pinn_engine* h, const float* params_dev, cudaStream_t st
   const int P = h->fmap.n_params;
   k_pack<<<(P + 255) / 256, 256, 0, st>>>(h->fmap, params_dev ? params_dev : h->d_params, h->d_wpack);
   CK(cudaGetLastError());
-  if (h->kcol->kind == 3) CK(jet_tc_build_images(h->d_wpack, h->net, h->kcol->ldw, h->d_wimg, PINN_TC_IMAGE_COPIES, st));
+  if (h->kcol->kind == 3) CK(jet_tc_build_images(h->d_wpack, h->net, h->kcol->ldw, h->d_wimg, tc_image_copies(), st));
   return 0;
 }
 

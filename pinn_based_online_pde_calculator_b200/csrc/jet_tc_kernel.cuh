@@ -48,9 +48,30 @@ struct TcCfg {
   static constexpr int NROW = NP * K;                        // N of the forward / data-gradient MMAs
   static constexpr int SWB = (NROW % 64 == 0) ? 128 : 32;    // swizzle span (bytes per line) of the activation tiles
   static constexpr int NBLK = (NROW * 2 + SWB - 1) / SWB;    // n-blocks per plane
+  // HALVES (C4-type tiles: one M block, 32 points x 4 channels): the tile is two 16-point halves (pass h of every
+  // epilogue thread) with their own operand regions, accumulator columns and forward MMAs, so that the epilogue of one
+  // half runs under the forward GEMM of the other.  Column order n = h*64 + n8*16 + c*4 + i (a thread's 16 values of a
+  // pass are 16 consecutive TMEM columns: one tcgen05.ld.x16 per accumulator block).
+  // MEASURED on C4 (1M points, same box): 21.3 ms with HALVES against 19.1 ms without.  The forward wait for the tensor
+  // core drops from 7.4 M to 3.9 M cycles per CTA, but the weight image of a layer is streamed twice, the epilogue passes
+  // get 30 % slower while they share shared memory and TMEM with running MMAs (act_fwd 8.8 M -> 11.4 M cycles), and the
+  // three-block accumulator reads cost registers (spills 132 -> 320 B) that the backward pass pays for.  Off by default.
+#ifndef TC_HALVES
+#define TC_HALVES 0
+#endif
+  static constexpr bool HALVES = (TC_HALVES != 0) && (WP == 128) && (NP == 32) && (K == 4);
+  static constexpr int HN = NROW / 2;                        // columns per half
+  static constexpr int HP = WP * SWB;                        // HALVES: one (half, plane) block = WP lines x 128 B; R1 order [h][plane]
+  static constexpr int FWD_COLS = HALVES ? 6 * HN : (WP / 128) * 2 * NROW;   // forward accumulators (HALVES: A | B | C per half)
   static constexpr int PLANE1 = NBLK * WP * SWB;             // region 1: all WP lines
   static constexpr int PLANE2 = NBLK * 128 * SWB;            // region 2: one block of 128 lines
-  static constexpr int YP = 2;                               // planes of the recomputed layer input (weight gradient only)
+#ifndef TC_YP
+#define TC_YP 2      // (1: timing experiment only -- wrong weight gradient)
+#endif
+#ifndef TC_NSLOT
+#define TC_NSLOT 4
+#endif
+  static constexpr int YP = TC_YP;                           // planes of the recomputed layer input (weight gradient only)
   // [y0 | y1] as ONE N = 2*NROW operand (four MMAs per k-step instead of six).  Measured on C4: no gain (the tensor
   // pipe is not the limiter) and three truncating adds per k-step in the leading accumulator instead of one
   // (u 2.3e-7 -> 7.9e-7, gradient 6.9e-7 -> 1.2e-6), so it stays off.
@@ -75,7 +96,7 @@ struct TcCfg {
   static constexpr int KSW = NROW / 16;                      // k-steps of the weight-gradient GEMM
   static constexpr int PLANE_W = 4096;                       // one weight plane of a k-step: 128 rows x 32 B
   static constexpr int SLOT = 3 * PLANE_W;                   // ring stage = one k-step, planes b2 | b1 | b0
-  static constexpr int NSLOT = 4;
+  static constexpr int NSLOT = TC_NSLOT;
   static constexpr int CHUNKS = MB * KS;                     // ring stages per forward / data-gradient GEMM
   static constexpr int PARTLD = NROW + 4;                    // row stride of the output-layer partial products
   // TMEM columns: per M block (big | small) accumulators, then two weight-gradient blocks (ping-pong)
@@ -87,7 +108,7 @@ struct TcCfg {
                                      Q * WP /*gradient partials*/ + PINN_MAX_OPS + PINN_MAX_CONSTS;
   static constexpr size_t smem_bytes() { return (size_t)R1_BYTES + R2_BYTES + NSLOT * SLOT + MISC_FLOATS * 4 + 256; }
   static constexpr size_t STL = (size_t)(K + 1) * WP * NP;   // stash floats per layer and CTA (K jets + cos for the sin activation)
-  static constexpr bool OK = (NROW % 16 == 0) && (NROW <= 256) && (TC_USED <= 512) && (smem_bytes() <= 232448 - 1024) &&
+  static constexpr bool OK = (NROW % 16 == 0) && (NROW <= 256) && (TC_USED <= 512) && (FWD_COLS <= 512) && (smem_bytes() <= 232448 - 1024) &&
                              ((size_t)WP * PARTLD * 4 <= (size_t)R1_BYTES) && (MB <= 2);
 };
 
@@ -132,6 +153,16 @@ __device__ __forceinline__ void store_split4(uint8_t* chunk, int plane_bytes, in
   split_pair<NPL>(v[0], v[1], a);
   split_pair<NPL>(v[2], v[3], b);
   uint8_t* d = chunk + 8 * h;
+#pragma unroll
+  for (int p = 0; p < NPL; ++p) *reinterpret_cast<uint2*>(d + p * plane_bytes) = make_uint2(a[p], b[p]);
+}
+
+// split 4 values and store them into NPL planes at the 8-byte slot `d` of plane 0
+template <int NPL>
+__device__ __forceinline__ void store_split4p(uint8_t* d, int plane_bytes, const float (&v)[4]) {
+  uint32_t a[3], b[3];
+  split_pair<NPL>(v[0], v[1], a);
+  split_pair<NPL>(v[2], v[3], b);
 #pragma unroll
   for (int p = 0; p < NPL; ++p) *reinterpret_cast<uint2*>(d + p * plane_bytes) = make_uint2(a[p], b[p]);
 }
@@ -299,7 +330,7 @@ __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("ba
 
 }  // namespace tc
 
-enum { TC_BAR_EPI = 1, TC_BAR_OP1 = 2, TC_BAR_OP2 = 3, TC_BAR_OP3 = 4 };
+enum { TC_BAR_EPI = 1, TC_BAR_OP1 = 2, TC_BAR_OP2 = 3, TC_BAR_OP3 = 4, TC_BAR_OP1B = 5 };
 
 // ---------------------------------------------------------------- the kernel
 template <class C, bool TRAIN, bool PROF = false>
@@ -324,8 +355,8 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
   uint64_t* const bars = reinterpret_cast<uint64_t*>(s_consts + PINN_MAX_CONSTS);
   uint64_t* const bar_full = bars;
   uint64_t* const bar_empty = bars + NSLOT;
-  uint64_t* const bar_fd = bars + 2 * NSLOT;
-  uint64_t* const bar_w = bar_fd + 1;
+  uint64_t* const bar_fd = bars + 2 * NSLOT;                   // [2]: forward GEMM of half h (HALVES); [0] otherwise and for dgrad
+  uint64_t* const bar_w = bar_fd + 2;
   __shared__ uint32_t s_tmem;
   float* const part = reinterpret_cast<float*>(R1);            // [WP][PARTLD] output-layer partial products
 
@@ -339,7 +370,8 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
   if (warp == C::NEPI) umma::tmem_alloc(&s_tmem, 512);
   if (tid == 0) {
     for (int i = 0; i < NSLOT; ++i) { umma::mbar_init(&bar_full[i], 1); umma::mbar_init(&bar_empty[i], 1); }
-    umma::mbar_init(bar_fd, 1);
+    umma::mbar_init(&bar_fd[0], 1);
+    umma::mbar_init(&bar_fd[1], 1);
     umma::mbar_init(bar_w, 1);
     umma::fence_mbar_init();
   }
@@ -354,12 +386,17 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     // image stream (every CTA walks the same sequence at about the same time).
     if (lane == 0) {
       const uint8_t* img = reinterpret_cast<const uint8_t*>(L.wimg) + (size_t)(blockIdx.x % L.wimg_copies) * L.wimg_copy_bytes;
-      const int per_tile = (TRAIN ? 2 : 1) * NG * C::CHUNKS;
+      // HALVES: every forward GEMM is issued once per half, so its image is streamed twice in a row
+      constexpr int REP = C::HALVES ? 2 : 1;
+      const int fwd_len = REP * NG * C::CHUNKS;
+      const int per_tile = fwd_len + (TRAIN ? NG * C::CHUNKS : 0);
       const long long total = (long long)my_tiles * per_tile;
-      int c = 0;
+      int pos = 0;   // position inside the tile's stream
       for (long long i = 0; i < total; ++i) {
         const int s = (int)(i % NSLOT);
         const uint32_t round = (uint32_t)(i / NSLOT);
+        // image chunk of this position
+        const int c = (pos < fwd_len) ? (pos / (REP * C::CHUNKS)) * C::CHUNKS + pos % C::CHUNKS : NG * C::CHUNKS + (pos - fwd_len);
         if (round > 0) tc::wait_bar(&bar_empty[s], (round - 1) & 1);
         mbar_expect_tx(&bar_full[s], C::SLOT);
         bulk_g2s(ring + s * C::SLOT, img + (size_t)c * C::SLOT, C::SLOT, &bar_full[s]);
@@ -372,7 +409,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           for (int blk = 0; blk < C::MB; ++blk)
             tc::prefetch_l2(L.gacc + (size_t)blockIdx.x * net.pg + net.off_w[l] + (size_t)blk * 128 * L.ldw, (uint32_t)(128 * L.ldw * 4));
         }
-        if (++c == per_tile) c = 0;
+        if (++pos == per_tile) pos = 0;
       }
     }
   } else if (warp == C::NEPI) {
@@ -391,8 +428,11 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
       for (int mb = 0; mb < C::MB; ++mb) {
         const uint32_t DB = tb + C::TC_D(mb), DS = two_level ? DB + NROW : DB;
         for (int ks = 0; ks < C::KS; ++ks) {
-          const uint64_t b01 = umma::smem_desc(r1a + ks * 16 * SWB, WP * SWB, 8 * SWB, LT);
-          const uint64_t b2 = umma::smem_desc(r1a + 2 * C::PLANE1 + ks * 16 * SWB, WP * SWB, 8 * SWB, LT);
+          // HALVES (data-gradient GEMM over the whole tile): plane p of half h sits at (3h + p) * HP, so the two n-blocks
+          // of a plane are 3 * HP apart
+          constexpr uint32_t PST = C::HALVES ? C::HP : C::PLANE1, LBO = C::HALVES ? 3 * C::HP : WP * SWB;
+          const uint64_t b01 = umma::smem_desc(r1a + ks * 16 * SWB, LBO, 8 * SWB, LT);
+          const uint64_t b2 = umma::smem_desc(r1a + 2 * PST + ks * 16 * SWB, LBO, 8 * SWB, LT);
           const uint32_t acc = ks > 0 ? 1u : 0u;
           const int s = (int)(ci % NSLOT);
           tc::wait_bar(&bar_full[s], (uint32_t)((ci / NSLOT) & 1));
@@ -406,7 +446,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
             umma::mma_bf16_ss(DB, w0, b01, id_wx2, 1u);
             umma::mma_bf16_ss(DS, w0, b2, id_wx, 1u);
           } else {
-            const uint64_t b1 = umma::smem_desc(r1a + C::PLANE1 + ks * 16 * SWB, WP * SWB, 8 * SWB, LT);
+            const uint64_t b1 = umma::smem_desc(r1a + PST + ks * 16 * SWB, LBO, 8 * SWB, LT);
             umma::mma_bf16_ss(DS, w2, b01, id_wx, acc);
             umma::mma_bf16_ss(DS, w1, b1, id_wx, 1u);
             umma::mma_bf16_ss(DS, w1, b01, id_wx, 1u);
@@ -420,6 +460,36 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
       }
       umma::commit(bar_fd);
     };
+    // HALVES forward GEMM of half h: FOUR MMAs per k-step into three accumulator blocks of HN columns,
+    //   C    = w2*y0            (N = HN;   initialises C at k-step 0)
+    //   A, B = w0*[y0 | y1]     (N = 2 HN: the planes b0, b1 of a half are adjacent n-blocks)
+    //   B, C += w1*[y0 | y1]
+    //   C   += w0*y2
+    // A holds only the leading products, B + C the five small ones: the same two-level accumulation as the
+    // six-MMA form (the epilogue adds A + (B + C) with round-to-nearest adds), at two thirds of the MMA count.
+    const uint32_t id_h = umma::idesc_bf16(128, C::HN, 0, 1), id_2h = umma::idesc_bf16(128, 2 * C::HN, 0, 1);
+    auto gemm_fwd_half = [&](int h) {
+      const uint32_t DA = tb + h * 3 * C::HN;
+      for (int ks = 0; ks < C::KS; ++ks) {
+        const uint32_t lo = r1a + h * 3 * C::HP + ks * 16 * SWB;
+        const uint64_t b01 = umma::smem_desc(lo, C::HP, 8 * SWB, LT);
+        const uint64_t b2 = umma::smem_desc(lo + 2 * C::HP, C::HP, 8 * SWB, LT);
+        const uint32_t acc = ks > 0 ? 1u : 0u;
+        const int s = (int)(ci % NSLOT);
+        tc::wait_bar(&bar_full[s], (uint32_t)((ci / NSLOT) & 1));
+        umma::fence_after_sync();
+        const uint64_t w2 = umma::smem_desc(rga + s * C::SLOT, 16, 256, 6);
+        const uint64_t w1 = umma::smem_desc(rga + s * C::SLOT + C::PLANE_W, 16, 256, 6);
+        const uint64_t w0 = umma::smem_desc(rga + s * C::SLOT + 2 * C::PLANE_W, 16, 256, 6);
+        umma::mma_bf16_ss(DA + 2 * C::HN, w2, b01, id_h, acc);
+        umma::mma_bf16_ss(DA, w0, b01, id_2h, acc);
+        umma::mma_bf16_ss(DA + C::HN, w1, b01, id_2h, 1u);
+        umma::mma_bf16_ss(DA + 2 * C::HN, w0, b2, id_h, 1u);
+        umma::commit(&bar_empty[s]);
+        ++ci;
+      }
+      umma::commit(&bar_fd[h]);
+    };
     // DW[out][in] = sum_n G[out][n] * Y[in][n]: G in R1 (M rows = output units: the flush then writes the gradient
     // with coalesced accesses), Y block in R2 (two planes), both K-major views; five products (everything down
     // to 2^-16 of the leading term; the sum over the points averages the remaining rounding noise)
@@ -428,9 +498,11 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
       for (int ks = 0; ks < C::KSW; ++ks) {
         uint64_t ag[3], by[2];
 #pragma unroll
-        for (int p = 0; p < 3; ++p) ag[p] = umma::smem_desc(r1a + p * C::PLANE1 + iblk * 128 * SWB + tc::kmajor_koff<SWB>(ks, WP), 16, 8 * SWB, LT);
+        for (int p = 0; p < 3; ++p)
+          ag[p] = C::HALVES ? umma::smem_desc(r1a + ((ks >> 2) * 3 + p) * C::HP + (ks & 3) * 32, 16, 8 * SWB, LT)
+                            : umma::smem_desc(r1a + p * C::PLANE1 + iblk * 128 * SWB + tc::kmajor_koff<SWB>(ks, WP), 16, 8 * SWB, LT);
 #pragma unroll
-        for (int p = 0; p < 2; ++p) by[p] = umma::smem_desc(r2a + p * C::PLANE2 + tc::kmajor_koff<SWB>(ks, 128), 16, 8 * SWB, LT);
+        for (int p = 0; p < 2; ++p) by[p] = umma::smem_desc(r2a + (p % C::YP) * C::PLANE2 + tc::kmajor_koff<SWB>(ks, 128), 16, 8 * SWB, LT);
         umma::mma_bf16_ss(DW, ag[2], by[0], id_wg, ks > 0 ? 1u : 0u);
         umma::mma_bf16_ss(DW, ag[1], by[1], id_wg, 1u);
         umma::mma_bf16_ss(DW, ag[1], by[0], id_wg, 1u);
@@ -445,12 +517,22 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     uint32_t mp_fd = 0, mp_w = 0;
     for (int it = 0; it < my_tiles; ++it) {
       for (int l = 1; l < Lh; ++l) {
-        tc::named_sync(TC_BAR_OP1, C::NEPI_T + 32);
-        umma::fence_after_sync();
-        const long long t0 = PROF ? clock64() : 0;
-        if (lane == 0) gemm_wx(true, C::CONCAT);   // forward: two-level accumulation (loss / residual precision)
-        if (PROF && C::MB == 1 && lane == 0) { tc::wait_bar(bar_fd, mp_fd); mp_fd ^= 1; gclk[0] += clock64() - t0; }
-        __syncwarp();
+        if (C::HALVES) {
+          for (int h = 0; h < 2; ++h) {
+            tc::named_sync(h ? TC_BAR_OP1B : TC_BAR_OP1, C::NEPI_T + 32);
+            umma::fence_after_sync();
+            if (lane == 0) gemm_fwd_half(h);
+            __syncwarp();
+          }
+          if (PROF) mp_fd ^= 1;   // bar_fd[0] completed one more phase
+        } else {
+          tc::named_sync(TC_BAR_OP1, C::NEPI_T + 32);
+          umma::fence_after_sync();
+          const long long t0 = PROF ? clock64() : 0;
+          if (lane == 0) gemm_wx(true, C::CONCAT);   // forward: two-level accumulation (loss / residual precision)
+          if (PROF && C::MB == 1 && lane == 0) { tc::wait_bar(bar_fd, mp_fd); mp_fd ^= 1; gclk[0] += clock64() - t0; }
+          __syncwarp();
+        }
       }
       if (TRAIN) {
         for (int l = Lh - 1; l >= 1; --l) {
@@ -493,8 +575,19 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     const int u = 32 * quad + lane;                        // this thread's unit (= TMEM lane)
     const uint32_t tl = tb + ((uint32_t)(32 * quad) << 16);
     const int n8 = q;                                      // 8-point block of this warp
-    uint32_t par_fd = 0, par_w = 0;
+    uint32_t par_fd = 0, par_fd1 = 0, par_w = 0;   // par_fd: bar_fd[0], par_fd1: bar_fd[1] (HALVES forward)
     auto epi_sync = [&]() { tc::named_sync(TC_BAR_EPI, C::NEPI_T); };
+    // 8-byte slots of this thread's four points of pass h (channel c) in plane 0 of the operand tiles; the plane stride
+    // of R1 is R1_PST.  HALVES: column n = h*HN + n8*16 + c*4 + i  ->  16-byte chunk n8*2 + c/2 of half h, slot c & 1.
+    constexpr int R1_PST = C::HALVES ? C::HP : C::PLANE1;
+    auto r1_slot = [&](int line, int c, int h) -> uint8_t* {
+      if (C::HALVES) return R1 + h * 3 * C::HP + tc::chunk_off<SWB>(line, n8 * 2 + (c >> 1), WP) + 8 * (c & 1);
+      return R1 + tc::chunk_off<SWB>(line, c * PB + n8, WP) + 8 * h;
+    };
+    auto r2_slot = [&](int line, int c, int h) -> uint8_t* {
+      if (C::HALVES) return R2 + tc::chunk_off<SWB>(line, h * 8 + n8 * 2 + (c >> 1), 128) + 8 * (c & 1);
+      return R2 + tc::chunk_off<SWB>(line, c * PB + n8, 128) + 8 * h;
+    };
     // Hand an operand tile to the MMA warp: writer-side generic -> async proxy fence (the conventional place), then a
     // non-blocking arrive.  fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: it also waits for this
     // thread's outstanding GLOBAL stores, which is why the stash stores of the last half are issued after it.
@@ -530,21 +623,46 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     };
     // accumulators of the last forward / data-gradient GEMM (big + small), points 4h..4h+3 of the block
     auto load_acc = [&](float (&a)[K][V], int h, int mb) {
-      float sm[K][V];
+      if constexpr (C::HALVES) {   // the thread's 16 values of the pass are 16 consecutive columns
+        float big[16], sm[16];
+        umma::tmem_ld16(tl + C::TC_D(0) + h * C::HN + n8 * 16, big);
+        umma::tmem_ld16(tl + C::TC_D(0) + NROW + h * C::HN + n8 * 16, sm);
+        umma::tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < K; ++c) {
-        umma::tmem_ld4(tl + C::TC_D(mb) + c * NP + 8 * n8 + V * h, a[c]);
-        umma::tmem_ld4(tl + C::TC_D(mb) + NROW + c * NP + 8 * n8 + V * h, sm[c]);
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+          for (int i = 0; i < V; ++i) a[c][i] = big[c * V + i] + sm[c * V + i];
+      } else {
+        float sm[K][V];
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          umma::tmem_ld4(tl + C::TC_D(mb) + c * NP + 8 * n8 + V * h, a[c]);
+          umma::tmem_ld4(tl + C::TC_D(mb) + NROW + c * NP + 8 * n8 + V * h, sm[c]);
+        }
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+          for (int i = 0; i < V; ++i) a[c][i] += sm[c][i];
       }
+    };
+    // HALVES forward accumulators of half h: blocks A | B | C of HN columns; result A + (B + C)
+    auto load_acc_fwd = [&](float (&a)[K][V], int h) {
+      float A[16], B[16], Cc[16];
+      const uint32_t base = tl + h * 3 * C::HN + n8 * 16;
+      umma::tmem_ld16(base + C::HN, B);
+      umma::tmem_ld16(base + 2 * C::HN, Cc);
+      umma::tmem_ld16(base, A);
       umma::tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < K; ++c)
 #pragma unroll
-        for (int i = 0; i < V; ++i) a[c][i] += sm[c][i];
+        for (int i = 0; i < V; ++i) a[c][i] = A[c * V + i] + (B[c * V + i] + Cc[c * V + i]);
     };
     // data-gradient GEMM with ONE accumulator: half the TMEM read traffic of B1 (TMEM reads run at ~64 B/cycle/SM:
     // measured 1.1 k cycles per half-pass for the two-block read)
     auto load_acc1 = [&](float (&a)[K][V], int h, int mb) {
+      static_assert(!C::HALVES || C::DGRAD_TWO_LEVEL, "HALVES uses the two-level data-gradient accumulators");
 #pragma unroll
       for (int c = 0; c < K; ++c) umma::tmem_ld4(tl + C::TC_D(mb) + c * NP + 8 * n8 + V * h, a[c]);
       umma::tmem_ld_wait();
@@ -641,9 +759,11 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
       for (int l = 0; l < Lh; ++l) {
         const int act = (l == 0) ? net.act_first : net.act_hidden;
         const bool last = (l == Lh - 1);
-        if (l > 0) {
-          tc::wait_bar(bar_fd, par_fd);
+        if (l > 0 && (!C::HALVES || last)) {
+          // (HALVES, last layer: the output-layer partial products alias R1, so both halves of the GEMM must be done)
+          tc::wait_bar(&bar_fd[0], par_fd);
           par_fd ^= 1;
+          if (C::HALVES) { tc::wait_bar(&bar_fd[1], par_fd1); par_fd1 ^= 1; }
           umma::fence_after_sync();
           lap(0);
         }
@@ -668,6 +788,14 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
                 const float4 hh = *reinterpret_cast<const float4*>(s_hj + ((8 * n8 + V * h + i) * K + c) * 4);
                 a[c][i] = net.scl * fmaf(hh.x, w00, fmaf(hh.y, w01, hh.z * w02));
               }
+          } else if (C::HALVES) {
+            if (!last) {   // forward GEMM of this half (the other half's may still be running)
+              if (h == 0) { tc::wait_bar(&bar_fd[0], par_fd); par_fd ^= 1; }
+              else { tc::wait_bar(&bar_fd[1], par_fd1); par_fd1 ^= 1; }
+              umma::fence_after_sync();
+              lap(0);
+            }
+            load_acc_fwd(a, h);
           } else {
             load_acc(a, h, mb);
           }
@@ -692,7 +820,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           }
           if (!last) {
 #pragma unroll
-            for (int c = 0; c < K; ++c) tc::store_split4<3>(R1 + tc::chunk_off<SWB>(uu, c * PB + n8, WP), C::PLANE1, h, a[c]);
+            for (int c = 0; c < K; ++c) tc::store_split4p<3>(r1_slot(uu, c, h), R1_PST, a[c]);
           } else {
 #pragma unroll
             for (int c = 0; c < K; ++c) {
@@ -702,8 +830,12 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
               tc::st4(part + (size_t)uu * C::PARTLD + c * NP + 8 * n8 + V * h, pv);
             }
           }
-          if (TRAIN) {
+          if (C::HALVES) {
+            if (!last) { operands_ready(h ? TC_BAR_OP1B : TC_BAR_OP1); lap(1); }   // this half may go to the tensor core
+          } else if (TRAIN) {
             if (mb == C::MB - 1 && h == NH - 1 && !last) operands_ready(TC_BAR_OP1);
+          }
+          if (TRAIN) {
             if (!(TC_EXP & 4) && l > 0) {
 #pragma unroll
               for (int c = 0; c < K; ++c) tc::st4(stash_ptr(l, c, h, mb), sv[c]);
@@ -712,7 +844,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           }
         }
         }  // mb
-        if (!TRAIN && !last) operands_ready(TC_BAR_OP1);
+        if (!TRAIN && !last && !C::HALVES) operands_ready(TC_BAR_OP1);
         lap(1);
       }
 
@@ -851,7 +983,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
                 lap(5);
               }
 #pragma unroll
-              for (int c = 0; c < K; ++c) tc::store_split4<3>(R1 + tc::chunk_off<SWB>(u, c * PB + n8, WP), C::PLANE1, h, yb[c]);
+              for (int c = 0; c < K; ++c) tc::store_split4p<3>(r1_slot(u, c, h), R1_PST, yb[c]);
             } else {
 #pragma unroll
               for (int i = 0; i < V; ++i)
@@ -899,7 +1031,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
                 tc::jets_outputs<C, V>(st, y, d1, d2, beta);
               }
 #pragma unroll
-              for (int c = 0; c < K; ++c) tc::store_split4<C::YP>(R2 + tc::chunk_off<SWB>(u, c * PB + n8, 128), C::PLANE2, h, st[c]);
+              for (int c = 0; c < K; ++c) tc::store_split4p<C::YP>(r2_slot(u, c, h), C::PLANE2, st[c]);
             }
             operands_ready(TC_BAR_OP2);
             lap(4);

@@ -41,8 +41,10 @@ def test_engine_matches_golden_fixture(path, kernel, monkeypatch):
     assert rel_err(g.cpu().numpy(), z["grad"]) < TOL
     u, f, _ = eng.eval(z["x_col"])
     assert rel_err(u, z["u"]) < TOL
-    # the 5x256 residual is a difference of large terms: measured 1.1e-5 in fp32
-    assert rel_err(f, z["f"]) < (2e-5 if kw["width"] == 256 else TOL)
+    # The 5x256 residual is a difference of large terms.  The production kernel (`auto`: tcgen05 family D) holds the
+    # 1e-5 bar (measured 5e-6); only the plain-fp32 SIMT kernel, forced here on a width it is never selected for
+    # (sequential fp32 accumulation over 256 inputs, no blocked partial sums), measures 1.1e-5.
+    assert rel_err(f, z["f"]) < (2e-5 if (kw["width"] == 256 and kernel == "simt") else TOL)
     eng.close()
 
 

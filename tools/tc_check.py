@@ -59,7 +59,7 @@ def timing(n_col=1 << 20, name="C4"):
     wl = make_workload(name, n_col=n_col)
     x_col, x_bd, u_bd = make_points(wl)
     fl = wl.flops_per_point()
-    for kern in ("mma", "tc"):
+    for kern in os.environ.get("TC_CHECK_KERNELS", "mma,tc").split(","):
         os.environ["PINN_B200_KERNEL"] = kern
         eng = PinnEngine(wl.net, wl.eq, n_bc=len(x_bd))
         eng.set_params(init_params(wl.net))

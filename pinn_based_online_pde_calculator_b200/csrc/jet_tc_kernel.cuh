@@ -32,6 +32,11 @@
 #include "jet_kernel.cuh"
 #include "umma_common.cuh"
 
+#ifndef TC_DISCARD
+#define TC_DISCARD 0   // 1: discard the stash lines of a layer from the L2 (discard.global.L2, SASS CCTL.E.RML2) once its backward
+                       // pass has consumed them, so that dead dirty lines are never written back.  Measured: C4 19.8 ms with,
+                       // 19.2 ms without; C5 49.6 / 49.7 ms -- the write-backs are not what the kernel waits for.  Off.
+#endif
 #ifndef TC_EXP
 #define TC_EXP 0   // timing experiments (wrong results): 1 no accumulator flush, 2 no B2 stash read, 4 no stash write, 8 no B1 stash read
 #endif
@@ -325,6 +330,9 @@ __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// drop a 128-byte line from the L2 WITHOUT writing it back (its contents become indeterminate): for scratch whose
+// last reader is done -- the next tile overwrites it before anybody reads it again
+__device__ __forceinline__ void discard_l2(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
@@ -999,6 +1007,11 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           }
           s_bg[q * WP + u] = gb;
           if (l > 0) operands_ready(TC_BAR_OP1);
+          if (TC_DISCARD && l > 0 && lane < 8) {
+            // the stash of layer l is dead (B2(l+1) and B1(l) were its readers): 8 lines per channel and warp
+            const int nch = K + (act == PINN_SIN ? 1 : 0);
+            for (int c = 0; c < nch; ++c) tc::discard_l2(stash + (size_t)l * C::STL + ((size_t)(c * Q + q) * 128 + 32 * quad) * 8 + lane * 32);
+          }
           lap(3);
           if (l > 0) {
             // ---- F(l+1): flush the previous layer's weight-gradient block (wgrad(l+1) completed: B1 waited for it)
@@ -1134,6 +1147,12 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
             s_bg[q * WP + uu] = gb;
           }
           if (l > 0) operands_ready(TC_BAR_OP1);
+          if (TC_DISCARD && l > 0 && lane < 8) {
+            const int nch = K + (act == PINN_SIN ? 1 : 0);
+            for (int mb = 0; mb < C::MB; ++mb)
+              for (int c = 0; c < nch; ++c)
+                tc::discard_l2(stash + (size_t)l * C::STL + ((size_t)((mb * (K + 1) + c) * Q + q) * 128 + 32 * quad) * 8 + lane * 32);
+          }
           lap(3);
           if (l > 0) {
             const int actp = (l - 1 == 0) ? net.act_first : net.act_hidden;

@@ -112,7 +112,20 @@ struct TcCfg {
   static constexpr int MISC_FLOATS = NP * 4 /*z*/ + 3 * NP /*beta*/ + NP * K * 4 /*hj*/ + NROW /*ubar*/ + 4 * NROW /*psum*/ +
                                      Q * WP /*gradient partials*/ + PINN_MAX_OPS + PINN_MAX_CONSTS;
   static constexpr size_t smem_bytes() { return (size_t)R1_BYTES + R2_BYTES + NSLOT * SLOT + MISC_FLOATS * 4 + 256; }
-  static constexpr size_t STL = (size_t)(K + 1) * WP * NP;   // stash floats per layer and CTA (K jets + cos for the sin activation)
+  // YSIDE (one M block): the forward pass also keeps the bf16 planes b0, b1 of every layer's OUTPUT tile -- a raw copy of
+  // the swizzled operand region, stored by the bulk-copy engine (cp.async.bulk shared -> global) while the next GEMM runs
+  // -- and the backward pass loads them straight back into the weight-gradient operand region R2, instead of
+  // recomputing them from the fp32 stash in the epilogue warps (B2: 15 % of the C4 step).
+  // MEASURED on C4 (1M points, same box): correct (bit-identical gradient), B2 4.2 M cycles per CTA cheaper, but the forward
+  // GEMM wait grows by 4.5 M (the 64 KB bulk store out of the operand tile takes longer than the GEMM that reads the same
+  // tile) and the flush by 2.7 M (it now shares the L2 path with the 64 KB reload): 21.8 ms vs 19.2 ms.  Off by default.
+#ifndef TC_YSIDE
+#define TC_YSIDE 0
+#endif
+  static constexpr bool YSIDE = (TC_YSIDE != 0) && (MB == 1) && !HALVES;
+  static constexpr size_t STL_F = (size_t)(K + 1) * WP * NP;           // fp32 stash floats per layer and CTA (K jets + cos for the sin activation)
+  static constexpr size_t YS_F = YSIDE ? (size_t)YP * PLANE2 / 4 : 0;  // side stash (floats) per layer and CTA
+  static constexpr size_t STL = STL_F + YS_F;                          // per-layer stride of the CTA's scratch
   static constexpr bool OK = (NROW % 16 == 0) && (NROW <= 256) && (TC_USED <= 512) && (FWD_COLS <= 512) && (smem_bytes() <= 232448 - 1024) &&
                              ((size_t)WP * PARTLD * 4 <= (size_t)R1_BYTES) && (MB <= 2);
 };
@@ -333,6 +346,13 @@ __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
 // drop a 128-byte line from the L2 WITHOUT writing it back (its contents become indeterminate): for scratch whose
 // last reader is done -- the next tile overwrites it before anybody reads it again
 __device__ __forceinline__ void discard_l2(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
+// bulk copy shared -> global (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(umma::smem_addr(src_smem)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources read
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }        // writes done
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
@@ -365,6 +385,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
   uint64_t* const bar_empty = bars + NSLOT;
   uint64_t* const bar_fd = bars + 2 * NSLOT;                   // [2]: forward GEMM of half h (HALVES); [0] otherwise and for dgrad
   uint64_t* const bar_w = bar_fd + 2;
+  uint64_t* const bar_y = bar_w + 1;                           // YSIDE: side-stash tile landed in R2
   __shared__ uint32_t s_tmem;
   float* const part = reinterpret_cast<float*>(R1);            // [WP][PARTLD] output-layer partial products
 
@@ -381,6 +402,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     umma::mbar_init(&bar_fd[0], 1);
     umma::mbar_init(&bar_fd[1], 1);
     umma::mbar_init(bar_w, 1);
+    umma::mbar_init(bar_y, 1);
     umma::fence_mbar_init();
   }
   umma::fence_before_sync();
@@ -413,7 +435,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           // l-1 (B2(l), B1(l-1)) and the accumulator block of layer l (flushed during iteration l-1).  The per-CTA
           // scratch of all SMs together is about the size of the L2, so a part of it lives in HBM between uses.
           const int l = (Lh - 1) - (c / C::CHUNKS - NG);
-          if (l > 1) tc::prefetch_l2(L.stash + ((size_t)blockIdx.x * Lh + (l - 1)) * C::STL, (uint32_t)(C::STL * 4));  // layer 0 has no stash
+          if (l > 1) tc::prefetch_l2(L.stash + ((size_t)blockIdx.x * Lh + (l - 1)) * C::STL, (uint32_t)(C::STL_F * 4));  // layer 0 has no stash
           for (int blk = 0; blk < C::MB; ++blk)
             tc::prefetch_l2(L.gacc + (size_t)blockIdx.x * net.pg + net.off_w[l] + (size_t)blk * 128 * L.ldw, (uint32_t)(128 * L.ldw * 4));
         }
@@ -432,7 +454,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     // the columns [sum_p w_p*y0 | sum_p w_p*y1] at the N = 256 rate (128 cycles instead of 2 x 103); the sixth
     // product w0*y2 goes into the second block.  The epilogue adds the two blocks with a round-to-nearest add
     // (two-level accumulation; the extra w2*y1 term is 2^-24 of the leading one).
-    auto gemm_wx = [&](bool two_level, bool concat) {
+    auto gemm_wx = [&](bool two_level, bool concat, bool store_in_flight = false) {
       for (int mb = 0; mb < C::MB; ++mb) {
         const uint32_t DB = tb + C::TC_D(mb), DS = two_level ? DB + NROW : DB;
         for (int ks = 0; ks < C::KS; ++ks) {
@@ -466,6 +488,8 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           ++ci;
         }
       }
+      // (YSIDE: the side-stash store reads the same operand tile; the epilogue may overwrite it once bar_fd completes)
+      if (store_in_flight) tc::bulk_wait_read();
       umma::commit(bar_fd);
     };
     // HALVES forward GEMM of half h: FOUR MMAs per k-step into three accumulator blocks of HN columns,
@@ -522,7 +546,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     // PROF: the issuing lane also waits for each GEMM and accumulates its duration (slots 8 fwd, 9 dgrad, 10 wgrad)
     const bool mprof = PROF && (L.phase_clk != nullptr) && blockIdx.x == 0 && lane == 0;
     long long gclk[3] = {0, 0, 0};
-    uint32_t mp_fd = 0, mp_w = 0;
+    uint32_t mp_fd = 0, mp_w = 0, mp_y = 0;
     for (int it = 0; it < my_tiles; ++it) {
       for (int l = 1; l < Lh; ++l) {
         if (C::HALVES) {
@@ -537,7 +561,10 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           tc::named_sync(TC_BAR_OP1, C::NEPI_T + 32);
           umma::fence_after_sync();
           const long long t0 = PROF ? clock64() : 0;
-          if (lane == 0) gemm_wx(true, C::CONCAT);   // forward: two-level accumulation (loss / residual precision)
+          const bool side = TRAIN && C::YSIDE;
+          if (side && lane == 0)   // Y^(l-1), planes b0 | b1 -> side stash of layer l-1
+            tc::bulk_s2g(L.stash + ((size_t)blockIdx.x * Lh + (l - 1)) * C::STL + C::STL_F, R1, (uint32_t)(C::YS_F * 4));
+          if (lane == 0) gemm_wx(true, C::CONCAT, side);   // forward: two-level accumulation (loss / residual precision)
           if (PROF && C::MB == 1 && lane == 0) { tc::wait_bar(bar_fd, mp_fd); mp_fd ^= 1; gclk[0] += clock64() - t0; }
           __syncwarp();
         }
@@ -547,11 +574,22 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           tc::named_sync(TC_BAR_OP1, C::NEPI_T + 32);
           umma::fence_after_sync();
           const long long t0 = PROF ? clock64() : 0;
+          if (C::YSIDE && lane == 0) {
+            // R2 is free (B1(l) waited for wgrad(l+1) before it wrote G): fetch Y^(l-1) from the side stash under dgrad(l)
+            if (l == Lh - 1) tc::bulk_wait_all();   // the forward pass's last side-stash store has reached global memory
+            mbar_expect_tx(bar_y, (uint32_t)(C::YS_F * 4));
+            bulk_g2s(R2, L.stash + ((size_t)blockIdx.x * Lh + (l - 1)) * C::STL + C::STL_F, (uint32_t)(C::YS_F * 4), bar_y);
+          }
           if (lane == 0) gemm_wx(C::DGRAD_TWO_LEVEL, C::CONCAT_DGRAD);
           __syncwarp();
           if (C::MB == 1) {
-            tc::named_sync(TC_BAR_OP2, C::NEPI_T + 32);
-            umma::fence_after_sync();
+            if (C::YSIDE) {
+              if (lane == 0) { tc::wait_bar(bar_y, mp_y); umma::fence_after_sync(); }
+              mp_y ^= 1;
+            } else {
+              tc::named_sync(TC_BAR_OP2, C::NEPI_T + 32);
+              umma::fence_after_sync();
+            }
             const long long t1 = PROF ? clock64() : 0;
             if (lane == 0) gemm_wgrad(l & 1, 0);
             if (PROF && lane == 0) {
@@ -1019,9 +1057,11 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
             if (l < Lh - 1) flush_dw(l + 1, (l + 1) & 1, 0, 0);
             lap(6);
             // ---- B2(l): the layer's input jets Y^(l-1) again (from the stash of layer l-1) -> R2 (two planes)
+            // (YSIDE: the MMA warp loads them from the side stash instead.  Issuing B2's stash reads before the flush, to hide
+            // their L2 round trip behind it, was measured slower: 40 more live registers across the flush spill, 22.4 vs 20.2 ms.)
             const int actp = (l - 1 == 0) ? net.act_first : net.act_hidden;
 #pragma unroll 1
-            for (int h = 0; h < NH; ++h) {
+            for (int h = 0; h < (C::YSIDE ? 0 : NH); ++h) {
               float st[K][V], d1[V], d2[V], d3[V], beta[3][V];
               if ((PROF && (L.exp_flags & 2)) || (TC_EXP & 2)) {  // experiment: B2 without its stash read (timing only)
 #pragma unroll
@@ -1046,7 +1086,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
 #pragma unroll
               for (int c = 0; c < K; ++c) tc::store_split4p<C::YP>(r2_slot(u, c, h), C::PLANE2, st[c]);
             }
-            operands_ready(TC_BAR_OP2);
+            if (!C::YSIDE) operands_ready(TC_BAR_OP2);
             lap(4);
           } else if (Lh > 1) {
             tc::wait_bar(bar_w, par_w);  // wgrad(1)

@@ -490,7 +490,7 @@ def main():
     e2e_value = wl.n_col * world * e2e_steps / e2e_s
     h2d = 4 * (R.x_col.size + sum(a.size for a in R.x_bd) + sum(a.size for a in R.u_bd))
     d2h = 8 * eng.n_info
-    launches_per_step = eng.launches_per_eval() + 1
+    launches_per_step = eng.launches_per_adam_step()
 
     # ---------------- roofline of the dominant kernel (collocation jet kernel), rank 0
     roofline = None

@@ -83,6 +83,9 @@ int32_t pinn_engine_num_loss_info(pinn_engine_t* h);
 int32_t pinn_engine_tile_points(pinn_engine_t* h);
 /* kernels one loss/gradient evaluation enqueues (an Adam step adds one) -- the bench's gpu_launches claim */
 int32_t pinn_engine_launches_per_eval(pinn_engine_t* h);
+/* kernels one Adam step of pinn_engine_adam_steps enqueues (evaluation kernels + the fused reduce / loss_info / Adam /
+ * re-pack tail; PINN_B200_FUSED_TAIL=0 restores the separate kernels) */
+int32_t pinn_engine_launches_per_adam_step(pinn_engine_t* h);
 /* kernel family chosen at create: 0 = fp32 SIMT (packed FFMA2), 1 = 3xTF32 mma.sync tensor-core kernel.
  * Selection: environment PINN_B200_KERNEL = simt | mma | auto (auto: tensor-core kernel for padded
  * widths 64, 128 and 256, fp32 kernel for 32). */

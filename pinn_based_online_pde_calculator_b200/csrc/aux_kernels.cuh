@@ -124,6 +124,102 @@ __global__ void k_adam(int n, float* __restrict__ p, const float* __restrict__ g
   p[i] -= lr[0] * mh / (sqrtf(vh) + 1e-8f);
 }
 
+// Fused tail of an Adam step (one launch instead of k_grad_reduce + k_loss_reduce + k_loss_info + k_adam + the next step's
+// k_pack): per parameter the fixed-order gradient reduction over the CTA rows (REDUCE; after an allreduce the gradient
+// is read from `fused` instead), the optax.adam update and the re-pack of the new value for the next evaluation.  The
+// LAST block to take a ticket reduces the loss partial sums, writes the loss_info row and advances the step count --
+// every block has read the count before it takes its ticket.  Same arithmetic, in the same order, as the separate kernels.
+template <bool REDUCE>
+__global__ void k_adam_tail(const FlatMap M, const float* __restrict__ gacc, int nb, int pg, float* __restrict__ fused,
+                            const double* __restrict__ loss_part, int n_slots, const LossMeta* __restrict__ meta,
+                            double* __restrict__ ring, int* __restrict__ ring_pos, int ring_cap, int* __restrict__ adam_count,
+                            float* __restrict__ adam_c, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                            const float* __restrict__ lr, float* __restrict__ wpack, unsigned* __restrict__ ticket) {
+  __shared__ float s_c[2];
+  __shared__ int s_last;
+  __shared__ double s_S[PINN_MAX_SEG];
+  if (threadIdx.x == 0) {
+    const int t = *adam_count + 1;
+    s_c[0] = (float)(1.0 - pow(0.9, (double)t));
+    s_c[1] = (float)(1.0 - pow(0.999, (double)t));
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M.n_params) {
+    int pt;
+    const int pk = flat_to_pack(M, i, pt);
+    float gi;
+    if (REDUCE) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int b = 0;
+      for (; b + 4 <= nb; b += 4) {
+        s0 += gacc[(size_t)(b + 0) * pg + pk];
+        s1 += gacc[(size_t)(b + 1) * pg + pk];
+        s2 += gacc[(size_t)(b + 2) * pg + pk];
+        s3 += gacc[(size_t)(b + 3) * pg + pk];
+      }
+      for (; b < nb; ++b) s0 += gacc[(size_t)b * pg + pk];
+      gi = (s0 + s1) + (s2 + s3);
+      fused[i] = gi;
+    } else {
+      gi = fused[i];
+    }
+    const float mi = 0.9f * m[i] + 0.1f * gi;
+    const float vi = 0.999f * v[i] + 0.001f * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float mh = mi / s_c[0];
+    const float vh = vi / s_c[1];
+    const float pn = p[i] - lr[0] * mh / (sqrtf(vh) + 1e-8f);
+    p[i] = pn;
+    wpack[pk] = pn;
+    if (pt >= 0) wpack[pt] = pn;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x >= 32) return;
+  __threadfence();
+  const int s = threadIdx.x;
+  float* tail = fused + M.n_params;
+  if (s < n_slots) {
+    if (REDUCE) {
+      double t = 0.0;
+      for (int b = 0; b < nb; ++b) t += loss_part[(size_t)b * n_slots + s];
+      const float hi = (float)t;
+      const float lo = (float)(t - (double)hi);
+      tail[2 * s] = hi;
+      tail[2 * s + 1] = lo;
+      s_S[s] = (double)hi + (double)lo;
+    } else {
+      s_S[s] = (double)tail[2 * s] + (double)tail[2 * s + 1];
+    }
+  }
+  __syncwarp();
+  if (s == 0) {
+    const int n = meta->n_slots;
+    const int pos = *ring_pos;
+    double* row = ring + (size_t)(pos % ring_cap) * (3 + n);
+    double ld = 0.0, le = 0.0;
+    for (int k = 0; k < n; ++k) {
+      const double mm = s_S[k] / meta->count[k];
+      row[3 + k] = mm;
+      if (k < n - 1) ld += mm; else le += mm;
+    }
+    row[1] = ld;
+    row[2] = le;
+    row[0] = ld + meta->weight[n - 1] * le;
+    *ring_pos = pos + 1;
+    *adam_count = *adam_count + 1;
+    adam_c[0] = s_c[0];
+    adam_c[1] = s_c[1];
+    *ticket = 0u;
+  }
+}
+
 __global__ void k_set_f32(float* dst, float v) { *dst = v; }
 
 // Aux program: scalar stack VM, one thread per point, run once per set_points/eval.

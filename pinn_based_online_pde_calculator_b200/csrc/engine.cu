@@ -136,6 +136,8 @@ struct pinn_engine {
   // graph
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_valid = false;
+  bool fused_tail = true;        // Adam step = evaluation kernels + ONE tail kernel (PINN_B200_FUSED_TAIL=0: separate kernels)
+  unsigned* d_ticket = nullptr;  // last-block ticket of the fused tail
   double cur_lr = -1.0;
 
   // nccl
@@ -363,6 +365,9 @@ static int create_impl(pinn_engine* h, const pinn_spec_t* spec, int device) {
   CK(cudaMalloc(&h->d_meta, sizeof(LossMeta)));
   CK(cudaMemset(h->d_ring_pos, 0, sizeof(int)));
   CK(cudaMemset(h->d_adam_count, 0, sizeof(int)));
+  CK(cudaMalloc(&h->d_ticket, sizeof(unsigned)));
+  CK(cudaMemset(h->d_ticket, 0, sizeof(unsigned)));
+  if (const char* ft = getenv("PINN_B200_FUSED_TAIL")) h->fused_tail = atoi(ft) != 0;
   if (h->kcol->kind == 3) CK(cudaMalloc(&h->d_wimg, jet_tc_image_bytes(h->net) * tc_image_copies()));
   if (h->use_umma) {
     CK(cudaMalloc(&h->d_uimg, sizeof(float) * jet_umma_image_floats(h->net)));
@@ -413,7 +418,7 @@ extern "C" void pinn_engine_destroy(pinn_engine_t* h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void* bufs[] = {h->d_params, h->d_fused, h->d_m, h->d_v, h->d_wpack, h->d_stash, h->d_seg_scale,
                   h->d_lr, h->d_adam_c, h->d_loss_part, h->d_ring, h->d_ring_pos, h->d_adam_count, h->d_meta,
-                  h->d_x, h->d_g, h->d_d, h->d_xt, h->d_S, h->d_Y, h->d_rho, h->d_alpha, h->d_scal, h->d_uimg, h->d_uclk, h->d_wimg};
+                  h->d_x, h->d_g, h->d_d, h->d_xt, h->d_S, h->d_Y, h->d_rho, h->d_alpha, h->d_scal, h->d_uimg, h->d_uclk, h->d_wimg, h->d_ticket};
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (auto& b : h->eval_bufs)
@@ -521,6 +526,12 @@ extern "C" int32_t pinn_engine_tile_points(pinn_engine_t* h) { return h->kcol->t
 extern "C" int32_t pinn_engine_launches_per_eval(pinn_engine_t* h) {
   return 5 + (h->kcol->kind == 3 ? 1 : 0) + (h->use_umma ? 1 : 0) + ((h->points_set && h->Lbc.n_tiles > 0) ? 1 : 0);
 }
+// kernels one Adam step enqueues: with the fused tail [weight images], [boundary kernel], collocation kernel, tail
+// (+ gradient reduce and loss reduce in front of an NCCL allreduce); otherwise one evaluation + k_adam
+extern "C" int32_t pinn_engine_launches_per_adam_step(pinn_engine_t* h) {
+  if (!h->fused_tail) return pinn_engine_launches_per_eval(h) + 1;
+  return 2 + (h->comm ? 2 : 0) + (h->kcol->kind == 3 ? 1 : 0) + (h->use_umma ? 1 : 0) + ((h->points_set && h->Lbc.n_tiles > 0) ? 1 : 0);
+}
 extern "C" int32_t pinn_engine_kernel_kind(pinn_engine_t* h) { return h->use_umma ? 2 : h->kcol->kind; }
 
 extern "C" int pinn_engine_set_params(pinn_engine_t* h, const float* flat, int on_device) {
@@ -589,10 +600,12 @@ static void fill_launch(pinn_engine* h, PinnLaunch& L, const JetKernelInfo* k, c
 
 // everything the fused kernels read besides the points: the padded fp32 pack and, for the tcgen05
 // family, the bf16x3 weight-image stream
-static int enqueue_pack(pinn_engine* h, const float* params_dev, cudaStream_t st) {
+static int enqueue_pack(pinn_engine* h, const float* params_dev, cudaStream_t st, bool pack = true) {
   const int P = h->fmap.n_params;
-  k_pack<<<(P + 255) / 256, 256, 0, st>>>(h->fmap, params_dev ? params_dev : h->d_params, h->d_wpack);
-  CK(cudaGetLastError());
+  if (pack) {   // (the fused Adam tail re-packs the updated parameters itself)
+    k_pack<<<(P + 255) / 256, 256, 0, st>>>(h->fmap, params_dev ? params_dev : h->d_params, h->d_wpack);
+    CK(cudaGetLastError());
+  }
   if (h->kcol->kind == 3) CK(jet_tc_build_images(h->d_wpack, h->net, h->kcol->ldw, h->d_wimg, tc_image_copies(), st));
   return 0;
 }
@@ -818,13 +831,15 @@ extern "C" int pinn_engine_set_loss(pinn_engine_t* h, double lw_eqn, double lref
 }
 
 // enqueue one evaluation: pack -> zero -> bc -> col -> reduce -> (allreduce) -> loss_info
-static int enqueue_eval(pinn_engine* h, const float* params_dev, int tick) {
+// adam_tail: the evaluation is the first half of an Adam step whose second half is the fused tail kernel (gradient
+// reduction + loss_info + Adam + re-pack in ONE launch; the caller packs once before the first step of a sequence)
+static int enqueue_eval(pinn_engine* h, const float* params_dev, int tick, bool adam_tail = false) {
   if (!h->points_set) return fail("set_points has not been called");
   cudaStream_t st = h->stream;
   const int P = h->fmap.n_params;
   const bool has_bc = h->Lbc.n_tiles > 0, fork = has_bc && h->fork_bc;
   const int nb = fork ? h->grid_col + h->grid_bc : std::max(h->grid_col, h->grid_bc);
-  if (enqueue_pack(h, params_dev, st)) return 1;
+  if (enqueue_pack(h, params_dev, st, !adam_tail)) return 1;
   CK(cudaMemsetAsync(h->d_gacc, 0, sizeof(float) * (size_t)nb * h->net.pg, st));
   CK(cudaMemsetAsync(h->d_loss_part, 0, sizeof(double) * (size_t)nb * h->n_slots, st));
   if (fork) {
@@ -842,6 +857,13 @@ static int enqueue_eval(pinn_engine* h, const float* params_dev, int tick) {
     CK(h->kcol->launch(h->Lcol, true, h->grid_col, st));
   }
   if (fork) CK(cudaStreamWaitEvent(st, h->ev_join, 0));  // join
+  if (adam_tail && !h->comm) {
+    k_adam_tail<true><<<(P + 127) / 128, 128, 0, st>>>(h->fmap, h->d_gacc, nb, h->net.pg, h->d_fused, h->d_loss_part, h->n_slots,
+                                                       h->d_meta, h->d_ring, h->d_ring_pos, h->ring_cap, h->d_adam_count, h->d_adam_c,
+                                                       h->d_params, h->d_m, h->d_v, h->d_lr, h->d_wpack, h->d_ticket);
+    CK(cudaGetLastError());
+    return 0;
+  }
   k_grad_reduce<<<(P + 127) / 128, 128, 0, st>>>(h->fmap, h->d_gacc, nb, h->net.pg, h->d_fused);
   CK(cudaGetLastError());
   k_loss_reduce<<<1, 32, 0, st>>>(h->d_loss_part, nb, h->n_slots, h->d_fused + P);
@@ -850,6 +872,13 @@ static int enqueue_eval(pinn_engine* h, const float* params_dev, int tick) {
     const int rc = g_nccl.AllReduce(h->d_fused, h->d_fused, (size_t)P + 2 * h->n_slots, /*ncclFloat32*/ 7,
                                     /*ncclSum*/ 0, h->comm, st);
     if (rc != 0) return fail("ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+  }
+  if (adam_tail) {   // after the allreduce: loss_info + Adam + re-pack in one launch
+    k_adam_tail<false><<<(P + 127) / 128, 128, 0, st>>>(h->fmap, h->d_gacc, nb, h->net.pg, h->d_fused, h->d_loss_part, h->n_slots,
+                                                        h->d_meta, h->d_ring, h->d_ring_pos, h->ring_cap, h->d_adam_count, h->d_adam_c,
+                                                        h->d_params, h->d_m, h->d_v, h->d_lr, h->d_wpack, h->d_ticket);
+    CK(cudaGetLastError());
+    return 0;
   }
   k_loss_info<<<1, 32, 0, st>>>(h->d_meta, h->d_fused + P, h->d_ring, h->d_ring_pos, h->ring_cap, tick,
                                 h->d_adam_count, h->d_adam_c);
@@ -884,6 +913,7 @@ extern "C" int pinn_engine_adam_init(pinn_engine_t* h) {
 }
 
 static int enqueue_adam_step(pinn_engine* h) {
+  if (h->fused_tail) return enqueue_eval(h, nullptr, 1, true);
   if (enqueue_eval(h, nullptr, 1)) return 1;
   const int P = h->fmap.n_params;
   k_adam<<<(P + 255) / 256, 256, 0, h->stream>>>(P, h->d_params, h->d_fused, h->d_m, h->d_v, h->d_lr, h->d_adam_c);
@@ -913,6 +943,11 @@ extern "C" int pinn_engine_adam_steps(pinn_engine_t* h, int32_t n_steps, double 
     h->graph_valid = true;
   }
   CK(cudaEventRecord(h->ev0, h->stream));
+  if (h->fused_tail) {   // the steps re-pack after their update; the first one needs the pack of the current parameters
+    const int P = h->fmap.n_params;
+    k_pack<<<(P + 255) / 256, 256, 0, h->stream>>>(h->fmap, h->d_params, h->d_wpack);
+    CK(cudaGetLastError());
+  }
   int done = 0;
   while (done < n_steps) {
     const int chunk = std::min(n_steps - done, h->ring_cap);

@@ -28,7 +28,7 @@ _lib = None
 EXPORTS = [
     "pinn_last_error", "pinn_device_count", "pinn_engine_create", "pinn_engine_destroy",
     "pinn_engine_set_stream", "pinn_engine_num_params", "pinn_engine_num_loss_info",
-    "pinn_engine_tile_points", "pinn_engine_launches_per_eval", "pinn_engine_set_params",
+    "pinn_engine_tile_points", "pinn_engine_launches_per_eval", "pinn_engine_launches_per_adam_step", "pinn_engine_set_params",
     "pinn_engine_get_params", "pinn_engine_set_points", "pinn_engine_set_global_counts",
     "pinn_engine_set_loss", "pinn_engine_loss_grad", "pinn_engine_adam_init", "pinn_engine_adam_steps",
     "pinn_engine_eval", "pinn_engine_lbfgs", "pinn_nccl_unique_id", "pinn_engine_init_nccl",
@@ -82,6 +82,7 @@ def load_library(path: Optional[str] = None):
     lib.pinn_engine_num_loss_info.argtypes = [C.c_void_p]
     lib.pinn_engine_tile_points.argtypes = [C.c_void_p]
     lib.pinn_engine_launches_per_eval.argtypes = [C.c_void_p]
+    lib.pinn_engine_launches_per_adam_step.argtypes = [C.c_void_p]
     lib.pinn_engine_kernel_kind.argtypes = [C.c_void_p]
     lib.pinn_engine_phase_profile.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     lib.pinn_sample_lhs.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_int64, C.c_int32, C.POINTER(C.c_float),
@@ -353,6 +354,10 @@ class PinnEngine:
     def launches_per_eval(self) -> int:
         """kernels one loss/gradient evaluation enqueues (an Adam step adds one)"""
         return int(self.lib.pinn_engine_launches_per_eval(self.h))
+
+    def launches_per_adam_step(self) -> int:
+        """kernels one Adam step of adam_steps enqueues (evaluation kernels + the fused tail kernel)"""
+        return int(self.lib.pinn_engine_launches_per_adam_step(self.h))
 
     def last_ms(self) -> float:
         return float(self.lib.pinn_engine_last_ms(self.h))

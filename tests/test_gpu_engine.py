@@ -66,6 +66,36 @@ def test_adam_trajectory_matches_oracle():
     eng.close()
 
 
+@pytest.mark.parametrize("shape", ["C2_4x64", "C1_3x20", "W128_3x128"])
+def test_fused_adam_tail_equals_the_separate_kernels(shape, monkeypatch):
+    """An Adam step ends in ONE kernel (gradient reduction + loss_info + Adam + re-pack); PINN_B200_FUSED_TAIL=0
+    restores k_grad_reduce / k_loss_reduce / k_loss_info / k_adam / k_pack.  Same arithmetic in the same order: the
+    loss_info rows, the parameters and a gradient taken afterwards must agree bit for bit, also across several
+    adam_steps calls with different learning rates and a set_params in between."""
+    kw = {"C2_4x64": dict(n_hidden=4, width=64, d_in=2, expr="u_xx + u_yy + 2*y*(1-y) + 2*x*(1-x)", n_col=2000, n_bd=100, n_bc=4,
+                          lb=[0.0, 0.0], ub=[1.0, 1.0]),
+          "C1_3x20": dict(n_hidden=3, width=20, d_in=1, expr="u_xx + 2", n_col=300, n_bd=1, n_bc=2, lb=[0.0], ub=[1.0]),
+          "W128_3x128": dict(n_hidden=3, width=128, d_in=2, expr="u_xx + u_yy + 9*u - sin(3*x)*sin(2*y)", n_col=700, n_bd=40, n_bc=4,
+                             lb=[0.0, 0.0], ub=[1.0, 1.0], act_first=1, act_hidden=1, scl=2.0)}[shape]
+    pb = make_problem(**kw)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PINN_B200_FUSED_TAIL", mode)
+        eng = engine_for(pb, lref=1.3)
+        assert eng.launches_per_adam_step() < eng.launches_per_eval() + 1 if mode == "1" else True
+        eng.adam_init()
+        r1 = eng.adam_steps(17, 1e-3)
+        r2 = eng.adam_steps(5, 4e-4)
+        p_mid = eng.get_params()
+        eng.set_params(p_mid * np.float32(1.001))
+        r3 = eng.adam_steps(3, 1e-3)
+        g, info = eng.loss_grad()
+        out[mode] = (np.concatenate([r1, r2, r3]), eng.get_params(), g.cpu().numpy(), info)
+        eng.close()
+    for a, b in zip(out["0"], out["1"]):
+        assert np.array_equal(a, b)
+
+
 def test_adam_final_l2_within_one_percent_of_oracle_schedule():
     # identical Adam schedule (fixed points, 400 steps) on the engine (fp32) and the oracle (fp64):
     # final relative L2 error vs u* = x(1-x) agrees within 1 % (north_star)

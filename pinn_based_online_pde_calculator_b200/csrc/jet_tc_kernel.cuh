@@ -67,7 +67,17 @@ struct TcCfg {
   static constexpr bool HALVES = (TC_HALVES != 0) && (WP == 128) && (NP == 32) && (K == 4);
   static constexpr int HN = NROW / 2;                        // columns per half
   static constexpr int HP = WP * SWB;                        // HALVES: one (half, plane) block = WP lines x 128 B; R1 order [h][plane]
-  static constexpr int FWD_COLS = HALVES ? 6 * HN : (WP / 128) * 2 * NROW;   // forward accumulators (HALVES: A | B | C per half)
+  // FWD3: forward GEMM in the four-MMA form with THREE accumulator blocks per M block (A = leading products only,
+  // B + C = the five small ones; see gemm_fwd3) instead of six MMAs into two blocks -- the same two-level precision at
+  // two thirds of the tensor-pipe time.  TC_FWD3 bit 0: one-M-block kernels, bit 1: two-M-block kernels.
+  // Measured (same box): C4 19.07 -> 18.78 ms (forward wait 7.2 M -> 6.5 M cycles per CTA), C5 unchanged (50.6 ms: its
+  // forward wait drops 20.5 M -> 17.3 M cycles, but the step is bound by the weight-gradient flush).
+#ifndef TC_FWD3
+#define TC_FWD3 3
+#endif
+  static constexpr bool FWD3 = !HALVES && (((TC_FWD3 & 1) && WP == 128) || ((TC_FWD3 & 2) && WP == 256)) && (2 * NROW <= 256) &&
+                               ((WP / 128) * 3 * NROW <= 512);
+  static constexpr int FWD_COLS = HALVES ? 6 * HN : FWD3 ? (WP / 128) * 3 * NROW : (WP / 128) * 2 * NROW;   // forward accumulators
   static constexpr int PLANE1 = NBLK * WP * SWB;             // region 1: all WP lines
   static constexpr int PLANE2 = NBLK * 128 * SWB;            // region 2: one block of 128 lines
 #ifndef TC_YP
@@ -492,6 +502,32 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
       if (store_in_flight) tc::bulk_wait_read();
       umma::commit(bar_fd);
     };
+    // FWD3 forward GEMM: per M block the accumulator blocks A | B | C of NROW columns,
+    //   C = w2*y0;  A, B = w0*[y0 | y1];  B, C += w1*[y0 | y1];  C += w0*y2        (epilogue: A + (B + C))
+    auto gemm_fwd3 = [&](bool store_in_flight) {
+      for (int mb = 0; mb < C::MB; ++mb) {
+        const uint32_t DA = tb + mb * 3 * NROW;
+        for (int ks = 0; ks < C::KS; ++ks) {
+          const uint64_t b01 = umma::smem_desc(r1a + ks * 16 * SWB, WP * SWB, 8 * SWB, LT);
+          const uint64_t b2 = umma::smem_desc(r1a + 2 * C::PLANE1 + ks * 16 * SWB, WP * SWB, 8 * SWB, LT);
+          const uint32_t acc = ks > 0 ? 1u : 0u;
+          const int s = (int)(ci % NSLOT);
+          tc::wait_bar(&bar_full[s], (uint32_t)((ci / NSLOT) & 1));
+          umma::fence_after_sync();
+          const uint64_t w2 = umma::smem_desc(rga + s * C::SLOT, 16, 256, 6);
+          const uint64_t w1 = umma::smem_desc(rga + s * C::SLOT + C::PLANE_W, 16, 256, 6);
+          const uint64_t w0 = umma::smem_desc(rga + s * C::SLOT + 2 * C::PLANE_W, 16, 256, 6);
+          umma::mma_bf16_ss(DA + 2 * NROW, w2, b01, id_wx, acc);
+          umma::mma_bf16_ss(DA, w0, b01, id_wx2, acc);
+          umma::mma_bf16_ss(DA + NROW, w1, b01, id_wx2, 1u);
+          umma::mma_bf16_ss(DA + 2 * NROW, w0, b2, id_wx, 1u);
+          umma::commit(&bar_empty[s]);
+          ++ci;
+        }
+      }
+      if (store_in_flight) tc::bulk_wait_read();
+      umma::commit(bar_fd);
+    };
     // HALVES forward GEMM of half h: FOUR MMAs per k-step into three accumulator blocks of HN columns,
     //   C    = w2*y0            (N = HN;   initialises C at k-step 0)
     //   A, B = w0*[y0 | y1]     (N = 2 HN: the planes b0, b1 of a half are adjacent n-blocks)
@@ -564,7 +600,9 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           const bool side = TRAIN && C::YSIDE;
           if (side && lane == 0)   // Y^(l-1), planes b0 | b1 -> side stash of layer l-1
             tc::bulk_s2g(L.stash + ((size_t)blockIdx.x * Lh + (l - 1)) * C::STL + C::STL_F, R1, (uint32_t)(C::YS_F * 4));
-          if (lane == 0) gemm_wx(true, C::CONCAT, side);   // forward: two-level accumulation (loss / residual precision)
+          if (lane == 0) {   // forward: two-level accumulation (loss / residual precision)
+            if (C::FWD3) gemm_fwd3(side); else gemm_wx(true, C::CONCAT, side);
+          }
           if (PROF && C::MB == 1 && lane == 0) { tc::wait_bar(bar_fd, mp_fd); mp_fd ^= 1; gclk[0] += clock64() - t0; }
           __syncwarp();
         }
@@ -691,6 +729,22 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
 #pragma unroll
           for (int i = 0; i < V; ++i) a[c][i] += sm[c][i];
       }
+    };
+    // FWD3 forward accumulators: blocks A | B | C of NROW columns per M block; result A + (B + C)
+    auto load_acc_fwd3 = [&](float (&a)[K][V], int h, int mb) {
+      float sb[K][V], sc[K][V];
+      const uint32_t base = tl + mb * 3 * NROW + 8 * n8 + V * h;
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        umma::tmem_ld4(base + NROW + c * NP, sb[c]);
+        umma::tmem_ld4(base + 2 * NROW + c * NP, sc[c]);
+        umma::tmem_ld4(base + c * NP, a[c]);
+      }
+      umma::tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < K; ++c)
+#pragma unroll
+        for (int i = 0; i < V; ++i) a[c][i] += sb[c][i] + sc[c][i];
     };
     // HALVES forward accumulators of half h: blocks A | B | C of HN columns; result A + (B + C)
     auto load_acc_fwd = [&](float (&a)[K][V], int h) {
@@ -842,6 +896,8 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
               lap(0);
             }
             load_acc_fwd(a, h);
+          } else if (C::FWD3) {
+            load_acc_fwd3(a, h, mb);
           } else {
             load_acc(a, h, mb);
           }

@@ -138,6 +138,8 @@ struct pinn_engine {
   bool graph_valid = false;
   bool fused_tail = true;        // Adam step = evaluation kernels + ONE tail kernel (PINN_B200_FUSED_TAIL=0: separate kernels)
   unsigned* d_ticket = nullptr;  // last-block ticket of the fused tail
+  int tc_share = 1;              // tcgen05 family, padded width 256: CTAs per (token-ordered) gradient-accumulator row
+  unsigned* d_tokens = nullptr;  // [rows][PINN_TOKENS] flush-order tokens of the shared rows
   double cur_lr = -1.0;
 
   // nccl
@@ -369,6 +371,18 @@ static int create_impl(pinn_engine* h, const pinn_spec_t* spec, int device) {
   CK(cudaMemset(h->d_ticket, 0, sizeof(unsigned)));
   if (const char* ft = getenv("PINN_B200_FUSED_TAIL")) h->fused_tail = atoi(ft) != 0;
   if (h->kcol->kind == 3) CK(cudaMalloc(&h->d_wimg, jet_tc_image_bytes(h->net) * tc_image_copies()));
+  if (h->kcol->kind == 3) {
+    // Padded width 256: 148 private accumulator rows of 1.3 MB (194 MB) cannot stay in the L2 and every weight-gradient
+    // flush became a DRAM read-modify-write; four CTAs per row (48 MB, inside the persisting carve-out) with a
+    // token-ordered, bit-reproducible flush (jet_tc_kernel.cuh).  PINN_TC_SHARE overrides (1 = private rows).
+    h->tc_share = (h->net.wp == 256) ? 4 : 1;
+    if (const char* e = getenv("PINN_TC_SHARE")) h->tc_share = (h->net.wp == 256) ? std::max(1, std::min(8, atoi(e))) : 1;
+    if (h->tc_share > 1) {
+      const size_t rows = (size_t)(h->grid_max_col + h->tc_share - 1) / h->tc_share;
+      CK(cudaMalloc(&h->d_tokens, sizeof(unsigned) * rows * PINN_TOKENS));
+      CK(cudaMemset(h->d_tokens, 0, sizeof(unsigned) * rows * PINN_TOKENS));
+    }
+  }
   if (h->use_umma) {
     CK(cudaMalloc(&h->d_uimg, sizeof(float) * jet_umma_image_floats(h->net)));
     CK(cudaMalloc(&h->d_uclk, sizeof(long long) * 8));
@@ -418,7 +432,7 @@ extern "C" void pinn_engine_destroy(pinn_engine_t* h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void* bufs[] = {h->d_params, h->d_fused, h->d_m, h->d_v, h->d_wpack, h->d_stash, h->d_seg_scale,
                   h->d_lr, h->d_adam_c, h->d_loss_part, h->d_ring, h->d_ring_pos, h->d_adam_count, h->d_meta,
-                  h->d_x, h->d_g, h->d_d, h->d_xt, h->d_S, h->d_Y, h->d_rho, h->d_alpha, h->d_scal, h->d_uimg, h->d_uclk, h->d_wimg, h->d_ticket};
+                  h->d_x, h->d_g, h->d_d, h->d_xt, h->d_S, h->d_Y, h->d_rho, h->d_alpha, h->d_scal, h->d_uimg, h->d_uclk, h->d_wimg, h->d_ticket, h->d_tokens};
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (auto& b : h->eval_bufs)
@@ -476,7 +490,9 @@ static void apply_l2_policy(pinn_engine* h) {
   const bool tcfam = h->kcol && h->kcol->kind == 3;
   const bool only_gacc = wsel ? !strcmp(wsel, "gacc") : tcfam, only_stash = wsel && !strcmp(wsel, "stash");
   char* base = reinterpret_cast<char*>(only_gacc ? h->d_gacc : h->d_stash);
-  const size_t bytes = (only_gacc ? h->gacc_floats : only_stash ? h->stash_floats : h->stash_floats + h->gacc_floats) * sizeof(float);
+  size_t bytes = (only_gacc ? h->gacc_floats : only_stash ? h->stash_floats : h->stash_floats + h->gacc_floats) * sizeof(float);
+  if (only_gacc && tcfam && h->tc_share > 1)   // shared rows: the collocation kernel only touches the first grid / share rows
+    bytes = (size_t)((h->grid_max_col + h->tc_share - 1) / h->tc_share) * h->net.pg * sizeof(float);
   const size_t carve = std::min<size_t>(bytes, (size_t)prop.persistingL2CacheMaxSize);
   {
     std::lock_guard<std::mutex> lk(g_l2_mu);
@@ -595,7 +611,8 @@ static void fill_launch(pinn_engine* h, PinnLaunch& L, const JetKernelInfo* k, c
   L.wimg_copy_bytes = (long long)jet_tc_image_bytes(h->net);
   L.wimg_copies = tc_image_copies();
   L.ldw = h->kcol->ldw;
-  (void)k;
+  L.gacc_share = (k == h->kcol) ? h->tc_share : 1;
+  L.gacc_token = (k == h->kcol && h->tc_share > 1) ? h->d_tokens : nullptr;
 }
 
 // everything the fused kernels read besides the points: the padded fp32 pack and, for the tcgen05

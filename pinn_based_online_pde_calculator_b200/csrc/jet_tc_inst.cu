@@ -9,7 +9,30 @@
 
 using Cfg = TcCfg<J_WP, J_N1, J_N2, J_MIX>;
 
+// shared gradient-accumulator rows (gacc_share > 1): the flush-order tokens start at zero, and the members of a row wait
+// for each other, so the launch is cooperative (the grid starts only when all of its CTAs can be resident)
+template <class Kern>
+static cudaError_t launch_shared_rows(Kern kern, const PinnLaunch& L, int grid, cudaStream_t stream) {
+  const int rows = (grid + L.gacc_share - 1) / L.gacc_share;
+  cudaError_t e = cudaMemsetAsync(L.gacc_token, 0, sizeof(unsigned) * (size_t)rows * PINN_TOKENS, stream);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::NT);
+  cfg.dynamicSmemBytes = Cfg::smem_bytes();
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, L);
+}
+
 static cudaError_t launch_impl(const PinnLaunch& L, bool train, int grid, cudaStream_t stream) {
+  if (train && L.gacc_share > 1 && L.gacc_token)
+    return L.phase_clk ? launch_shared_rows(jet_tc_kernel<Cfg, true, true>, L, grid, stream)
+                       : launch_shared_rows(jet_tc_kernel<Cfg, true, false>, L, grid, stream);
   if (train && L.phase_clk)
     jet_tc_kernel<Cfg, true, true><<<grid, Cfg::NT, Cfg::smem_bytes(), stream>>>(L);   // phase-clock instantiation
   else if (train)

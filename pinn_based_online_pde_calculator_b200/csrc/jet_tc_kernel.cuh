@@ -363,6 +363,13 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32
 }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources read
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }        // writes done
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
@@ -447,7 +454,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           const int l = (Lh - 1) - (c / C::CHUNKS - NG);
           if (l > 1) tc::prefetch_l2(L.stash + ((size_t)blockIdx.x * Lh + (l - 1)) * C::STL, (uint32_t)(C::STL_F * 4));  // layer 0 has no stash
           for (int blk = 0; blk < C::MB; ++blk)
-            tc::prefetch_l2(L.gacc + (size_t)blockIdx.x * net.pg + net.off_w[l] + (size_t)blk * 128 * L.ldw, (uint32_t)(128 * L.ldw * 4));
+            tc::prefetch_l2(L.gacc + (size_t)(blockIdx.x / (L.gacc_share > 1 ? L.gacc_share : 1)) * net.pg + net.off_w[l] + (size_t)blk * 128 * L.ldw, (uint32_t)(128 * L.ldw * 4));
         }
         if (++pos == per_tile) pos = 0;
       }
@@ -682,7 +689,36 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
       tc::named_arrive(bar, C::NEPI_T + 32);
     };
     float* const stash = TRAIN ? (L.stash + (size_t)blockIdx.x * Lh * C::STL) : nullptr;
-    float* const gacc = TRAIN ? (L.gacc + (size_t)blockIdx.x * net.pg) : nullptr;
+    // Gradient-accumulator rows shared by `share` consecutive CTAs (padded width 256: 148 private rows of 1.3 MB do not
+    // fit the L2 and every flush became a DRAM read-modify-write).  The additions into a shared row stay in a FIXED order
+    // -- tile round by tile round, member by member -- through one token per layer: a CTA adds the layer's weight- and
+    // bias-gradient contributions only when the token says it is its turn, and passes the token on when all its
+    // additions have been performed.  Members run one layer's flush apart, so nobody waits in steady state, and the
+    // gradient stays bit-reproducible.  (The launch is cooperative: all members are resident.)
+    const int share = L.gacc_share > 1 ? L.gacc_share : 1;
+    const bool shared_rows = TRAIN && share > 1;
+    const int grp = blockIdx.x / share, mem = blockIdx.x % share;
+    const int kcount = ((int)gridDim.x - grp * share) < share ? ((int)gridDim.x - grp * share) : share;
+    float* const gacc = TRAIN ? (L.gacc + (size_t)grp * net.pg) : nullptr;
+    unsigned* const tok = shared_rows ? (L.gacc_token + (size_t)grp * PINN_TOKENS) : nullptr;
+    auto gadd = [&](float* p, float v) { if (shared_rows) tc::red_add(p, v); else *p += v; };
+    auto token_wait = [&](int e, int round) {
+      if (!shared_rows) return;
+      if (lane == 0) {
+        const unsigned want = (unsigned)(round * kcount + mem);
+        bool ok = false;
+        for (int i = 0; i < (1 << 24); ++i) {
+          if (tc::ld_acquire_gpu(tok + e) == want) { ok = true; break; }
+          __nanosleep(64);
+        }
+        if (!ok) __trap();   // a protocol bug traps (launch failure) instead of hanging the GPU
+      }
+      __syncwarp();
+    };
+    // every epilogue thread has fenced its additions and passed an epi_sync before thread 0 calls this
+    auto token_pass = [&](int e, int round) {
+      if (shared_rows && tid == 0) tc::st_release_gpu(tok + e, (unsigned)(round * kcount + mem + 1));
+    };
     const int ldw = L.ldw;
     float wlacc[C::MB], w0acc[C::MB][3], blacc = 0.f;   // this thread's units: u, u + 128 (one per M block)
 #pragma unroll
@@ -1284,6 +1320,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
                 par_w ^= 1;
                 umma::fence_after_sync();
                 lap(5);
+                if (i == 0 && j == 0) token_wait(l, it);
                 flush_dw(l, 0, i, j);
                 if (i == 0) tc::named_arrive(TC_BAR_OP3, C::NEPI_T + 32);  // block drained: the next one may be issued
                 lap(6);
@@ -1298,10 +1335,13 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
               float g = 0.f;
 #pragma unroll
               for (int qq = 0; qq < Q; ++qq) g += s_bg[qq * WP + u + 128 * mb];
-              gacc[net.off_b[l] + u + 128 * mb] += g;
+              if (l == 0 && mb == 0) token_wait(0, it);   // (layer 0 has no weight-gradient flush that took the token)
+              gadd(gacc + net.off_b[l] + u + 128 * mb, g);
             }
           }
+          if (shared_rows) __threadfence();   // this thread's additions of layer l are performed
           epi_sync();
+          token_pass(l, it);
         }
       }
     }
@@ -1320,7 +1360,8 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
 #pragma unroll
             for (int qq = 0; qq < Q; ++qq) g += s_bg[qq * WP + u + 128 * mb];
             const int dst = ((r == 0) ? net.off_wl : net.off_w0 + (r - 1) * WP) + u + 128 * mb;
-            gacc[dst] += g;
+            if (r == 0 && mb == 0) token_wait(Lh, 0);
+            gadd(gacc + dst, g);
           }
         }
         epi_sync();
@@ -1333,8 +1374,13 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
         }
         if (lane == 0) {
           L.loss_part[(size_t)blockIdx.x * L.n_slots + slot] += lcur;
-          gacc[net.off_bl] += blacc;
+          gadd(gacc + net.off_bl, blacc);   // (warp 0 has q == 0: it holds the token of the final fold)
         }
+      }
+      if (shared_rows) {
+        __threadfence();
+        epi_sync();
+        token_pass(Lh, 0);
       }
     }
     if (PROF) {

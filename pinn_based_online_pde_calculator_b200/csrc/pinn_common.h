@@ -9,6 +9,7 @@
 #define PINN_MAX_CONSTS 48
 #define PINN_VM_STACK 12
 #define PINN_MAX_LAYERS 16   // hidden layers
+#define PINN_TOKENS 32       // flush-order tokens per shared gradient-accumulator row (one per layer + one for the final fold)
 #define PINN_NT 256          // threads per CTA of the fused kernel (2 CTAs per SM, <=128 regs)
 #define PINN_TU 8            // units per thread
 
@@ -80,6 +81,8 @@ struct PinnLaunch {
   long long wimg_copy_bytes;  // bytes of one replica of the image stream
   int wimg_copies;         // replicas (CTA b reads replica b % copies: spreads the stream over the L2 slices)
   int ldw;                 // row stride of the hidden matrices in wpack / gacc
+  int gacc_share;          // tcgen05 family: CTAs per gradient-accumulator row (1 = CTA-private rows)
+  unsigned* gacc_token;    // tcgen05 family, gacc_share > 1: [rows][PINN_TOKENS] flush-order tokens (zero before every launch)
   int exp_flags;           // experiment switches of the profiling instantiation (PINN_TC_EXP; 0 in production)
   PinnProgram prog;
 };

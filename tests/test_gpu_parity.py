@@ -124,6 +124,32 @@ def test_gradient_parity_on_a_131072_point_slice_of_c2():
 
 
 @pytest.mark.gpu
+def test_shared_accumulator_rows_are_bit_reproducible_and_match_private_rows(monkeypatch):
+    """Padded width 256 (C5): four CTAs share one gradient-accumulator row and add into it in a fixed, token-passed order
+    (jet_tc_kernel.cuh).  Two full tile rounds per CTA plus a ragged last round (37 whole tiles and one partial tile, so
+    some members of a row sit the last round out): repeated evaluations are bit-identical, and 4- and 3-CTA rows agree
+    with CTA-private rows (PINN_TC_SHARE=1, the configuration the oracle tests cover) to summation-order accuracy."""
+    from tests.helpers import problem_from_workload
+
+    pb = problem_from_workload("C5", 148 * 16 * 2 + 16 * 37 + 5)
+    grads = {}
+    for share in ("4", "1", "3"):
+        monkeypatch.setenv("PINN_TC_SHARE", share)
+        eng = engine_for(pb, lref=1.0)
+        assert eng.kernel == "tc_bf16x3"
+        g1, i1 = eng.loss_grad()
+        g1 = g1.cpu().numpy().copy()
+        for _ in range(3):
+            g2, i2 = eng.loss_grad()
+            assert np.array_equal(g1, g2.cpu().numpy()) and np.array_equal(i1, i2), share
+        grads[share] = (g1, i1)
+        eng.close()
+    for share in ("4", "3"):
+        assert rel_err(grads[share][0], grads["1"][0]) < 2e-6, rel_err(grads[share][0], grads["1"][0])
+        assert np.allclose(grads[share][1], grads["1"][1], rtol=1e-12, atol=0)   # the loss sums never were shared
+
+
+@pytest.mark.gpu
 def test_tcgen05_family_matches_oracle_and_production_kernel(monkeypatch):
     """Experimental tcgen05 family (PINN_B200_KERNEL=umma): TS-form layer GEMMs with the
     activation operand in Tensor Memory, swizzled MN-major weight-gradient GEMMs.  Loss, gradient and

@@ -81,7 +81,7 @@ if __name__ == "__main__":
     what = sys.argv[1:] or ["C4s", "W128tanh", "timing"]
     for w in what:
         if w == "timing":
-            timing()
+            timing(int(os.environ.get("TC_CHECK_NCOL", 1 << 20)))
         elif w == "timing5":
             timing(1 << 19, "C5")
         else:

@@ -406,6 +406,63 @@ def time_to_l2_c1(local_rank, cpu: bool, n_adam=2000, n_lbfgs=300, thresholds=(1
     return out
 
 
+def reference_problem_r0(local_rank, cpu: bool, gpu_steps=4000, cpu_budget_s=12.0):
+    """The reference's OWN problem size (pinn_app/software.py:1142-1201: 5,200 collocation + 200 boundary points, 6x60
+    network with the polar feature map): steady-state time of one Adam step through the CUDA-graph replay, an L-BFGS leg
+    (per objective evaluation, device-resident loop) and the CPU oracle (float64, all host cores) on the identical step."""
+    from pinn_based_online_pde_calculator_b200 import PinnEngine
+    from pinn_based_online_pde_calculator_b200.workloads import init_params, make_points, make_workload, unflatten
+
+    wl = make_workload("R0")
+    x_col, x_bd, u_bd = make_points(wl)
+    eng = PinnEngine(wl.net, wl.eq, n_bc=len(x_bd), device=local_rank)
+    eng.set_params(init_params(wl.net))
+    eng.set_points(x_col, x_bd, u_bd)
+    eng.set_loss(wl.lw, 1.0)
+    eng.set_loss(wl.lw, float(eng.loss_grad(want_grad=False)[1][0]))
+    eng.adam_init()
+    eng.adam_steps(100, 1e-3, want_rows=False)
+    t0 = time.perf_counter()
+    rows = eng.adam_steps(gpu_steps, 1e-3)          # rows come back: the wall clock includes the final synchronisation
+    adam_wall = time.perf_counter() - t0
+    adam_dev_ms = eng.last_ms()
+    t0 = time.perf_counter()
+    res, ev = eng.lbfgs(200, 1e-12)
+    lb_wall = time.perf_counter() - t0
+    out = {"workload": "R0: the reference's own smoke problem, 5,200 + 200 points, 6x60 tanh, polar feature map (software.py:1142-1201)",
+           "kernel": eng.kernel, "adam": {"steps": gpu_steps, "us_per_step_device": 1e3 * adam_dev_ms / gpu_steps,
+                                          "us_per_step_wall": 1e6 * adam_wall / gpu_steps, "launches_per_step": eng.launches_per_adam_step(),
+                                          "loss_first": float(rows[0, 0]), "loss_last": float(rows[-1, 0])},
+           "lbfgs": {"iterations": int(res["iterations"]), "evaluations": int(res["evaluations"]),
+                     "us_per_evaluation_wall": 1e6 * lb_wall / max(1, int(res["evaluations"])), "host_syncs": eng.lbfgs_host_syncs(),
+                     "final_loss": float(res["final_loss"])}}
+    eng.close()
+    if cpu:
+        import torch
+
+        from oracle import reference_oracle as O
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        net = wl.net
+        params = [[torch.tensor(W, dtype=torch.float64), torch.tensor(b, dtype=torch.float64)] for W, b in unflatten(net, init_params(net))]
+        limit = [torch.tensor(net.lb, dtype=torch.float64), torch.tensor(net.ub, dtype=torch.float64)]
+        f_u = O.sol_pred_create(limit, net.scl, net.epsil, act_s=net.act_first, feature_map=net.feature_map)
+        lossf = O.loss_create(f_u, torch.tensor([wl.lw, 0.0], dtype=torch.float64), 1.0)   # residual: the reference's gov_eqn (polar Laplacian)
+        data = dict(x_col=torch.tensor(x_col, dtype=torch.float64), cond_bd=[[torch.tensor(a, dtype=torch.float64) for a in x_bd],
+                                                                            [torch.tensor(a, dtype=torch.float64)[:, None] for a in u_bd]])
+        lossf.ref = float(lossf(params, data)[1][0])
+        st = O.AdamState(params)
+        params, _, st = O.adam_minimizer(lossf, params, data, 1e-3, st)   # warm-up
+        n, t0 = 0, time.perf_counter()
+        while n < 200 and time.perf_counter() - t0 < cpu_budget_s:
+            params, info, st = O.adam_minimizer(lossf, params, data, 1e-3, st)
+            n += 1
+        cpu_ms = 1e3 * (time.perf_counter() - t0) / max(1, n)
+        out["cpu"] = {"cores": os.cpu_count(), "dtype": "f64", "kind": "port", "adam_steps_run": n, "ms_per_step": cpu_ms,
+                      "speedup_adam_step": cpu_ms * 1e3 / out["adam"]["us_per_step_wall"]}
+    return out
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     args = parse_args()
@@ -549,8 +606,10 @@ def main():
         return
 
     ttl2 = None
+    ref_problem = None
     if world == 1 and not args.no_extra:
         ttl2 = time_to_l2_c1(local_rank, cpu=not args.no_cpu_baseline)
+        ref_problem = reference_problem_r0(local_rank, cpu=not args.no_cpu_baseline)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -576,7 +635,7 @@ def main():
                 "note": "host buffers through PinnEngine.prefetch_points/commit_points + adam_steps: the H2D copy of step i+1 runs on a copy stream under the compute of step i; loss_info read back every step"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "configs": configs, "time_to_l2": ttl2, "strong": strong,
+        "configs": configs, "time_to_l2": ttl2, "reference_problem": ref_problem, "strong": strong,
         "loss_first": float(R.info0[0]), "loss_last": float(info1[0]), "wall_s_timed_region": t_wall,
     }
     print(json.dumps(out))

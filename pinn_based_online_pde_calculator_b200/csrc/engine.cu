@@ -1214,7 +1214,9 @@ static int lbfgs_alloc(pinn_engine* h) {
   CK(cudaMalloc(&h->d_S, sizeof(float) * (size_t)P * m));
   CK(cudaMalloc(&h->d_Y, sizeof(float) * (size_t)P * m));
   CK(cudaMalloc(&h->d_rho, sizeof(double) * m));
-  CK(cudaMalloc(&h->d_alpha, sizeof(double) * m));
+  CK(cudaMalloc(&h->d_alpha, sizeof(double) * lb_scratch_doubles(P)));   // scratch of the vector-free two-loop recursion
+  CK(cudaMemsetAsync(h->d_S, 0, sizeof(float) * (size_t)P * m, h->stream));   // (its Gram pass reads every history slot)
+  CK(cudaMemsetAsync(h->d_Y, 0, sizeof(float) * (size_t)P * m, h->stream));
   CK(cudaMalloc(&h->d_scal, sizeof(double) * 4));
   return 0;
 }
@@ -1243,7 +1245,7 @@ static int lbfgs_legacy(pinn_engine_t* h, int32_t max_iter, double tol, int32_t 
   int cnt = 0, head = 0;
   R.converged = ginf <= tol;
   while (!R.converged && !R.failed && R.iterations < max_iter) {
-    k_lbfgs_direction<<<1, 1024, 0, st>>>(P, m, cnt, head, h->d_g, h->d_S, h->d_Y, h->d_rho, h->d_d, h->d_alpha);
+    CK(lb_two_loop(P, nullptr, m, cnt, head, h->d_g, h->d_S, h->d_Y, h->d_rho, h->d_d, h->d_alpha, st));
     k_dot_inf<<<1, 1024, 0, st>>>(P, h->d_g, h->d_d, h->d_scal);
     CK(cudaMemcpyAsync(sc, h->d_scal, sizeof sc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

@@ -37,6 +37,15 @@
                        // pass has consumed them, so that dead dirty lines are never written back.  Measured: C4 19.8 ms with,
                        // 19.2 ms without; C5 49.6 / 49.7 ms -- the write-backs are not what the kernel waits for.  Off.
 #endif
+// B2MERGE (one-M-block kernels): the weight-gradient operand Y^l is produced at the TOP of backward iteration l, from the
+// stash values B1(l) has just loaded anyway (one stash read per layer instead of two), while dgrad(l+1) runs; the tensor
+// core sees the same order of GEMMs as before.
+// Measured on C4 (1M points, same box): bit-identical results, 19.75 ms with, 19.67 ms without -- the stash loads that
+// were hidden behind the wait for dgrad(l+1) are now needed at once (Y-part 6.0 M -> 8.2 M cycles per CTA), which costs
+// what the second read cost.  Off by default.
+#ifndef TC_B2MERGE
+#define TC_B2MERGE 0
+#endif
 #ifndef TC_EXP
 #define TC_EXP 0   // timing experiments (wrong results): 1 no accumulator flush, 2 no B2 stash read, 4 no stash write, 8 no B1 stash read
 #endif
@@ -1063,6 +1072,27 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
               if (act == PINN_SIN) tc::ld4(stash_ptr(l, K, h, 0), csA[h]);
             }
           }
+          constexpr bool MERGE = (TC_B2MERGE != 0) && !C::YSIDE;
+          if (MERGE && l < Lh - 1) {
+            // ---- Y^l (the layer's output jets, two planes) -> R2 for wgrad(l+1).  R2 is free: B1(l+1) waited for wgrad(l+2).
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+              float o[K][V], y[V], d1[V], d2[V], d3[V], beta[3][V];
+#pragma unroll
+              for (int i = 0; i < V; ++i) { y[i] = stA[h][0][i]; d1[i] = csA[h][i]; }
+#pragma unroll
+              for (int c = 0; c < K; ++c)
+#pragma unroll
+                for (int i = 0; i < V; ++i) o[c][i] = stA[h][c][i];
+              load_beta(beta, h);
+              tc::act_bwd<V, false>(act, y, d1, d2, d3);
+              tc::jets_outputs<C, V>(o, y, d1, d2, beta);
+#pragma unroll
+              for (int c = 0; c < K; ++c) tc::store_split4p<C::YP>(r2_slot(u, c, h), C::PLANE2, o[c]);
+            }
+            operands_ready(TC_BAR_OP2);
+            lap(4);
+          }
           if (l < Lh - 1) {
             tc::wait_bar(bar_fd, par_fd);  // dgrad(l+1)
             par_fd ^= 1;
@@ -1123,6 +1153,13 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
 #pragma unroll
               for (int c = 0; c < K; ++c) tc::store_split4p<3>(r1_slot(u, c, h), R1_PST, yb[c]);
             } else {
+              if (MERGE && h == 0 && Lh > 1) {
+                lap(3);
+                tc::wait_bar(bar_w, par_w);  // wgrad(1): its block is flushed below
+                par_w ^= 1;
+                umma::fence_after_sync();
+                lap(5);
+              }
 #pragma unroll
               for (int i = 0; i < V; ++i)
 #pragma unroll
@@ -1143,7 +1180,11 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
             for (int c = 0; c < nch; ++c) tc::discard_l2(stash + (size_t)l * C::STL + ((size_t)(c * Q + q) * 128 + 32 * quad) * 8 + lane * 32);
           }
           lap(3);
-          if (l > 0) {
+          if (MERGE) {
+            // ---- F(l+1): the block of wgrad(l+1) (complete: B1(l) waited for it), under dgrad(l)
+            if (l < Lh - 1) flush_dw(l + 1, (l + 1) & 1, 0, 0);
+            lap(6);
+          } else if (l > 0) {
             // ---- F(l+1): flush the previous layer's weight-gradient block (wgrad(l+1) completed: B1 waited for it)
             // first -- global traffic only, dgrad(l) has the shared-memory bandwidth to itself meanwhile
             if (l < Lh - 1) flush_dw(l + 1, (l + 1) & 1, 0, 0);

@@ -36,6 +36,12 @@ int32_t pinn_engine_lbfgs_trace_rows(pinn_engine_t* h);
 int pinn_engine_lbfgs_trace_get(pinn_engine_t* h, float* out_host, int32_t rows);
 int32_t pinn_engine_lbfgs_host_syncs(pinn_engine_t* h);
 
+/* L-BFGS search direction in isolation (test hook): d = -H g from host arrays S, Y [m][n] (m <= 10), rho [m], the live
+ * pair count cnt and the ring head (newest pair at slot head - 1), through the engine's vector-free two-loop recursion
+ * (Gram matrix -> coefficient recursion -> combination; csrc/lbfgs_dev.cu).  No engine handle needed. */
+int pinn_lbfgs_direction_test(int device, int32_t n, int32_t m, int32_t cnt, int32_t head, const float* g, const float* S,
+                              const float* Y, const double* rho, float* d_out);
+
 #ifdef __cplusplus
 }
 #endif

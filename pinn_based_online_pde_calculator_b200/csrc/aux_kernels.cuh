@@ -63,16 +63,26 @@ __global__ void k_grad_reduce(const FlatMap M, const float* __restrict__ gacc, i
   fused[i] = (s0 + s1) + (s2 + s3);
 }
 
-// loss partial sums: tail[2s], tail[2s+1] = hi/lo split of sum_b loss_part[b][s]
+// sum over the CTA rows of loss term s by ONE WARP, in a fixed order: lane l adds rows l, l+32, ..., then a butterfly
+// over the lanes (every lane returns the sum).  Shared by k_loss_reduce and the fused Adam tail: same bits.
+__device__ __forceinline__ double loss_slot_sum(const double* __restrict__ loss_part, int nb, int n_slots, int s) {
+  double t = 0.0;
+  for (int b = threadIdx.x & 31; b < nb; b += 32) t += loss_part[(size_t)b * n_slots + s];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+// loss partial sums: tail[2s], tail[2s+1] = hi/lo split of sum_b loss_part[b][s]; one warp per loss term
 __global__ void k_loss_reduce(const double* __restrict__ loss_part, int nb, int n_slots,
                               float* __restrict__ tail) {
-  const int s = threadIdx.x;
+  const int s = threadIdx.x >> 5;
   if (s >= n_slots) return;
-  double t = 0.0;
-  for (int b = 0; b < nb; ++b) t += loss_part[(size_t)b * n_slots + s];
-  const float hi = (float)t;
-  tail[2 * s] = hi;
-  tail[2 * s + 1] = (float)(t - (double)hi);
+  const double t = loss_slot_sum(loss_part, nb, n_slots, s);
+  if ((threadIdx.x & 31) == 0) {
+    const float hi = (float)t;
+    tail[2 * s] = hi;
+    tail[2 * s + 1] = (float)(t - (double)hi);
+  }
 }
 
 struct LossMeta {
@@ -181,25 +191,25 @@ __global__ void k_adam_tail(const FlatMap M, const float* __restrict__ gacc, int
     s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
   }
   __syncthreads();
-  if (!s_last || threadIdx.x >= 32) return;
+  if (!s_last) return;
   __threadfence();
-  const int s = threadIdx.x;
   float* tail = fused + M.n_params;
-  if (s < n_slots) {
+  for (int s = threadIdx.x >> 5; s < n_slots; s += (int)(blockDim.x >> 5)) {   // one warp per loss term
     if (REDUCE) {
-      double t = 0.0;
-      for (int b = 0; b < nb; ++b) t += loss_part[(size_t)b * n_slots + s];
-      const float hi = (float)t;
-      const float lo = (float)(t - (double)hi);
-      tail[2 * s] = hi;
-      tail[2 * s + 1] = lo;
-      s_S[s] = (double)hi + (double)lo;
-    } else {
+      const double t = loss_slot_sum(loss_part, nb, n_slots, s);
+      if ((threadIdx.x & 31) == 0) {
+        const float hi = (float)t;
+        const float lo = (float)(t - (double)hi);
+        tail[2 * s] = hi;
+        tail[2 * s + 1] = lo;
+        s_S[s] = (double)hi + (double)lo;
+      }
+    } else if ((threadIdx.x & 31) == 0) {
       s_S[s] = (double)tail[2 * s] + (double)tail[2 * s + 1];
     }
   }
-  __syncwarp();
-  if (s == 0) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
     const int n = meta->n_slots;
     const int pos = *ring_pos;
     double* row = ring + (size_t)(pos % ring_cap) * (3 + n);

@@ -883,7 +883,7 @@ static int enqueue_eval(pinn_engine* h, const float* params_dev, int tick, bool 
   }
   k_grad_reduce<<<(P + 127) / 128, 128, 0, st>>>(h->fmap, h->d_gacc, nb, h->net.pg, h->d_fused);
   CK(cudaGetLastError());
-  k_loss_reduce<<<1, 32, 0, st>>>(h->d_loss_part, nb, h->n_slots, h->d_fused + P);
+  k_loss_reduce<<<1, 32 * h->n_slots, 0, st>>>(h->d_loss_part, nb, h->n_slots, h->d_fused + P);
   CK(cudaGetLastError());
   if (h->comm) {
     const int rc = g_nccl.AllReduce(h->d_fused, h->d_fused, (size_t)P + 2 * h->n_slots, /*ncclFloat32*/ 7,
@@ -1494,6 +1494,30 @@ extern "C" int pinn_engine_lbfgs_trace_get(pinn_engine_t* h, float* out_host, in
   if (rows > 0) CK(cudaMemcpy(out_host, h->d_trace, sizeof(float) * (size_t)rows * h->fmap.n_params, cudaMemcpyDeviceToHost));
   return 0;
 }
+extern "C" int pinn_lbfgs_direction_test(int device, int32_t n, int32_t m, int32_t cnt, int32_t head, const float* g, const float* S,
+                                         const float* Y, const double* rho, float* d_out) {
+  if (n <= 0 || m <= 0 || m > 10 || cnt < 0 || cnt > m) return fail("lbfgs_direction_test: bad sizes");
+  CK(cudaSetDevice(device));
+  float *dg = nullptr, *dS = nullptr, *dY = nullptr, *dd = nullptr;
+  double *drho = nullptr, *dscr = nullptr;
+  auto cleanup = [&]() { for (void* p : {(void*)dg, (void*)dS, (void*)dY, (void*)dd, (void*)drho, (void*)dscr}) if (p) cudaFree(p); };
+  cudaError_t e = cudaMalloc(&dg, sizeof(float) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&dS, sizeof(float) * (size_t)n * m);
+  if (e == cudaSuccess) e = cudaMalloc(&dY, sizeof(float) * (size_t)n * m);
+  if (e == cudaSuccess) e = cudaMalloc(&dd, sizeof(float) * n);
+  if (e == cudaSuccess) e = cudaMalloc(&drho, sizeof(double) * m);
+  if (e == cudaSuccess) e = cudaMalloc(&dscr, sizeof(double) * lb_scratch_doubles(n));
+  if (e == cudaSuccess) e = cudaMemcpy(dg, g, sizeof(float) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dS, S, sizeof(float) * (size_t)n * m, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dY, Y, sizeof(float) * (size_t)n * m, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(drho, rho, sizeof(double) * m, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = lb_two_loop(n, nullptr, m, cnt, head, dg, dS, dY, drho, dd, dscr, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(d_out, dd, sizeof(float) * n, cudaMemcpyDeviceToHost);
+  cleanup();
+  if (e != cudaSuccess) return fail("lbfgs_direction_test: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 extern "C" int32_t pinn_engine_lbfgs_host_syncs(pinn_engine_t* h) { return h->lbfgs_syncs; }
 
 // ---------------------------------------------------------------- NCCL

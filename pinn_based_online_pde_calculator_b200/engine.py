@@ -32,7 +32,7 @@ EXPORTS = [
     "pinn_engine_get_params", "pinn_engine_set_points", "pinn_engine_set_global_counts",
     "pinn_engine_set_loss", "pinn_engine_loss_grad", "pinn_engine_adam_init", "pinn_engine_adam_steps",
     "pinn_engine_eval", "pinn_engine_lbfgs", "pinn_nccl_unique_id", "pinn_engine_init_nccl",
-    "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels", "pinn_engine_kernel_kind", "pinn_engine_phase_profile", "pinn_sample_lhs", "pinn_sample_cdf2d", "pinn_engine_sync", "pinn_umma_probe", "pinn_engine_prefetch_points", "pinn_engine_commit_points", "pinn_engine_umma_clocks",
+    "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels", "pinn_engine_kernel_kind", "pinn_engine_phase_profile", "pinn_sample_lhs", "pinn_sample_cdf2d", "pinn_engine_sync", "pinn_umma_probe", "pinn_engine_prefetch_points", "pinn_engine_commit_points", "pinn_engine_umma_clocks", "pinn_lbfgs_direction_test",
     "pinn_engine_lbfgs_trace", "pinn_engine_lbfgs_trace_rows", "pinn_engine_lbfgs_trace_get", "pinn_engine_lbfgs_host_syncs",
 ]
 
@@ -475,6 +475,22 @@ def fma_peak_tflops(device: int = 0, variant: int = 0) -> float:
     out = C.c_double()
     _check(lib, lib.pinn_fma_peak(device, variant, C.byref(out)))
     return out.value
+
+
+def lbfgs_direction(g, S, Y, rho, cnt: int, head: int, device: int = 0) -> np.ndarray:
+    """Test hook: d = -H g through the engine's vector-free two-loop recursion (csrc/lbfgs_dev.cu) for a history of
+    `cnt` live pairs in the ring S, Y [m][n] (newest at slot head - 1), rho[i] = 1 / (s_i . y_i)."""
+    lib = load_library()
+    g = np.ascontiguousarray(g, dtype=np.float32)
+    S = np.ascontiguousarray(S, dtype=np.float32)
+    Y = np.ascontiguousarray(Y, dtype=np.float32)
+    rho = np.ascontiguousarray(rho, dtype=np.float64)
+    m, n = S.shape
+    out = np.empty(n, dtype=np.float32)
+    lib.pinn_lbfgs_direction_test.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]
+    _check(lib, lib.pinn_lbfgs_direction_test(device, n, m, int(cnt), int(head), _ptr(g), _ptr(S), _ptr(Y), _ptr(rho), _ptr(out)))
+    return out
 
 
 def shard_range(n: int, rank: int, world: int):

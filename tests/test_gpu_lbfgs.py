@@ -133,3 +133,36 @@ def test_final_solution_agrees_with_an_independent_lbfgs(case):
     f_gpu, f_ref = rows[-1][0] / lref, sp.fun
     assert f_gpu < 5 * f_ref + 1e-12 or f_gpu < 1e-6, (f_gpu, f_ref)
     eng.close()
+
+
+@pytest.mark.parametrize("n,cnt,head", [(901, 0, 0), (901, 3, 3), (1024, 10, 4), (1025, 7, 9), (18781, 10, 0), (264449, 10, 6)])
+def test_vector_free_direction_matches_the_two_loop_recursion(n, cnt, head):
+    """The search direction is computed from the Gram matrix of [S | Y | g] (one multi-block pass), a recursion on
+    coefficient vectors and one combination pass (csrc/lbfgs_dev.cu).  Against Nocedal & Wright's algorithm 7.4 in float64
+    numpy on random histories: single-launch path (n <= 1024), multi-block path, partially filled and wrapped rings,
+    stale data in the dead slots."""
+    from pinn_based_online_pde_calculator_b200.engine import lbfgs_direction
+
+    m = 10
+    rng = np.random.RandomState(n + 31 * cnt + head)
+    S = (rng.standard_normal((m, n)) * 1e-2).astype(np.float32)
+    Y = (S * rng.uniform(0.5, 2.0, size=(m, 1)) + 1e-3 * rng.standard_normal((m, n))).astype(np.float32)   # s.y > 0
+    g = rng.standard_normal(n).astype(np.float32)
+    live = [((head - 1 - j) % m + m) % m for j in range(cnt)]                                              # newest -> oldest
+    rho = np.full(m, np.nan)
+    for sl in live:
+        rho[sl] = 1.0 / float(S[sl].astype(np.float64) @ Y[sl].astype(np.float64))
+    rho_dev = np.where(np.isnan(rho), 123.0, rho)   # dead slots: arbitrary finite numbers the kernel must ignore
+    d = lbfgs_direction(g, S, Y, rho_dev, cnt, head)
+    q = g.astype(np.float64)
+    alpha = {}
+    for sl in live:
+        alpha[sl] = rho[sl] * (S[sl].astype(np.float64) @ q)
+        q = q - alpha[sl] * Y[sl]
+    if cnt:
+        sl = live[0]
+        q = q * ((S[sl].astype(np.float64) @ Y[sl]) / (Y[sl].astype(np.float64) @ Y[sl]))
+    for sl in reversed(live):
+        beta = rho[sl] * (Y[sl].astype(np.float64) @ q)
+        q = q + (alpha[sl] - beta) * S[sl]
+    assert rel_err(d, -q) < 2e-6, rel_err(d, -q)

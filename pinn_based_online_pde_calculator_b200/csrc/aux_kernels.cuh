@@ -315,56 +315,6 @@ __global__ void k_dot_inf(int n, const float* __restrict__ g, const float* __res
   }
 }
 
-// two-loop recursion (Nocedal & Wright alg. 7.4): d = -H g, history ring of `cnt` pairs,
-// newest at slot (head-1) mod m.  Single block.
-__global__ void k_lbfgs_direction(int n, int m, int cnt, int head, const float* __restrict__ g,
-                                  const float* __restrict__ Sh, const float* __restrict__ Yh,
-                                  const double* __restrict__ rho, float* __restrict__ d,
-                                  double* __restrict__ alpha /* [m] scratch */) {
-  __shared__ double sh[32];
-  for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = g[i];
-  __syncthreads();
-  for (int j = 0; j < cnt; ++j) {
-    const int slot = ((head - 1 - j) % m + m) % m;
-    const float* s = Sh + (size_t)slot * n;
-    const float* y = Yh + (size_t)slot * n;
-    double t = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) t += (double)s[i] * (double)d[i];
-    t = block_sum_d(t, sh);
-    const double a = rho[slot] * t;
-    if (threadIdx.x == 0) alpha[slot] = a;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = (float)((double)d[i] - a * (double)y[i]);
-    __syncthreads();
-  }
-  if (cnt > 0) {
-    const int slot = ((head - 1) % m + m) % m;
-    const float* s = Sh + (size_t)slot * n;
-    const float* y = Yh + (size_t)slot * n;
-    double sy = 0.0, yy = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      sy += (double)s[i] * (double)y[i];
-      yy += (double)y[i] * (double)y[i];
-    }
-    sy = block_sum_d(sy, sh);
-    yy = block_sum_d(yy, sh);
-    const double gamma = sy / yy;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = (float)(gamma * (double)d[i]);
-    __syncthreads();
-  }
-  for (int j = cnt - 1; j >= 0; --j) {
-    const int slot = ((head - 1 - j) % m + m) % m;
-    const float* s = Sh + (size_t)slot * n;
-    const float* y = Yh + (size_t)slot * n;
-    double t = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) t += (double)y[i] * (double)d[i];
-    t = block_sum_d(t, sh);
-    const double b = rho[slot] * t;
-    const double a = alpha[slot];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = (float)((double)d[i] + (a - b) * (double)s[i]);
-    __syncthreads();
-  }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = -d[i];
-}
 
 // push (s,y) = (xt-x, gt-g) into slot; x<-xt, g<-gt; out[0]=s.y, out[1]=||gt||_inf, rho[slot]=1/s.y
 __global__ void k_lbfgs_push(int n, int slot, float* __restrict__ x, float* __restrict__ g,

@@ -46,6 +46,12 @@
 #ifndef TC_B2MERGE
 #define TC_B2MERGE 0
 #endif
+// Measured on C5 (512k points, same box): 41.4 -> 40.7 ms (waiting for the weight-gradient blocks 20.4 M -> 13.0 M cycles
+// per CTA, but the data-gradient GEMM now ends later: 10.7 M -> 15.2 M) -- its chunks are bound by the weight-image stream
+// (192 KB per layer and 16-point tile at ~16 B/cycle), not by their place in the issue order.
+#ifndef TC_DGRAD_INTERLEAVE
+#define TC_DGRAD_INTERLEAVE 1
+#endif
 #ifndef TC_EXP
 #define TC_EXP 0   // timing experiments (wrong results): 1 no accumulator flush, 2 no B2 stash read, 4 no stash write, 8 no B1 stash read
 #endif
@@ -480,10 +486,14 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     // the columns [sum_p w_p*y0 | sum_p w_p*y1] at the N = 256 rate (128 cycles instead of 2 x 103); the sixth
     // product w0*y2 goes into the second block.  The epilogue adds the two blocks with a round-to-nearest add
     // (two-level accumulation; the extra w2*y1 term is 2^-24 of the leading one).
-    auto gemm_wx = [&](bool two_level, bool concat, bool store_in_flight = false) {
+    // (chunk q of NQ: the k-steps [q, q+1) * MB*KS/NQ of the (M block, k-step) sequence -- the data-gradient GEMM of the
+    // two-block kernel is issued in four chunks between the weight-gradient blocks; the commit comes with the last chunk)
+    auto gemm_wx = [&](bool two_level, bool concat, bool store_in_flight = false, int q = 0, int NQ = 1) {
+      const int per = C::MB * C::KS / NQ;
       for (int mb = 0; mb < C::MB; ++mb) {
         const uint32_t DB = tb + C::TC_D(mb), DS = two_level ? DB + NROW : DB;
         for (int ks = 0; ks < C::KS; ++ks) {
+          if ((mb * C::KS + ks) / per != q) continue;
           // HALVES (data-gradient GEMM over the whole tile): plane p of half h sits at (3h + p) * HP, so the two n-blocks
           // of a plane are 3 * HP apart
           constexpr uint32_t PST = C::HALVES ? C::HP : C::PLANE1, LBO = C::HALVES ? 3 * C::HP : WP * SWB;
@@ -516,7 +526,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
       }
       // (YSIDE: the side-stash store reads the same operand tile; the epilogue may overwrite it once bar_fd completes)
       if (store_in_flight) tc::bulk_wait_read();
-      umma::commit(bar_fd);
+      if (q == NQ - 1) umma::commit(bar_fd);
     };
     // FWD3 forward GEMM: per M block the accumulator blocks A | B | C of NROW columns,
     //   C = w2*y0;  A, B = w0*[y0 | y1];  B, C += w1*[y0 | y1];  C += w0*y2        (epilogue: A + (B + C))
@@ -634,7 +644,8 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
             mbar_expect_tx(bar_y, (uint32_t)(C::YS_F * 4));
             bulk_g2s(R2, L.stash + ((size_t)blockIdx.x * Lh + (l - 1)) * C::STL + C::STL_F, (uint32_t)(C::YS_F * 4), bar_y);
           }
-          if (lane == 0) gemm_wx(C::DGRAD_TWO_LEVEL, C::CONCAT_DGRAD);
+          constexpr bool ILV = (TC_DGRAD_INTERLEAVE != 0) && (C::MB == 2) && (C::KS % 2 == 0);
+          if (lane == 0 && !ILV) gemm_wx(C::DGRAD_TWO_LEVEL, C::CONCAT_DGRAD);
           __syncwarp();
           if (C::MB == 1) {
             if (C::YSIDE) {
@@ -654,14 +665,17 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
           } else {
             // two blocks of input units (the Y block in R2 is recomputed per block) x two blocks of output units;
             // ONE weight-gradient block in TMEM: the epilogue warps drain it between the two output blocks
+            // ILV: the data-gradient GEMM goes to the tensor core in four chunks, one BEHIND each weight-gradient block, so
+            // that the pipe works on a chunk while the epilogue warps drain the block (and recompute the next Y block)
+            // instead of idling through the drain: W(0,0) D.0 | W(1,0) D.1 | W(0,1) D.2 | W(1,1) D.3.
             for (int j = 0; j < C::MB; ++j) {
               tc::named_sync(TC_BAR_OP2, C::NEPI_T + 32);
               umma::fence_after_sync();
-              if (lane == 0) gemm_wgrad(0, 0);
+              if (lane == 0) { gemm_wgrad(0, 0); if (ILV) gemm_wx(C::DGRAD_TWO_LEVEL, C::CONCAT_DGRAD, false, 2 * j, 4); }
               __syncwarp();
               tc::named_sync(TC_BAR_OP3, C::NEPI_T + 32);
               umma::fence_after_sync();
-              if (lane == 0) gemm_wgrad(0, 1);
+              if (lane == 0) { gemm_wgrad(0, 1); if (ILV) gemm_wx(C::DGRAD_TWO_LEVEL, C::CONCAT_DGRAD, false, 2 * j + 1, 4); }
               __syncwarp();
             }
           }
@@ -727,6 +741,14 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
     // every epilogue thread has fenced its additions and passed an epi_sync before thread 0 calls this
     auto token_pass = [&](int e, int round) {
       if (shared_rows && tid == 0) tc::st_release_gpu(tok + e, (unsigned)(round * kcount + mem + 1));
+    };
+    int pending_tok = -1, pending_round = 0;   // layer whose token this CTA still holds (all epilogue threads agree)
+    auto pass_pending = [&]() {
+      if (pending_tok < 0) return;
+      if (shared_rows) __threadfence();
+      epi_sync();
+      token_pass(pending_tok, pending_round);
+      pending_tok = -1;
     };
     const int ldw = L.ldw;
     float wlacc[C::MB], w0acc[C::MB][3], blacc = 0.f;   // this thread's units: u, u + 128 (one per M block)
@@ -1361,7 +1383,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
                 par_w ^= 1;
                 umma::fence_after_sync();
                 lap(5);
-                if (i == 0 && j == 0) token_wait(l, it);
+                if (i == 0 && j == 0) { pass_pending(); token_wait(l, it); }
                 flush_dw(l, 0, i, j);
                 if (i == 0) tc::named_arrive(TC_BAR_OP3, C::NEPI_T + 32);  // block drained: the next one may be issued
                 lap(6);
@@ -1369,6 +1391,7 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
             }
           }
           // ---- bias gradients of layer l: fixed-order fold over the Q point blocks
+          if (l == 0) pass_pending();
           epi_sync();
           if (q == 0) {
 #pragma unroll
@@ -1380,9 +1403,17 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
               gadd(gacc + net.off_b[l] + u + 128 * mb, g);
             }
           }
-          if (shared_rows) __threadfence();   // this thread's additions of layer l are performed
-          epi_sync();
-          token_pass(l, it);
+          // The token of layer l is passed on when this CTA reaches the flush of layer l-1 (pass_pending): by then the
+          // layer's 256 KB of `red` additions have drained and the fence in front of the hand-over costs nothing (an
+          // immediate fence waited ~10 k cycles per layer).  Layer 0 (bias only) hands over at once.
+          if (l == 0) {
+            if (shared_rows) __threadfence();
+            epi_sync();
+            token_pass(0, it);
+          } else {
+            epi_sync();
+            pending_tok = l; pending_round = it;
+          }
         }
       }
     }

@@ -52,6 +52,12 @@
 #ifndef TC_DGRAD_INTERLEAVE
 #define TC_DGRAD_INTERLEAVE 1
 #endif
+// bulk copies per ring stage.  Measured: 3 copies of 4 KB change nothing (C4 19.47 vs 19.56 ms, C5 40.6 vs 40.7), 12 copies of
+// 1 KB cost C5 9 %: the GEMMs do not wait for the copy engine but for shared-memory bandwidth (per k-step the MMAs read
+// ~31 KB of operands and the ring writes 12 KB: ~340 cycles at 128 B/cycle against 412 cycles of MMA issue).
+#ifndef TC_RING_SPLIT
+#define TC_RING_SPLIT 1
+#endif
 #ifndef TC_EXP
 #define TC_EXP 0   // timing experiments (wrong results): 1 no accumulator flush, 2 no B2 stash read, 4 no stash write, 8 no B1 stash read
 #endif
@@ -461,7 +467,10 @@ __global__ void __launch_bounds__(C::NT, 1) jet_tc_kernel(const __grid_constant_
         const int c = (pos < fwd_len) ? (pos / (REP * C::CHUNKS)) * C::CHUNKS + pos % C::CHUNKS : NG * C::CHUNKS + (pos - fwd_len);
         if (round > 0) tc::wait_bar(&bar_empty[s], (round - 1) & 1);
         mbar_expect_tx(&bar_full[s], C::SLOT);
-        bulk_g2s(ring + s * C::SLOT, img + (size_t)c * C::SLOT, C::SLOT, &bar_full[s]);
+#pragma unroll
+        for (int part = 0; part < TC_RING_SPLIT; ++part)   // (several smaller bulk copies per stage: more copies in flight)
+          bulk_g2s(ring + s * C::SLOT + part * (C::SLOT / TC_RING_SPLIT), img + (size_t)c * C::SLOT + part * (C::SLOT / TC_RING_SPLIT),
+                   C::SLOT / TC_RING_SPLIT, &bar_full[s]);
         if (TRAIN && c >= NG * C::CHUNKS && c % C::CHUNKS == 0 && !(PROF && (L.exp_flags & 4))) {
           // first stage of dgrad(l): pull what the epilogue warps touch one layer later into L2 -- the stash of layer
           // l-1 (B2(l), B1(l-1)) and the accumulator block of layer l (flushed during iteration l-1).  The per-CTA

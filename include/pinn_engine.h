@@ -86,9 +86,10 @@ int32_t pinn_engine_launches_per_eval(pinn_engine_t* h);
 /* kernels one Adam step of pinn_engine_adam_steps enqueues (evaluation kernels + the fused reduce / loss_info / Adam /
  * re-pack tail; PINN_B200_FUSED_TAIL=0 restores the separate kernels) */
 int32_t pinn_engine_launches_per_adam_step(pinn_engine_t* h);
-/* kernel family chosen at create: 0 = fp32 SIMT (packed FFMA2), 1 = 3xTF32 mma.sync tensor-core kernel.
- * Selection: environment PINN_B200_KERNEL = simt | mma | auto (auto: tensor-core kernel for padded
- * widths 64, 128 and 256, fp32 kernel for 32). */
+/* kernel family chosen at create: 0 = fp32 SIMT (packed FFMA2), 1 = split-precision mma.sync tensor-core kernel,
+ * 2 = experimental tcgen05 family C (opt-in), 3 = tcgen05 family D (bf16x3 split, accumulators in Tensor Memory).
+ * Selection: environment PINN_B200_KERNEL = simt | mma | tc | umma | auto (auto: family D for padded widths 128 and
+ * 256 with at least three jet channels, the mma.sync kernel for padded width 64, the fp32 kernel for 32). */
 int32_t pinn_engine_kernel_kind(pinn_engine_t* h);
 
 /* params pytree <-> flat fp32 vector (sw:142-154 layout, sw:466 order) */

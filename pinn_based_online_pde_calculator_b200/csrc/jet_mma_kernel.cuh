@@ -32,7 +32,17 @@ struct MmaCfg {
   static constexpr int ROWS = TP / 2;           // thread rows (mw, g)
   static constexpr int SP = K * WP + 8;         // smem point stride == 8 (mod 32)
   static constexpr int WPS = WP + 8;            // weight row stride (smem chunk and pack)
-  static constexpr int KC = (NT <= 64) ? 16 : (K >= 6) ? (WP <= 64 ? 16 : 8) : (WP <= 64 ? (K <= 4 ? 64 : 32) : (WP <= 128 && K <= 4) ? 32 : 16);  // W = 128, K <= 4: 32 keeps 2 CTAs/SM (101 KB); W = 256, K <= 5: 16 fits (199 KB)
+  // Experiment knobs (padded width 64).  Three CTAs per SM -- 8-row weight chunks (73 KB of shared memory) and a 168-register
+  // cap, 12 instead of 8 warps per SM -- measured SLOWER on every width-64 workload: C2 6.00 -> 7.20 ms, C3 54.1 -> 65.2 ms,
+  // R0 99.6 -> 148.5 us (the eight mbarrier round trips per weight matrix and the register cap cost more than the extra
+  // warps hide).
+#ifndef PINN_MMA_KC
+#define PINN_MMA_KC 0       // weight rows per chunk (0 = the tuned table below)
+#endif
+#ifndef PINN_MMA_REGCAP
+#define PINN_MMA_REGCAP 256 // registers per thread the occupancy target assumes
+#endif
+  static constexpr int KC = (PINN_MMA_KC > 0 && WP_ == 64) ? PINN_MMA_KC : (NT <= 64) ? 16 : (K >= 6) ? (WP <= 64 ? 16 : 8) : (WP <= 64 ? (K <= 4 ? 64 : 32) : (WP <= 128 && K <= 4) ? 32 : 16);  // W = 128, K <= 4: 32 keeps 2 CTAs/SM (101 KB); W = 256, K <= 5: 16 fits (199 KB)
   static constexpr int NCH = WP / KC;
   static constexpr uint32_t CHUNK_BYTES = KC * WPS * 4;
   static constexpr int SCR_HALF = ((5 * ROWS * WP + ROWS + 1) / 2 + 3) / 4 * 4;  // final-fold scratch / 2
@@ -56,7 +66,7 @@ struct MmaCfg {
   static constexpr bool USE_TMEM = (PINN_TMEM_STASH != 0) && (NT == 128);
   static constexpr int TMEM_LAYERS = PINN_TMEM_COLS / (16 * K);
   static constexpr int MINB_S = (int)(232448 / (smem_bytes(true) + 1024));            // smem-limited CTAs per SM
-  static constexpr int MINB_R = 65536 / (NT * 256);                                     // at 255 registers per thread
+  static constexpr int MINB_R = 65536 / (NT * (WP_ == 64 ? PINN_MMA_REGCAP : 256));      // at 255 registers per thread
   static constexpr int MINB_U = MINB_S < 1 ? 1 : (MINB_S < MINB_R ? MINB_S : MINB_R);
   static constexpr int MINB = (USE_TMEM && MINB_U > 2) ? 2 : MINB_U;   // resident CTAs per SM (2 x 256 TMEM columns)
 };

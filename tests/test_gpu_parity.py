@@ -147,6 +147,10 @@ def test_shared_accumulator_rows_are_bit_reproducible_and_match_private_rows(mon
     for share in ("4", "3"):
         assert rel_err(grads[share][0], grads["1"][0]) < 2e-6, rel_err(grads[share][0], grads["1"][0])
         assert np.allclose(grads[share][1], grads["1"][1], rtol=1e-12, atol=0)   # the loss sums never were shared
+    # ... and the production configuration (four CTAs per row) against the float64 oracle on the same 5,333 points
+    g_ref, info_ref, _, _ = oracle_loss_grad(pb, lref=1.0)
+    assert np.allclose(grads["4"][1], info_ref, rtol=TOL, atol=0), (grads["4"][1], info_ref)
+    assert rel_err(grads["4"][0], g_ref) < TOL, rel_err(grads["4"][0], g_ref)
 
 
 @pytest.mark.gpu

@@ -296,9 +296,9 @@ static int create_impl(pinn_engine* h, const pinn_spec_t* spec, int device) {
   cudaError_t e = h->kcol->prepare(&occ_col);
   if (e == cudaSuccess) e = h->kbc->prepare(&occ_bc);
   if (e != cudaSuccess) { return fail("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); }
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
-  h->num_sms = prop.multiProcessorCount;
+  // (cudaDeviceGetAttribute, not cudaGetDeviceProperties: the latter takes tens of milliseconds per call, and the
+  // reference's call site creates two engines per training run)
+  CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
   h->grid_max_col = h->num_sms * occ_col;
   if (const char* g = getenv("PINN_TC_GRID")) {  // experiment knob: cap the collocation grid of the tcgen05 family
     if (h->kcol->kind == 3 && atoi(g) > 0) h->grid_max_col = std::min(h->grid_max_col, atoi(g));
@@ -478,8 +478,13 @@ static void l2_release(pinn_engine* h) {
   if (had) l2_set_limit_locked(h->device);
 }
 static void apply_l2_policy(pinn_engine* h) {
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return;
+  struct { int persistingL2CacheMaxSize = 0, accessPolicyMaxWindowSize = 0, l2CacheSize = 0; } prop;
+  if (cudaDeviceGetAttribute(&prop.persistingL2CacheMaxSize, cudaDevAttrMaxPersistingL2CacheSize, h->device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&prop.accessPolicyMaxWindowSize, cudaDevAttrMaxAccessPolicyWindowSize, h->device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&prop.l2CacheSize, cudaDevAttrL2CacheSize, h->device) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
   if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
   // what the window covers: the whole per-CTA scratch [stash | gradient accumulators] (default), or only one of
   // the two regions (PINN_B200_L2_WINDOW = both | gacc | stash; experiment knob for scratch sets near the L2 size)

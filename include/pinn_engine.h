@@ -133,6 +133,10 @@ int pinn_engine_loss_grad(pinn_engine_t* h, const float* params_dev, float* grad
  * m, v, count are kept (sw:439-440). */
 int pinn_engine_adam_init(pinn_engine_t* h);
 int pinn_engine_adam_steps(pinn_engine_t* h, int32_t n_steps, double lr, double* loss_rows_host);
+/* The loss_info rows of the LAST pinn_engine_adam_steps call (n_rows <= min(its n_steps, 4096)), with the host
+ * synchronisation that call skipped when it was given loss_rows_host == NULL: the host can prepare the next
+ * collocation set (sw:416-422) while the steps run and collect the rows for logging (sw:418-419, 425) afterwards. */
+int pinn_engine_adam_rows(pinn_engine_t* h, int32_t n_rows, double* loss_rows_host);
 
 /* f_u (sw:213) and gov_eqn (sw:283) without parameter gradient (sw:608-616, 766-770).
  * Outputs may be NULL. jets_out: [n,K]. */

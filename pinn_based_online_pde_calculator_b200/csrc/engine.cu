@@ -988,6 +988,14 @@ extern "C" int pinn_engine_adam_steps(pinn_engine_t* h, int32_t n_steps, double 
   return 0;
 }
 
+extern "C" int pinn_engine_adam_rows(pinn_engine_t* h, int32_t n_rows, double* rows) {
+  CK(cudaSetDevice(h->device));
+  if (!rows || n_rows <= 0 || n_rows > h->ring_cap) return fail("adam_rows: n_rows must be 1..%d", h->ring_cap);
+  CK(cudaMemcpyAsync(rows, h->d_ring, sizeof(double) * (size_t)n_rows * h->n_info, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 extern "C" double pinn_engine_last_ms(pinn_engine_t* h) {
   if (!h->timed) return -1.0;
   cudaSetDevice(h->device);

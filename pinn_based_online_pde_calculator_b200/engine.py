@@ -30,7 +30,7 @@ EXPORTS = [
     "pinn_engine_set_stream", "pinn_engine_num_params", "pinn_engine_num_loss_info",
     "pinn_engine_tile_points", "pinn_engine_launches_per_eval", "pinn_engine_launches_per_adam_step", "pinn_engine_set_params",
     "pinn_engine_get_params", "pinn_engine_set_points", "pinn_engine_set_global_counts",
-    "pinn_engine_set_loss", "pinn_engine_loss_grad", "pinn_engine_adam_init", "pinn_engine_adam_steps",
+    "pinn_engine_set_loss", "pinn_engine_loss_grad", "pinn_engine_adam_init", "pinn_engine_adam_steps", "pinn_engine_adam_rows",
     "pinn_engine_eval", "pinn_engine_lbfgs", "pinn_nccl_unique_id", "pinn_engine_init_nccl",
     "pinn_fma_peak", "pinn_engine_last_ms", "pinn_engine_time_kernels", "pinn_engine_kernel_kind", "pinn_engine_phase_profile", "pinn_sample_lhs", "pinn_sample_cdf2d", "pinn_engine_sync", "pinn_umma_probe", "pinn_engine_prefetch_points", "pinn_engine_commit_points", "pinn_engine_umma_clocks", "pinn_lbfgs_direction_test",
     "pinn_engine_lbfgs_trace", "pinn_engine_lbfgs_trace_rows", "pinn_engine_lbfgs_trace_get", "pinn_engine_lbfgs_host_syncs",
@@ -99,6 +99,7 @@ def load_library(path: Optional[str] = None):
     lib.pinn_engine_loss_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pinn_engine_adam_init.argtypes = [C.c_void_p]
     lib.pinn_engine_adam_steps.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_void_p]
+    lib.pinn_engine_adam_rows.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.pinn_engine_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_int]
     lib.pinn_engine_lbfgs.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_int32, EVAL_CB, C.c_void_p,
@@ -349,6 +350,22 @@ class PinnEngine:
     def adam_steps(self, n_steps: int, lr: float, want_rows: bool = True) -> Optional[np.ndarray]:
         rows = np.empty((n_steps, self.n_info), dtype=np.float64) if want_rows else None
         _check(self.lib, self.lib.pinn_engine_adam_steps(self.h, int(n_steps), float(lr), _ptr(rows)))
+        return rows
+
+    RING_CAP = 4096
+
+    def adam_steps_begin(self, n_steps: int, lr: float) -> bool:
+        """Enqueue n_steps Adam steps WITHOUT waiting for them (software.py:416-425: the caller samples the next collocation
+        set meanwhile) -- False when the rows would not fit the device ring (use adam_steps then)."""
+        if n_steps > self.RING_CAP:
+            return False
+        _check(self.lib, self.lib.pinn_engine_adam_steps(self.h, int(n_steps), float(lr), None))
+        return True
+
+    def adam_steps_end(self, n_steps: int) -> np.ndarray:
+        """loss_info rows of the steps adam_steps_begin enqueued (synchronises)."""
+        rows = np.empty((n_steps, self.n_info), dtype=np.float64)
+        _check(self.lib, self.lib.pinn_engine_adam_rows(self.h, int(n_steps), _ptr(rows)))
         return rows
 
     def launches_per_eval(self) -> int:

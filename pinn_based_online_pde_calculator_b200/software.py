@@ -226,14 +226,24 @@ def adam_optimizer(R_add, T_add, model: Model, dataf, F, epoch: int, key_adam: K
         c1 = ((step + 99) // 100) * 100 or 100          # s % 100 == 0 and s > 0
         c2 = ((step + nc0) // nc0) * nc0 - 1            # (s + 1) % nc0 == 0
         nxt = min(c1, c2, epoch - 1)
-        rows = eng.adam_steps(nxt - step + 1, lr)
+        s = nxt
+        resample = s % 100 == 0 and s > 0
+        # The steps are enqueued without waiting; the host samples the NEXT collocation set (sw:420-422: it depends on
+        # the key and on F, which only changes at the predictF boundaries that end their own chunk) while they run.
+        begun = getattr(eng, "adam_steps_begin", None) is not None and eng.adam_steps_begin(nxt - step + 1, lr)
+        next_data = None
+        if begun and resample:
+            key = key.split(1)[0]
+            next_data = dataf(key, F, R_add, T_add)
+        rows = eng.adam_steps_end(nxt - step + 1) if begun else eng.adam_steps(nxt - step + 1, lr)
         loss_all.extend(rows)
         info = rows[-1]
-        s = nxt
-        if s % 100 == 0 and s > 0:
+        if resample:
             print(_log_line(s, info), file=sys.stderr)
-            key = key.split(1)[0]
-            model.set_data(dataf(key, F, R_add, T_add))
+            if next_data is None:
+                key = key.split(1)[0]
+                next_data = dataf(key, F, R_add, T_add)
+            model.set_data(next_data)
         if (s + 1) % nc0 == 0:
             F = predictF(model, R, T)
         if (s + 1) % (2 * nc0) == 0:

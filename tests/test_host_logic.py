@@ -155,6 +155,49 @@ def test_adam_schedule_events(capsys):
     assert len(loss) >= 4100
 
 
+class _FakeAsyncEngine(_FakeEngine):
+    """An engine with the non-blocking pair adam_steps_begin / adam_steps_end: records what the host does in between."""
+
+    def adam_steps_begin(self, n, lr):
+        self.calls.append(("begin", n, lr))
+        self.in_flight = True
+        return True
+
+    def adam_steps_end(self, n):
+        self.calls.append(("end", n))
+        self.in_flight = False
+        return _FakeEngine.adam_steps(self, n, 0.0)[:n]
+
+
+def test_adam_schedule_samples_the_next_set_while_the_steps_run(capsys):
+    """Same events, same key sequence and the same number of resamples as the blocking schedule; every resample of the
+    Adam loop is computed while the enqueued steps are in flight (software.py:416-422)."""
+    seen = {"blocking": [], "async": []}
+
+    def run(engine, tag):
+        m = _FakeModel()
+        m.engine = engine
+
+        def dataf(key, F, R, T):
+            seen[tag].append(((key.ss.entropy, tuple(key.ss.spawn_key)), getattr(engine, "in_flight", False)))
+            return {}
+
+        dataf.R, dataf.T = np.zeros((4, 4)), np.zeros((4, 4))
+        loss = sw.adam_optimizer(dataf.R, dataf.T, m, dataf, np.ones((4, 4)), 2100, sw.Key(0), lr=1e-3)
+        return m, loss
+
+    m0, l0 = run(_FakeEngine(), "blocking")
+    m1, l1 = run(_FakeAsyncEngine(), "async")
+    capsys.readouterr()
+    assert m0.n_set == m1.n_set == 1 + 20
+    assert [k for k, _ in seen["blocking"]] == [k for k, _ in seen["async"]]      # identical key sequence
+    assert not any(f for _, f in seen["blocking"])
+    assert all(f for _, f in seen["async"][1:]) and not seen["async"][0][1]        # all but the initial set: overlapped
+    assert np.array_equal(np.array(l0)[:, 0], np.array(l1)[:, 0])
+    begins = [c for c in m1.engine.calls if c[0] == "begin"]
+    assert sum(c[1] for c in begins) >= 2100
+
+
 def test_equation_front_end_never_raises_for_ui_input():
     """The reference ignores `equation` (software.py:627): None (an untouched Dash input), non-strings and
     expressions whose constants fold out of the reals must fall back to the polar Laplacian instead of

@@ -28,6 +28,26 @@ def timed(self, n_steps, lr, want_rows=True):
 
 
 E.PinnEngine.adam_steps = timed
+orig_begin, orig_end = E.PinnEngine.adam_steps_begin, E.PinnEngine.adam_steps_end
+t_begin = {}
+
+
+def timed_begin(self, n_steps, lr):
+    t_begin[id(self)] = time.perf_counter()
+    return orig_begin(self, n_steps, lr)
+
+
+def timed_end(self, n_steps):
+    r = orig_end(self, n_steps)
+    s = stats[id(self)]
+    s[0] += n_steps
+    s[1] += time.perf_counter() - t_begin[id(self)]   # wall from the enqueue to the rows (host sampling overlaps inside)
+    s[2] += self.last_ms() * 1e-3
+    s[3] += 1
+    return r
+
+
+E.PinnEngine.adam_steps_begin, E.PinnEngine.adam_steps_end = timed_begin, timed_end
 with tempfile.TemporaryDirectory() as d:
     run_pinn_training(**KW, epochs={"adam": 10, "lbfgs": 5}, output_dir=d + "/warm")  # library load, first launches
     stats.clear()

@@ -749,6 +749,16 @@ extern "C" int pinn_engine_set_points(pinn_engine_t* h, const float* x_col, int6
     // collocation CTAs'.  Otherwise the two persistent grids would only fight for the same CTA slots: they
     // run back to back and share rows (fewer rows to zero and reduce).
     h->fork_bc = tiles > 0 && h->grid_col + h->grid_bc <= h->grid_max;  // both grids fit next to each other (rows and CTA slots)
+    // A FEW boundary tiles next to a collocation grid that fills every slot (the reference's stage 2: 10,400 + 400 points
+    // = 326 + 13 tiles on 296 slots): the boundary kernel's single-tile latency (43 us) would be serial time in front of
+    // a 190 us collocation kernel.  Give it its own CTAs instead -- the collocation grid shrinks by as many (it needs a
+    // second round either way) -- and run the two side by side.  Not for the tcgen05 family (one 221 KB CTA per SM
+    // leaves no room for a neighbour) and not for large boundary sets (measured slower on C2).
+    if (!h->fork_bc && tiles > 0 && h->kcol->kind != 3 && h->grid_bc <= h->grid_max / 16 && h->grid_col > 2 * h->grid_bc &&
+        !getenv("PINN_B200_NO_SMALL_FORK")) {
+      h->grid_col = std::min(h->grid_col, h->grid_max - h->grid_bc);
+      h->fork_bc = true;
+    }
     if (h->fork_bc) {
       const size_t stash_row = (size_t)h->spec.n_hidden * std::max(h->kcol->stash_floats_per_layer, h->kbc->stash_floats_per_layer);
       L.stash = h->d_stash + (size_t)h->grid_col * stash_row;

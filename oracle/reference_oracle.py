@@ -14,20 +14,24 @@ written with ``torch.func.{vjp,vmap,grad}`` so that the nested reverse-mode
 structure of the JAX original (``jax.vjp`` / ``jax.vmap`` / ``jax.grad``) is
 kept call for call, in float64 (the reference enables x64 at software.py:18).
 
-PARITY UNPINNED (third-party arithmetic):
-  * the reference ships no tests, golden vectors or known-answer fixtures
-    (SURVEY.md section 4), and jax / optax / tensorflow_probability / pyDOE are
-    not installable here, so this oracle cannot be checked against outputs of
-    the reference itself.  It is pinned instead by (i) the analytic solution
-    the reference hard-codes at software.py:815 (u* = ln r / ln 0.1 has zero
-    polar-Laplace residual), (ii) an independent closed-form forward-jet
-    propagation (``jet_forward_closed_form`` below) that must agree with the
-    nested-vjp residual to ~1e-14, and (iii) central finite differences of the
-    loss.  tests/test_oracle.py runs all three and the committed golden vectors.
-  * jax.random (threefry) streams cannot be reproduced: initial weights and
-    sample points are always passed in as explicit arrays.
-  * optax.adam is restated from its published update rule
-    (b1=0.9, b2=0.999, eps=1e-8, eps_root=0, bias-corrected).
+PINNED AGAINST THE REFERENCE'S OWN SOURCE TEXT (network, derivatives, residual, loss, gradient, stage 2):
+  * jax / optax / tensorflow_probability / pyDOE are not installable here, so the reference MODULE cannot be imported
+    and it ships no tests or golden vectors.  Its function bodies can be run, though:
+    tests/golden/gen_reference_shim_golden.py lifts neural_net, sol_pred_create, mNN_pred_create, ms_error, vgmat,
+    vectgrad, gov_eqn and loss_create (software.py:158-383) out of the file with ``ast`` and executes them with the jax
+    names they use bound to float64 torch equivalents (two jax-only method idioms rewritten mechanically, listed in that
+    script).  tests/test_oracle.py checks this oracle against those outputs to float64 round-off (u, du/dz, f, loss_info,
+    d(loss/lref)/dparams, stage-2 u and f) and tests/test_gpu_parity.py checks the CUDA engine against them at 1e-5.
+  * further pins: (i) the analytic solution the reference hard-codes at software.py:815 (u* = ln r / ln 0.1 has zero
+    polar-Laplace residual), (ii) an independent closed-form forward-jet propagation (``jet_forward_closed_form``
+    below) that agrees with the nested-vjp residual to ~1e-14, (iii) central finite differences of the loss.
+
+PARITY UNPINNED (third-party arithmetic only):
+  * jax.random (threefry) streams cannot be reproduced: initial weights and sample points are always passed in as
+    explicit arrays.
+  * optax.adam is restated from its published update rule (b1=0.9, b2=0.999, eps=1e-8, eps_root=0, bias-corrected) and
+    checked against torch.optim.Adam; tfp's L-BFGS / Hager-Zhang line search is restated from the paper and checked
+    against scipy's L-BFGS-B (final solutions, not iterates).
 
 Generalisations beyond the reference (needed by BASELINE.json configs C1..C5,
 see SURVEY.md section 8d) are opt-in keyword arguments whose defaults reproduce

@@ -110,6 +110,37 @@ def test_literal_baseline_workloads_match_oracle(name, n_col, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", ["smoke_6x60", "sin_3x24"])
+def test_engine_matches_the_reference_source_executed_on_a_jax_shim(case):
+    """The CUDA engine against numbers the REFERENCE'S OWN source text produced (software.py:158-383 lifted with ast and
+    executed on a float64 torch shim of the jax calls it makes: tests/golden/gen_reference_shim_golden.py) -- not against
+    the oracle: loss_info, the gradient of loss / lref in ravel_pytree order, u and the polar-Laplace residual."""
+    import os
+
+    from pinn_based_online_pde_calculator_b200 import NetworkSpec, PinnEngine, compile_equation
+    from pinn_based_online_pde_calculator_b200.equation import REFERENCE_POLAR_LAPLACE
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"reference_source_{case}.npz"))
+    n = int(z["n_layers"])
+    net = NetworkSpec(n_hidden=n - 1, width=int(z["W0"].shape[1]), lb=[0.1, 0.0], ub=[1.0, 1.0], scl=float(z["scl"]),
+                      epsil=float(z["epsil"]), act_first=int(z["act_s"]), feature_map="polar", d_in=2)
+    eq = compile_equation(REFERENCE_POLAR_LAPLACE, d_in=2)
+    eng = PinnEngine(net, eq, n_bc=2)
+    flat = np.concatenate([np.concatenate([z[f"W{i}"].ravel(), z[f"b{i}"].ravel()]) for i in range(n)]).astype(np.float32)
+    g_ref = np.concatenate([np.concatenate([z[f"gW{i}"].ravel(), z[f"gb{i}"].ravel()]) for i in range(n)])
+    eng.set_params(flat)
+    eng.set_points(z["x_col"].astype(np.float32), [z["x_bd0"].astype(np.float32), z["x_bd1"].astype(np.float32)],
+                   [z["u_bd0"].astype(np.float32), z["u_bd1"].astype(np.float32)])
+    eng.set_loss(float(z["lw0"]), float(z["lref"]))
+    g, info = eng.loss_grad()
+    assert np.allclose(info, z["loss_info"], rtol=TOL, atol=0), (info, z["loss_info"])
+    assert rel_err(g.cpu().numpy(), g_ref) < TOL, rel_err(g.cpu().numpy(), g_ref)
+    u, f, _ = eng.eval(z["x_col"].astype(np.float32))
+    assert rel_err(u, z["u"][:, 0]) < TOL and rel_err(f, z["f"][:, 0]) < TOL, (rel_err(u, z["u"][:, 0]), rel_err(f, z["f"][:, 0]))
+    eng.close()
+
+
+@pytest.mark.gpu
 def test_gradient_parity_on_a_131072_point_slice_of_c2():
     """gradient parity at (near) full size, not only on a few thousand points."""
     from tests.helpers import problem_from_workload

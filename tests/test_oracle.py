@@ -1,7 +1,8 @@
 """Pins for the float64 oracle (oracle/reference_oracle.py).  The reference ships no
 tests or golden vectors, so the restatement is pinned by:
-the analytic solution hard-coded at software.py:815, an independent closed-form jet
-propagation, finite differences, torch.optim.Adam, and the committed fixtures."""
+OUTPUTS OF THE REFERENCE'S OWN FUNCTION BODIES (software.py:158-383, executed on a torch shim of the jax calls they
+make: tests/golden/gen_reference_shim_golden.py), the analytic solution hard-coded at software.py:815, an independent
+closed-form jet propagation, finite differences, torch.optim.Adam, and the committed fixtures."""
 import glob
 import math
 import os
@@ -148,3 +149,44 @@ def test_oracle_reproduces_committed_golden_vectors(path):
     assert np.allclose(info, z["loss_info"], rtol=1e-12)
     assert rel_err(g, z["grad"]) < 1e-6  # fixture gradients are stored in fp32
     assert np.array_equal(O.ravel_params(pb["params"]).numpy().astype(np.float32), z["params"])
+
+
+def _load_reference_source_case(path):
+    z = np.load(path)
+    t = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)
+    n = int(z["n_layers"])
+    params = [[t(z[f"W{i}"]), t(z[f"b{i}"])] for i in range(n)]
+    params2 = [[t(z[f"W2_{i}"]), t(z[f"b2_{i}"])] for i in range(n)]
+    grads = [[t(z[f"gW{i}"]), t(z[f"gb{i}"])] for i in range(n)]
+    x_bd = [t(z[f"x_bd{i}"]) for i in range(2)]
+    u_bd = [t(z[f"u_bd{i}"]) for i in range(2)]
+    limit = [torch.tensor([0.1, 0.0], dtype=torch.float64), torch.tensor([1.0, 1.0], dtype=torch.float64)]
+    return z, params, params2, grads, t(z["x_col"]), x_bd, u_bd, limit
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "reference_source_*.npz"))))
+def test_oracle_matches_the_reference_source_executed_on_a_jax_shim(path):
+    """The numbers in tests/golden/reference_source_*.npz were produced by the REFERENCE'S OWN source text -- neural_net,
+    sol_pred_create, mNN_pred_create, ms_error, vgmat, vectgrad, gov_eqn, loss_create (software.py:158-383), lifted with ast
+    and executed with the jax names they use bound to float64 torch equivalents (gen_reference_shim_golden.py).  The
+    oracle restates those functions; it must reproduce every output to float64 round-off."""
+    z, params, params2, grads, x_col, x_bd, u_bd, limit = _load_reference_source_case(path)
+    scl, epsil, act_s = float(z["scl"]), float(z["epsil"]), int(z["act_s"])
+    f_u = O.sol_pred_create(limit, scl, epsil, act_s=act_s)
+    fz = lambda zz: f_u(params, zz)
+    tol = dict(rtol=1e-11, atol=1e-12)
+    assert np.allclose(fz(x_col).numpy(), z["u"], **tol)
+    assert np.allclose(O.vectgrad(fz, x_col)[0].numpy(), z["u_grad"], **tol)
+    f_ref = z["f"]
+    assert np.allclose(O.gov_eqn(fz, x_col).numpy(), f_ref, rtol=1e-9, atol=1e-9 * np.abs(f_ref).max())
+    lossf = O.loss_create(f_u, torch.tensor([float(z["lw0"]), 0.0], dtype=torch.float64), float(z["lref"]))
+    data = dict(x_col=x_col, cond_bd=[x_bd, u_bd])
+    loss_n, info = lossf(params, data)
+    assert np.allclose(info.numpy(), z["loss_info"], rtol=1e-10, atol=0) and abs(float(loss_n) / float(z["loss_n"]) - 1) < 1e-10
+    g, _ = O.loss_and_grad(lossf, params, data)
+    assert rel_err(O.ravel_params(g).numpy(), O.ravel_params(grads).numpy()) < 1e-10
+    # stage 2 (software.py:221-234)
+    f_comb = O.mNN_pred_create(fz, limit, 2.0 * scl, 0.1 * epsil, act_s=1)
+    assert np.allclose(f_comb(params2, x_col).numpy(), z["u_stage2"], **tol)
+    f2 = O.gov_eqn(lambda zz: f_comb(params2, zz), x_col).numpy()
+    assert np.allclose(f2, z["f_stage2"], rtol=1e-9, atol=1e-9 * np.abs(z["f_stage2"]).max())

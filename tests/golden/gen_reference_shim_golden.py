@@ -1,9 +1,10 @@
 """Generate tests/golden/reference_source_*.npz by EXECUTING THE REFERENCE'S OWN FUNCTION BODIES
 (pinn_app/software.py: neural_net 158-184, sol_pred_create 207-218, mNN_pred_create 221-234, ms_error 241-242,
-vgmat 246-264, vectgrad 268-279, gov_eqn 283-297, loss_create / loss_fun 310-383) on seeded float64 inputs.
+vgmat 246-264, vectgrad 268-279, gov_eqn 283-297, loss_create / loss_fun 310-383, lbfgs_function 464-496 (the value /
+gradient closure tfp's L-BFGS calls), predictF 608-623 with gaussian2D_smooth 71-83) on seeded float64 inputs.
 
 jax, optax and tensorflow_probability cannot be installed here, so the reference module cannot be imported.  Its
-source text CAN be run: the eight functions are lifted out of the file with ``ast`` (as gen_validator_golden.py does for
+source text CAN be run: the functions are lifted out of the file with ``ast`` (as gen_validator_golden.py does for
 the validator) and executed in a namespace where the ~15 names of the jax API they touch are bound to the float64
 torch equivalents (``jnp.tanh -> torch.tanh``, ``vjp -> torch.func.vjp``, ``vmap(f, in_axes=0) -> torch.func.vmap(f,
 in_dims=0)``, ``grad(f, has_aux=True) -> torch.func.grad(f, has_aux=True)`` ...).  Two jax-only METHOD idioms have no
@@ -24,7 +25,8 @@ import torch
 
 REF = "/root/reference/pinn_app/software.py"
 OUT_DIR = os.path.dirname(os.path.abspath(__file__))
-WANT = ["neural_net", "sol_pred_create", "mNN_pred_create", "ms_error", "vgmat", "vectgrad", "gov_eqn", "loss_create"]
+WANT = ["neural_net", "sol_pred_create", "mNN_pred_create", "ms_error", "vgmat", "vectgrad", "gov_eqn", "loss_create",
+        "lbfgs_function", "predictF"]          # + gaussian2D_smooth (sw:71-83), executed on numpy / scipy (see below)
 
 
 class _Idioms(ast.NodeTransformer):
@@ -78,6 +80,39 @@ def load_reference_functions():
     ns = {"jnp": jnp, "vjp": torch.func.vjp, "vmap": lambda f, in_axes=0: torch.func.vmap(f, in_dims=in_axes),
           "grad": lambda f, has_aux=False: torch.func.grad(f, has_aux=has_aux), "_at_set": _at_set, "slice": slice, "range": range,
           "len": len, "zip": zip}
+    # lbfgs_function: ravel_pytree, @jit and jax.debug.callback (sw:466-488)
+    def ravel_pytree(tree_):
+        leaves = [t for pair in tree_ for t in pair]
+        shapes = [t.shape for t in leaves]
+        flat = torch.cat([t.reshape(-1) for t in leaves])
+
+        def unflat(v):
+            out, o = [], 0
+            for i in range(0, len(shapes), 2):
+                pair = []
+                for sh in shapes[i:i + 2]:
+                    n = int(np.prod(sh))
+                    pair.append(v[o:o + n].reshape(sh))
+                    o += n
+                out.append(pair)
+            return out
+
+        return flat, unflat
+
+    ns["flat_utl"] = types.SimpleNamespace(ravel_pytree=ravel_pytree)
+    ns["jit"] = lambda f: f
+    ns["jax"] = types.SimpleNamespace(debug=types.SimpleNamespace(callback=lambda fn, x: fn(x.detach())))
+    ns["print"] = lambda *a, **k: None
+    # gaussian2D_smooth (sw:71-83) only builds a window and calls scipy.signal.convolve2d: run it on numpy / scipy.stats
+    import scipy
+    import scipy.signal
+    import scipy.stats
+    g2 = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "gaussian2D_smooth"]
+    ns_np = {"jnp": types.SimpleNamespace(int32=np.int32, linspace=np.linspace, sum=np.sum), "scipy": scipy,
+             "jsp": types.SimpleNamespace(stats=scipy.stats)}
+    exec(compile(ast.fix_missing_locations(ast.Module(body=g2, type_ignores=[])), REF, "exec"), ns_np)
+    ns["gaussian2D_smooth"] = lambda F, sig, wid: ns_np["gaussian2D_smooth"](np.asarray(F.detach() if isinstance(F, torch.Tensor) else F), sig, wid)
+    jnp.reshape = lambda x, shape: torch.reshape(x, tuple(shape))
     mod = ast.Module(body=body, type_ignores=[])
     exec(compile(ast.fix_missing_locations(mod), REF, "exec"), ns)
     return ns
@@ -121,7 +156,17 @@ def run_case(ns, name, **kw):
     f_comb = ns["mNN_pred_create"](fz, limit, 2.0 * c["scl"], 0.1 * c["epsil"], 1)
     u2 = f_comb(params2, x_col)
     f2 = ns["gov_eqn"](lambda z: f_comb(params2, z), x_col)
-    out = dict(n_layers=len(params), x_col=x_col.numpy(), u=u.numpy(), u_grad=ug.numpy(), f=f.numpy(), loss_n=float(loss_n),
+    # the closure tfp.optimizer.lbfgs_minimize evaluates (sw:464-496): UN-normalised value, gradient of loss / lref
+    flat = torch.cat([t.reshape(-1) for pair in params for t in pair])
+    fl = ns["lbfgs_function"](lossf, params, data)
+    lb_value, lb_grad = fl(flat)
+    # predictF (sw:608-623): residual-based sampling weight on a grid, smoothed by the 5x5 Gaussian window
+    r = torch.linspace(0.1, 1.0, 23, dtype=torch.float64)
+    t_ = torch.linspace(0.0, 1.0, 19, dtype=torch.float64)
+    Rg, Tg = torch.meshgrid(r, t_, indexing="xy")
+    Fs = ns["predictF"](f_u, params, Rg, Tg)
+    out = dict(lbfgs_value=float(lb_value), lbfgs_grad=lb_grad.numpy(), grid_r=r.numpy(), grid_t=t_.numpy(), predictF=np.asarray(Fs),
+               n_layers=len(params), x_col=x_col.numpy(), u=u.numpy(), u_grad=ug.numpy(), f=f.numpy(), loss_n=float(loss_n),
                loss_info=loss_info.numpy(), u_stage2=u2.numpy(), f_stage2=f2.numpy(), **{k: np.float64(v) for k, v in c.items()})
     for i, ((W, b), (gW, gb), (W2, b2)) in enumerate(zip(params, grads, params2)):
         out[f"W{i}"], out[f"b{i}"], out[f"gW{i}"], out[f"gb{i}"], out[f"W2_{i}"], out[f"b2_{i}"] = (

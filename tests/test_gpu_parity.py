@@ -137,6 +137,17 @@ def test_engine_matches_the_reference_source_executed_on_a_jax_shim(case):
     assert rel_err(g.cpu().numpy(), g_ref) < TOL, rel_err(g.cpu().numpy(), g_ref)
     u, f, _ = eng.eval(z["x_col"].astype(np.float32))
     assert rel_err(u, z["u"][:, 0]) < TOL and rel_err(f, z["f"][:, 0]) < TOL, (rel_err(u, z["u"][:, 0]), rel_err(f, z["f"][:, 0]))
+    # predictF (software.py:608-623, gaussian2D_smooth 71-83) through the product's host code + the eval kernel
+    from pinn_based_online_pde_calculator_b200 import software as sw
+
+    class _M:   # the one method software.predictF needs from its model
+        @staticmethod
+        def predict(zs, want_jets=False):
+            return eng.eval(np.ascontiguousarray(zs, dtype=np.float32))
+
+    Rg, Tg = np.meshgrid(z["grid_r"], z["grid_t"], indexing="xy")
+    Fs = sw.predictF(_M, Rg, Tg)
+    assert np.allclose(Fs, z["predictF"], rtol=2e-5, atol=0), float(np.abs(Fs / z["predictF"] - 1).max())
     eng.close()
 
 

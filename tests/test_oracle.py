@@ -185,6 +185,14 @@ def test_oracle_matches_the_reference_source_executed_on_a_jax_shim(path):
     assert np.allclose(info.numpy(), z["loss_info"], rtol=1e-10, atol=0) and abs(float(loss_n) / float(z["loss_n"]) - 1) < 1e-10
     g, _ = O.loss_and_grad(lossf, params, data)
     assert rel_err(O.ravel_params(g).numpy(), O.ravel_params(grads).numpy()) < 1e-10
+    # the closure tfp's L-BFGS evaluates (software.py:464-496): UN-normalised value, gradient of loss / lref
+    fl = O.lbfgs_function(lossf, params, data)
+    v, g1d = fl(O.ravel_params(params))
+    assert abs(float(v) / float(z["lbfgs_value"]) - 1) < 1e-10 and rel_err(g1d.numpy(), z["lbfgs_grad"]) < 1e-10
+    assert abs(float(z["lbfgs_value"]) - float(z["loss_info"][0])) == 0.0       # the reference returns loss_info[0], not loss_n
+    # predictF (software.py:608-623) with the reference's gaussian2D_smooth (software.py:71-83)
+    Rg, Tg = torch.meshgrid(torch.tensor(z["grid_r"]), torch.tensor(z["grid_t"]), indexing="xy")
+    assert np.allclose(O.predictF(f_u, params, Rg, Tg), z["predictF"], rtol=1e-9, atol=0)
     # stage 2 (software.py:221-234)
     f_comb = O.mNN_pred_create(fz, limit, 2.0 * scl, 0.1 * epsil, act_s=1)
     assert np.allclose(f_comb(params2, x_col).numpy(), z["u_stage2"], **tol)

@@ -1,6 +1,7 @@
 """CPU-only tests of the host side: the C-ABI library loads and exports every symbol
 include/pinn_engine.h declares (no compute calls), there is NO CPU fallback, the Adam
 schedule of software.py:396-460 is reproduced event for event, samplers and sharding."""
+import json
 import os
 import re
 
@@ -196,6 +197,68 @@ def test_adam_schedule_samples_the_next_set_while_the_steps_run(capsys):
     assert np.array_equal(np.array(l0)[:, 0], np.array(l1)[:, 0])
     begins = [c for c in m1.engine.calls if c[0] == "begin"]
     assert sum(c[1] for c in begins) >= 2100
+
+
+def _synthetic_row(t, n_info=6):   # the loss sequence of tests/golden/gen_reference_schedule_golden.py
+    base = 1.0 / (1.0 + 1e-3 * min(t, 4200)) + 0.02 * np.sin(0.37 * t)
+    if t >= 12000:
+        base += 2e-5 * (t - 12000)
+    return np.array([base, 0.6 * base, 0.4 * base] + [base / (k + 2) for k in range(n_info - 3)])
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_schedule.json"))),
+                         ids=lambda c: f"epoch{c['epoch']}")
+def test_adam_schedule_equals_the_reference_loop_body(case, capsys):
+    """tests/golden/reference_schedule.json holds the events of the REFERENCE'S OWN Adam loop (software.py:396-460, lifted
+    with ast and run on recording stand-ins, gen_reference_schedule_golden.py) for a fixed synthetic loss sequence: when it
+    re-samples, when it calls predictF, which learning rate and which collocation set every step uses, how long the tail
+    loop runs, every line it logs.  The B200 driver must produce the same events from the same loss sequence."""
+    ev = {"resample_at": [], "predictF_at": [], "lr_runs": [], "data_id_runs": []}
+    st = {"t": 0, "data_id": 0, "cur": None}
+
+    class Eng:
+        n_info = 6
+
+        def adam_init(self):
+            pass
+
+        def adam_steps(self, n, lr, want_rows=True):
+            rows = np.empty((n, 6))
+            for i in range(n):
+                t = st["t"]
+                if not ev["lr_runs"] or ev["lr_runs"][-1][1] != lr:
+                    ev["lr_runs"].append([t, lr])
+                if not ev["data_id_runs"] or ev["data_id_runs"][-1][1] != st["cur"]:
+                    ev["data_id_runs"].append([t, st["cur"]])
+                rows[i] = _synthetic_row(t)
+                st["t"] = t + 1
+            return rows
+
+    class Mdl:
+        engine = Eng()
+
+        def set_data(self, data):
+            st["cur"] = data
+
+        def predict(self, zs, want_jets=False):
+            ev["predictF_at"].append(st["t"])
+            return np.zeros(len(zs), np.float32), np.ones(len(zs), np.float32), None
+
+    def dataf(key, F, R, T):
+        st["data_id"] += 1
+        ev["resample_at"].append(st["t"])
+        return st["data_id"]
+
+    dataf.R, dataf.T = np.zeros((3, 3)), np.zeros((3, 3))
+    loss = sw.adam_optimizer(dataf.R, dataf.T, Mdl(), dataf, np.ones((3, 3)), case["epoch"], sw.Key(0), lr=1e-3)
+    err = capsys.readouterr().err.splitlines()
+    assert st["t"] == case["n_steps"] and len(loss) == case["n_rows"]
+    assert ev["resample_at"] == case["resample_at"]
+    assert ev["predictF_at"] == case["predictF_at"]
+    assert ev["lr_runs"] == case["lr_runs"]
+    assert ev["data_id_runs"] == case["data_id_runs"]
+    assert abs(float(np.sum(np.array(loss)[:, 0])) - case["loss0_checksum"]) < 1e-9 * abs(case["loss0_checksum"])
+    assert err == case["stderr"]
 
 
 def test_equation_front_end_never_raises_for_ui_input():

@@ -199,6 +199,46 @@ def test_adam_schedule_samples_the_next_set_while_the_steps_run(capsys):
     assert sum(c[1] for c in begins) >= 2100
 
 
+def test_samplers_equal_the_reference_source_on_the_same_random_table(monkeypatch):
+    """tests/golden/reference_sampling.npz: the reference's own colloc2D_set (software.py:87-136) and data_func_create /
+    dataf (software.py:521-577), lifted with ast and run on numpy with the random draws taken from a reproducible table
+    (gen_reference_sampling_golden.py).  The driver's samplers get the SAME table -- a fake Key whose children have the
+    ids 10 k + i and draw RandomState(id).uniform, a patched lhs -- and must return identical arrays: the LHS interior
+    points, the border-ring points, the boundary groups joined into the collocation set, the residual-adaptive points."""
+    from tests.golden.gen_reference_sampling_golden import BOUNDARY, DOMAIN, N_BD, N_COL, ROOT_KEY, LhsTable, table_uniform
+
+    class FakeKey:
+        def __init__(self, kid):
+            self.kid = kid
+
+        def split(self, num=2):
+            return [FakeKey(10 * self.kid + i) for i in range(num)]
+
+        def rng(self):
+            kid = self.kid
+
+            class G:
+                @staticmethod
+                def uniform(size):
+                    return table_uniform(kid, (size,) if np.isscalar(size) else size)
+
+            return G
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_sampling.npz"))
+    pts = sw.colloc2D_set(FakeKey(31), z["cs_X"], z["cs_Y"], z["cs_W"], 257)
+    assert np.array_equal(pts, z["cs_pts"])
+    table = LhsTable()
+    monkeypatch.setattr(sw, "lhs", table)
+    dataf = sw.data_func_create(N_COL, N_BD, BOUNDARY, DOMAIN, sampler="host")
+    assert np.array_equal(dataf.R, z["R"]) and np.array_equal(dataf.T, z["T"])
+    data = dataf(FakeKey(ROOT_KEY), z["F"], dataf.R, dataf.T)
+    assert table.calls == int(z["lhs_calls"])
+    assert data["x_col"].shape == z["x_col"].shape and np.allclose(data["x_col"], z["x_col"], rtol=0, atol=1e-15)
+    for i in range(2):
+        assert np.allclose(data["cond_bd"][0][i], z[f"x_bd{i}"], rtol=0, atol=1e-15)
+        assert np.array_equal(np.asarray(data["cond_bd"][1][i]), z[f"u_bd{i}"])
+
+
 def _synthetic_row(t, n_info=6):   # the loss sequence of tests/golden/gen_reference_schedule_golden.py
     base = 1.0 / (1.0 + 1e-3 * min(t, 4200)) + 0.02 * np.sin(0.37 * t)
     if t >= 12000:

@@ -239,6 +239,102 @@ def test_samplers_equal_the_reference_source_on_the_same_random_table(monkeypatc
         assert np.array_equal(np.asarray(data["cond_bd"][1][i]), z[f"u_bd{i}"])
 
 
+def test_run_pinn_training_equals_the_reference_body_on_a_synthetic_world(tmp_path, monkeypatch, capsys):
+    """tests/golden/reference_training.npz: the REFERENCE'S OWN run_pinn_training body (software.py:626-1139, lifted with ast)
+    executed on the stand-ins of tests/golden/training_world.py -- no training, but everything the function DERIVES: the 11
+    result files with their key names and contents, the stage-2 network (6x50, sin first layer), its scl / epsil / loss
+    weight computed from the stage-1 residual and error, the doubled sampling sizes, the tripled epoch counts, the loss
+    reference taken from the first evaluation.  The B200 driver runs on the same stand-ins and must derive the same."""
+    import types
+
+    from tests.golden import training_world as W
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_training.npz"))
+    rec = {}
+
+    class FakeModel:
+        def __init__(self, net, eq, n_bc, lw_eqn, device=0, base=None):
+            self.stage, self.version, self.ref = (1 if base is None else 2), 0, 1.0
+            rec[f"init{self.stage}"] = [net.n_hidden, net.width]
+            rec[f"pred{self.stage}"] = [net.scl, net.epsil, net.act_first]
+            rec[f"lw{self.stage}"] = lw_eqn
+            assert n_bc == 2 and net.feature_map == "polar" and list(net.lb) == [0.1, 0.0] and list(net.ub) == [1.0, 1.0]
+            self.engine = types.SimpleNamespace(set_params=lambda p: None)
+
+        def set_data(self, data):
+            pass
+
+        def set_ref(self, ref):
+            self.ref = float(ref)
+
+        def loss_info(self):
+            return np.array([W.initial_loss(self.stage)] + [0.0] * (W.N_INFO - 1))
+
+        def predict(self, z, want_jets=False):
+            u = W.u_field(self.stage, self.version, z)
+            return u[:, 0], W.residual_of(u, z)[:, 0], None
+
+        def close(self):
+            pass
+
+    def fake_adam(Rg, Tg, model, dataf, Fg, epoch, key, lr=1e-3):
+        rec[f"adam{model.stage}"] = [epoch, lr, model.ref]
+        model.version += 1
+        return W.loss_rows(model.stage, "adam", epoch)
+
+    def fake_lbfgs(model, epoch, *a, **k):
+        rec[f"lbfgs{model.stage}"] = [epoch]
+        model.version += 1
+        return W.loss_rows(model.stage, "lbfgs", int(epoch / 3)), None
+
+    n_df = {"n": 0}
+
+    def fake_data_func_create(N_col, N_bd, boundary, domain, **kw):
+        n_df["n"] += 1
+        stage, calls = n_df["n"], {"n": 0}
+        rec[f"dataf{stage}"] = [float(v) for v in np.asarray(N_col)] + [float(N_bd)]
+
+        def dataf(key, F, R_add, T_add):
+            calls["n"] += 1
+            n = int(np.sum(np.asarray(N_col))) + 2 * int(N_bd)
+            return {"x_col": W.sampled_points(stage, calls["n"], n), "cond_bd": [[None, None], [None, None]]}
+
+        dataf.R, dataf.T = np.meshgrid(np.linspace(domain["x_min"], domain["x_max"], 111), np.linspace(domain["y_min"], domain["y_max"], 111))
+        return dataf
+
+    monkeypatch.setattr(sw, "Model", FakeModel)
+    monkeypatch.setattr(sw, "adam_optimizer", fake_adam)
+    monkeypatch.setattr(sw, "lbfgs_optimizer", fake_lbfgs)
+    monkeypatch.setattr(sw, "predictF", lambda model, R, T: W.weight_map(model.version, np.asarray(R).shape))
+    monkeypatch.setattr(sw, "data_func_create", fake_data_func_create)
+    monkeypatch.setattr(sw, "init_params", lambda net, seed=0: np.zeros(1, np.float32))
+    sw.run_pinn_training(**W.KW, output_dir=str(tmp_path), sampler="host")
+    capsys.readouterr()
+    # ---- the 11 files: names, keys, contents
+    want = {}
+    for k in gold.files:
+        if k.startswith("file:"):
+            _, fname, key = k.split(":")
+            want.setdefault(fname, {})[key] = gold[k]
+    assert sorted(os.listdir(tmp_path)) == sorted(want)
+    for fname, keys in want.items():
+        z = np.load(tmp_path / fname)
+        assert sorted(z.files) == sorted(keys), (fname, z.files)
+        for key, ref in keys.items():
+            got = np.asarray(z[key], dtype=np.float64)
+            assert got.shape == ref.shape, (fname, key, got.shape, ref.shape)
+            assert np.allclose(got, ref, rtol=1e-9, atol=1e-12), (fname, key, float(np.abs(got - ref).max()))
+    # ---- what the orchestration derived and passed on
+    call = lambda k: gold[f"call:{k}"]
+    for stage in (1, 2):
+        assert rec[f"init{stage}"] == list(call(f"init{stage}"))                        # [hidden layers, units] (sw:695, 941-942)
+        assert np.allclose(rec[f"pred{stage}"], call(f"pred{stage}"), rtol=1e-9)        # scl, epsil, first-layer activation
+        assert np.isclose(rec[f"lw{stage}"], call(f"lw{stage}")[0], rtol=1e-9)          # weight of the equation term
+        assert rec[f"dataf{stage}"] == list(call(f"dataf{stage}"))                      # N_col (x2 in stage 2), N_bd (x2)
+        assert np.allclose(rec[f"adam{stage}"], call(f"adam{stage}"), rtol=1e-12)       # epochs (x3), lr, NN_loss.ref
+        assert rec[f"lbfgs{stage}"] == list(call(f"lbfgs{stage}"))
+
+
 def _synthetic_row(t, n_info=6):   # the loss sequence of tests/golden/gen_reference_schedule_golden.py
     base = 1.0 / (1.0 + 1e-3 * min(t, 4200)) + 0.02 * np.sin(0.37 * t)
     if t >= 12000:

@@ -335,6 +335,33 @@ def test_run_pinn_training_equals_the_reference_body_on_a_synthetic_world(tmp_pa
         assert rec[f"lbfgs{stage}"] == list(call(f"lbfgs{stage}"))
 
 
+@pytest.mark.parametrize("case", json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_lbfgs_wrapper.json"))),
+                         ids=lambda c: f"epoch{c['epoch']}")
+def test_lbfgs_wrapper_equals_the_reference_source(case, capsys):
+    """tests/golden/reference_lbfgs_wrapper.json: the reference's own lbfgs_optimizer / lbfgs_function (software.py:464-514,
+    lifted with ast) around a RECORDING tfp.optimizer.lbfgs_minimize: iteration cap int32(epoch / 3), tolerance 1e-10, the
+    closure returning the UN-normalised loss_info[0], one loss row and one 'Step: NaN' line per objective evaluation,
+    ' Total iterations:' printing the number of evaluations.  The driver's wrapper must hand the engine the same."""
+    got = {}
+    rows_ref = np.array(case["loss_rows"])
+
+    class Eng:
+        def lbfgs(self, max_iter, tol, value_unnormalised, on_eval):
+            got.update(max_iter=max_iter, tol=tol, value_unnormalised=value_unnormalised)
+            for r in rows_ref:
+                on_eval(r)
+            return {"evaluations": len(rows_ref), "iterations": 0, "converged": False, "failed": False, "final_loss": float(rows_ref[-1, 0])}, rows_ref
+
+    class Mdl:
+        engine = Eng()
+
+    rows, res = sw.lbfgs_optimizer(Mdl(), case["epoch"])
+    out = capsys.readouterr().out.splitlines()
+    assert got["max_iter"] == case["max_iterations"] and got["tol"] == case["tolerance"] and got["value_unnormalised"] is True
+    assert [v for v, _ in case["closure_returns"]] == [r[0] for r in case["loss_rows"]]     # the reference returns loss_info[0]
+    assert len(rows) == case["n_loss_rows"] and out == case["stdout"]
+
+
 def _synthetic_row(t, n_info=6):   # the loss sequence of tests/golden/gen_reference_schedule_golden.py
     base = 1.0 / (1.0 + 1e-3 * min(t, 4200)) + 0.02 * np.sin(0.37 * t)
     if t >= 12000:

@@ -362,6 +362,22 @@ def test_lbfgs_wrapper_equals_the_reference_source(case, capsys):
     assert len(rows) == case["n_loss_rows"] and out == case["stdout"]
 
 
+def test_signature_matches_the_reference_call_site():
+    """tests/golden/reference_call_site.json: the keyword names the Dash callback passes (pinn_app/callbacks/training.py,
+    the run_pinn_training(...) call inside the daemon-thread target) and the reference function's own parameter list
+    (software.py:626-638), both read from the reference source with ast.  The drop-in takes exactly these, in this order,
+    as its leading parameters; everything it adds is keyword-only with a default."""
+    import inspect
+
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_call_site.json")))
+    assert ref["call_site_keywords"] == ref["parameters"]
+    sig = inspect.signature(sw.run_pinn_training)
+    lead = [p.name for p in sig.parameters.values() if p.kind is inspect.Parameter.POSITIONAL_OR_KEYWORD]
+    assert lead == ref["parameters"]
+    extras = [p for p in sig.parameters.values() if p.kind is not inspect.Parameter.POSITIONAL_OR_KEYWORD]
+    assert extras and all(p.kind is inspect.Parameter.KEYWORD_ONLY and p.default is not inspect.Parameter.empty for p in extras)
+
+
 def _synthetic_row(t, n_info=6):   # the loss sequence of tests/golden/gen_reference_schedule_golden.py
     base = 1.0 / (1.0 + 1e-3 * min(t, 4200)) + 0.02 * np.sin(0.37 * t)
     if t >= 12000:

@@ -377,6 +377,8 @@ static int create_impl(pinn_engine* h, const pinn_spec_t* spec, int device) {
     // token-ordered, bit-reproducible flush (jet_tc_kernel.cuh).  PINN_TC_SHARE overrides (1 = private rows).
     h->tc_share = (h->net.wp == 256) ? 4 : 1;
     if (const char* e = getenv("PINN_TC_SHARE")) h->tc_share = (h->net.wp == 256) ? std::max(1, std::min(8, atoi(e))) : 1;
+    int coop = 0;   // the members of a row wait for each other: only with a cooperative launch (all CTAs resident)
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device) != cudaSuccess || !coop) { cudaGetLastError(); h->tc_share = 1; }
     if (h->tc_share > 1) {
       const size_t rows = (size_t)(h->grid_max_col + h->tc_share - 1) / h->tc_share;
       CK(cudaMalloc(&h->d_tokens, sizeof(unsigned) * rows * PINN_TOKENS));

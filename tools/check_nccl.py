@@ -32,6 +32,9 @@ eng.set_loss(1.0, 2.0)
 g, info = eng.loss_grad()
 eng.adam_init()
 rows = eng.adam_steps(5, 1e-3)
+# L-BFGS on the sharded problem: gradient and loss sums allreduced per evaluation, the two-loop recursion and the line
+# search run replicated on identical numbers (no further collective)
+res_lb, rows_lb = eng.lbfgs(15, 1e-12)
 p = torch.as_tensor(eng.get_params()).cuda()
 # replicas stay bit-identical
 pl = [torch.empty_like(p) for _ in range(world)]
@@ -45,6 +48,11 @@ if rank == 0:
     g1, info1 = ref.loss_grad()
     ref.adam_init()
     rows1 = ref.adam_steps(5, 1e-3)
+    res1, rows_lb1 = ref.lbfgs(15, 1e-12)
+    lb_rel = abs(res_lb["final_loss"] / res1["final_loss"] - 1)
+    print(f"world={world} L-BFGS: {res_lb['iterations']} iterations / {res_lb['evaluations']} evaluations, final loss {res_lb['final_loss']:.6e} "
+          f"(single GPU: {res1['iterations']} / {res1['evaluations']}, {res1['final_loss']:.6e}, rel {lb_rel:.2e}), mode syncs {eng.lbfgs_host_syncs()}")
+    assert lb_rel < 5e-3 and res_lb["final_loss"] < rows[-1, 0]
     rel = float((g - g1).norm() / g1.norm())
     print(f"world={world} grad rel err vs single GPU: {rel:.3e}; loss_info rel: {np.abs(info / info1 - 1).max():.3e}; "
           f"adam loss rows rel: {np.abs(rows[:, 0] / rows1[:, 0] - 1).max():.3e}; replicas identical: {same}")
